@@ -1,0 +1,233 @@
+"""genomicsbench_b200 -- B200-native banded Smith-Waterman extension (GenomicsBench `bsw`).
+
+Host-side mirror of the reference operator interface (benchmarks/bsw/bandedSWA.h:114-342):
+`BandedPairWiseSW` with the reference's constructor arguments and `getScores16` /
+`getScores8` / `scalarBandedSWAWrapper` methods, over numpy views of the reference's
+`SeqPair` records.  Everything is a thin ctypes call into libbsw_b200.so (CUDA, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from ._lib import (ABI, BSW_ZDROP_SCALAR, BSW_ZDROP_VECTOR, RESULT_FIELDS, SEQPAIR_DTYPE, BswGenConfig,
+                   BswParams, BswStats, LIB_PATH, load_library, ptr)
+
+__all__ = [
+    "BandedPairWiseSW", "Engine", "BswError", "SEQPAIR_DTYPE", "RESULT_FIELDS", "default_params",
+    "gen_named_config", "gen_pairs", "bucket_order", "partition", "read_pairs_file",
+    "write_pairs_file", "load_library", "NAMED_CONFIGS",
+]
+
+NAMED_CONFIGS = {"small": 0, "short8": 1, "long16": 2, "large": 3, "sweep": 4}
+
+
+class BswError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"bsw error {code}: {msg}")
+        self.code = code
+
+
+def default_params(**over) -> BswParams:
+    p = BswParams()
+    load_library().bsw_default_params(C.byref(p))
+    for k, v in over.items():
+        if k == "devices":
+            p.n_devices = len(v)
+            for i, d in enumerate(v):
+                p.devices[i] = int(d)
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def _check_arrays(pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray):
+    if pairs.dtype != SEQPAIR_DTYPE or not pairs.flags.c_contiguous:
+        raise TypeError("pairs must be a C-contiguous array of SEQPAIR_DTYPE")
+    for a in (seq_ref, seq_qer):
+        if a.dtype != np.uint8 or not a.flags.c_contiguous:
+            raise TypeError("sequence buffers must be C-contiguous uint8 arrays")
+
+
+class Engine:
+    """Owns one bsw_engine (C ABI).  One instance may drive several GPUs of the box."""
+
+    def __init__(self, params: Optional[BswParams] = None, **over):
+        self._lib = load_library()
+        self._h = None
+        p = params if params is not None else default_params(**over)
+        err = C.c_int(0)
+        h = self._lib.bsw_create(C.byref(p), C.byref(err))
+        if not h:
+            raise BswError(err.value, self._lib.bsw_last_error(None).decode())
+        self._h = h
+        self.params = p
+
+    def close(self):
+        if self._h:
+            self._lib.bsw_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _rc(self, rc: int):
+        if rc != 0:
+            raise BswError(rc, self._lib.bsw_last_error(self._h).decode())
+
+    def extend(self, pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray, w: int) -> None:
+        _check_arrays(pairs, seq_ref, seq_qer)
+        self._rc(self._lib.bsw_extend(self._h, ptr(pairs), ptr(seq_ref), ptr(seq_qer), len(pairs), w))
+
+    def stage(self, pairs, seq_ref, seq_qer, w: int) -> None:
+        _check_arrays(pairs, seq_ref, seq_qer)
+        self._rc(self._lib.bsw_stage(self._h, ptr(pairs), ptr(seq_ref), ptr(seq_qer), len(pairs), w))
+
+    def run_staged(self) -> None:
+        self._rc(self._lib.bsw_run_staged(self._h))
+
+    def fetch(self, pairs: np.ndarray) -> None:
+        self._rc(self._lib.bsw_fetch(self._h, ptr(pairs), len(pairs)))
+
+    def stats(self) -> dict:
+        s = BswStats()
+        self._rc(self._lib.bsw_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def measure_int_peak(self) -> float:
+        return float(self._lib.bsw_measure_int_peak(self._h))
+
+
+class BandedPairWiseSW:
+    """Mirror of the reference class (bandedSWA.h:114-342, ctor bandedSWA.cpp:51-100).
+
+    Same argument order and meaning as the C++ constructor; `mat` is accepted for
+    signature parity (the vector path ignores it, exactly like the reference,
+    bandedSWA.cpp:69)."""
+
+    def __init__(self, o_del: int, e_del: int, o_ins: int, e_ins: int, zdrop: int, end_bonus: int,
+                 mat: Optional[Sequence[int]], w_match: int, w_mismatch: int, numThreads: int = 1,
+                 devices: Optional[Sequence[int]] = None):
+        self._kw = dict(o_del=o_del, e_del=e_del, o_ins=o_ins, e_ins=e_ins, zdrop=zdrop,
+                        end_bonus=end_bonus, match=w_match, mismatch=w_mismatch)
+        if devices is not None:
+            self._kw["devices"] = list(devices)
+        self._mat = None if mat is None else [int(x) for x in mat]
+        self._vec: Optional[Engine] = None
+        self._scalar: Optional[Engine] = None
+        self.SW_cells = 0
+        self.last_stats: dict = {}
+
+    def _engine(self, scalar: bool) -> Engine:
+        if scalar:
+            if self._scalar is None:
+                kw = dict(self._kw, zdrop_mode=BSW_ZDROP_SCALAR)
+                if self._mat is not None:
+                    kw["ambig"] = self._mat[4]
+                self._scalar = Engine(**kw)
+            return self._scalar
+        if self._vec is None:
+            self._vec = Engine(**dict(self._kw, zdrop_mode=BSW_ZDROP_VECTOR))
+        return self._vec
+
+    def _run(self, scalar, pairs, seq_ref, seq_qer, numPairs, w):
+        eng = self._engine(scalar)
+        eng.extend(pairs[:numPairs], seq_ref, seq_qer, w)
+        self.last_stats = eng.stats()
+        self.SW_cells += self.last_stats["cells_effective"]
+
+    def getScores16(self, pairArray, seqBufRef, seqBufQer, numPairs, numThreads, w):
+        self._run(False, pairArray, seqBufRef, seqBufQer, numPairs, w)
+
+    def getScores8(self, pairArray, seqBufRef, seqBufQer, numPairs, numThreads, w):
+        self._run(False, pairArray, seqBufRef, seqBufQer, numPairs, w)
+
+    def scalarBandedSWAWrapper(self, seqPairArray, seqBufRef, seqBufQer, numPairs, nthreads, w):
+        self._run(True, seqPairArray, seqBufRef, seqBufQer, numPairs, w)
+
+    def close(self):
+        for e in (self._vec, self._scalar):
+            if e is not None:
+                e.close()
+        self._vec = self._scalar = None
+
+
+# ---------------------------------------------------------------------------------------
+# host utilities (no GPU needed)
+# ---------------------------------------------------------------------------------------
+def gen_named_config(which) -> BswGenConfig:
+    idx = NAMED_CONFIGS[which] if isinstance(which, str) else int(which)
+    cfg = BswGenConfig()
+    rc = load_library().bsw_gen_named_config(idx, C.byref(cfg))
+    if rc:
+        raise BswError(rc, "unknown named config")
+    return cfg
+
+
+def gen_pairs(cfg: BswGenConfig, first: int = 0, n: Optional[int] = None):
+    """Returns (pairs, seq_ref, seq_qer) for pairs [first, first+n) of the config's stream."""
+    lib = load_library()
+    n = int(cfg.n_pairs if n is None else n)
+    sub = BswGenConfig.from_buffer_copy(cfg)
+    sub.n_pairs = n
+    rb, qb = C.c_int64(0), C.c_int64(0)
+    rc = lib.bsw_gen_bounds(C.byref(sub), C.byref(rb), C.byref(qb))
+    if rc:
+        raise BswError(rc, "bad generator config")
+    pairs = np.zeros(n, dtype=SEQPAIR_DTYPE)
+    ref = np.empty(rb.value, dtype=np.uint8)
+    qer = np.empty(qb.value, dtype=np.uint8)
+    ru, qu = C.c_int64(0), C.c_int64(0)
+    rc = lib.bsw_gen_pairs(C.byref(cfg), first, n, ptr(pairs), ptr(ref), ptr(qer), C.byref(ru), C.byref(qu))
+    if rc:
+        raise BswError(rc, "generator failed")
+    return pairs, ref[: ru.value + 64], qer[: qu.value + 64]
+
+
+def bucket_order(pairs: np.ndarray) -> np.ndarray:
+    order = np.empty(len(pairs), dtype=np.int64)
+    rc = load_library().bsw_bucket_order(ptr(pairs), len(pairs), ptr(order))
+    if rc:
+        raise BswError(rc, "bucket_order")
+    return order
+
+
+def partition(pairs: np.ndarray, w: int, n_shards: int):
+    order = np.empty(len(pairs), dtype=np.int64)
+    begin = np.zeros(n_shards + 1, dtype=np.int64)
+    rc = load_library().bsw_partition(ptr(pairs), len(pairs), w, n_shards, ptr(order), ptr(begin))
+    if rc:
+        raise BswError(rc, "partition")
+    return order, begin
+
+
+def read_pairs_file(path: str, max_pairs: Optional[int] = None):
+    lib = load_library()
+    n = lib.bsw_count_pairs_file(path.encode())
+    if n < 0:
+        raise BswError(int(n), f"cannot read {path}")
+    if max_pairs is not None:
+        n = min(n, max_pairs)
+    import os
+    cap = os.path.getsize(path) + 64
+    pairs = np.zeros(n, dtype=SEQPAIR_DTYPE)
+    ref = np.zeros(cap, dtype=np.uint8)
+    qer = np.zeros(cap, dtype=np.uint8)
+    got = C.c_int64(0)
+    rc = lib.bsw_read_pairs_file(path.encode(), n, ptr(pairs), ptr(ref), cap, ptr(qer), cap, C.byref(got))
+    if rc:
+        raise BswError(rc, f"parse error in {path}")
+    return pairs[: got.value], ref, qer
+
+
+def write_pairs_file(path: str, pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray) -> None:
+    rc = load_library().bsw_write_pairs_file(path.encode(), ptr(pairs), len(pairs), ptr(seq_ref), ptr(seq_qer))
+    if rc:
+        raise BswError(rc, f"cannot write {path}")

@@ -1,0 +1,120 @@
+"""ctypes binding of libbsw_b200.so -- the C ABI declared in include/bsw.h.
+
+Python is plumbing only (tests, bench.py, multi-process launch); all DP work happens in
+the CUDA library.  There is deliberately no Python or CPU implementation of the hot path:
+if the library (or a GPU) is missing, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "lib" / "libbsw_b200.so"
+
+# SeqPair, 72 bytes: benchmarks/bsw/bandedSWA.h:91-100
+SEQPAIR_DTYPE = np.dtype(
+    {
+        "names": ["idr", "idq", "id", "len1", "len2", "h0", "seqid", "regid",
+                  "score", "tle", "gtle", "qle", "gscore", "max_off"],
+        "formats": ["<i8", "<i8", "<i8"] + ["<i4"] * 11,
+        "offsets": [0, 8, 16, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64],
+        "itemsize": 72,
+    }
+)
+RESULT_FIELDS = ("score", "qle", "tle", "gtle", "gscore", "max_off")
+
+BSW_OK = 0
+BSW_ERR_PARAM, BSW_ERR_DOMAIN, BSW_ERR_CUDA, BSW_ERR_NOMEM, BSW_ERR_STATE, BSW_ERR_IO = -1, -2, -3, -4, -5, -6
+BSW_ZDROP_VECTOR, BSW_ZDROP_SCALAR = 0, 1
+
+
+class BswParams(C.Structure):
+    _fields_ = [
+        ("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32), ("e_ins", C.c_int32),
+        ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32),
+        ("ambig", C.c_int32), ("zdrop_mode", C.c_int32), ("n_devices", C.c_int32),
+        ("devices", C.c_int32 * 16), ("host_threads", C.c_int32), ("reserved", C.c_int32 * 8),
+    ]
+
+
+class BswStats(C.Structure):
+    _fields_ = [
+        ("pairs", C.c_int64), ("cells_nominal", C.c_int64), ("cells_effective", C.c_int64),
+        ("ms_sort", C.c_double), ("ms_pack", C.c_double), ("ms_h2d", C.c_double),
+        ("ms_kernel", C.c_double), ("ms_d2h", C.c_double), ("ms_scatter", C.c_double),
+        ("ms_total", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("kernel_launches", C.c_int32), ("n_short", C.c_int32), ("n_long", C.c_int32),
+        ("reserved", C.c_int32 * 5),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class BswGenConfig(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64), ("n_pairs", C.c_int64),
+        ("qlen_min", C.c_int32), ("qlen_max", C.c_int32),
+        ("tail_min", C.c_int32), ("tail_max", C.c_int32),
+        ("h0_min", C.c_int32), ("h0_max", C.c_int32),
+        ("max_len1", C.c_int32), ("max_score8", C.c_int32),
+        ("error_rate", C.c_double), ("n_rate", C.c_double),
+        ("match", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+# every symbol include/bsw.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+ABI = [
+    ("bsw_create", _P, [C.POINTER(BswParams), C.POINTER(C.c_int)]),
+    ("bsw_destroy", None, [_P]),
+    ("bsw_last_error", C.c_char_p, [_P]),
+    ("bsw_default_params", None, [C.POINTER(BswParams)]),
+    ("bsw_extend", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32]),
+    ("bsw_stage", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32]),
+    ("bsw_run_staged", C.c_int, [_P]),
+    ("bsw_fetch", C.c_int, [_P, _P, C.c_int64]),
+    ("bsw_get_stats", C.c_int, [_P, C.POINTER(BswStats)]),
+    ("bsw_bucket_order", C.c_int, [_P, C.c_int64, _P]),
+    ("bsw_partition", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    ("bsw_gen_named_config", C.c_int, [C.c_int32, C.POINTER(BswGenConfig)]),
+    ("bsw_gen_bounds", C.c_int, [C.POINTER(BswGenConfig), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("bsw_gen_pairs", C.c_int, [C.POINTER(BswGenConfig), C.c_int64, C.c_int64, _P, _P, _P,
+                                C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("bsw_count_pairs_file", C.c_int64, [C.c_char_p]),
+    ("bsw_read_pairs_file", C.c_int, [C.c_char_p, C.c_int64, _P, _P, C.c_int64, _P, C.c_int64,
+                                      C.POINTER(C.c_int64)]),
+    ("bsw_write_pairs_file", C.c_int, [C.c_char_p, _P, C.c_int64, _P, _P]),
+    ("bsw_measure_int_peak", C.c_double, [_P]),
+    ("bsw_version", C.c_char_p, []),
+]
+
+_lib = None
+
+
+def load_library(path: os.PathLike | None = None) -> C.CDLL:
+    """Loads libbsw_b200.so and types every exported entry point.  Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise RuntimeError(
+            f"{p} not found: build it with `python -m genomicsbench_b200.build` "
+            "(there is no Python/CPU fallback for the bsw hot path)")
+    lib = C.CDLL(str(p))
+    for name, restype, argtypes in ABI:
+        fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def ptr(a: np.ndarray) -> int:
+    return a.ctypes.data

@@ -1,0 +1,233 @@
+// bsw_kernels.cuh -- hand-written sm_100a kernels of the banded Smith-Waterman extension.
+//
+// Per-pair semantics: SURVEY.md Appendix A == BandedPairWiseSW::scalarBandedSWA
+// (benchmarks/bsw/bandedSWA.cpp:128-249; canonical twin tools/bwa/ksw.c:380-479) with the
+// z-drop rule of the vector kernel the benchmark runs (ZSCORE16, bandedSWA.cpp:323-336),
+// i.e. exactly what getScores16 (bandedSWA.cpp:1124-1148 -> smithWaterman256_16 :1433-1831)
+// returns for a pair run alone in its SIMD group.
+//
+// Two kernels replace the reference's 8-bit / 16-bit AVX dispatch:
+//   bsw_short_kernel  thread-per-pair (inter-sequence), the eh[] row lives in shared memory
+//                     as one packed word per cell, DPX (VIADDMNMX / VIMNMX3) recurrence.
+//   bsw_long_kernel   warp-per-pair row sweep: lanes own column strips of the band window,
+//                     __shfl_sync hands H / F between lanes, a 5-step max-plus scan resolves F.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bsw {
+
+struct KParams {
+    int match;          // +a
+    int mismatch_neg;   // -b
+    int ambig;          // score of any cell touching an N
+    int o_del, e_del, o_ins, e_ins;
+    int oe_del, oe_ins;
+    int zdrop, end_bonus;
+    int zmode;          // BSW_ZDROP_VECTOR / BSW_ZDROP_SCALAR
+    int mx;             // max entry of the scoring matrix (band clamp, bandedSWA.cpp:160-168)
+    int w;              // caller's band width
+};
+
+// Packed shared-memory cell of the short kernel:  [31:17] e   [16:15] query base   [14:0] h
+// (h, e < 32768 is the reference's own 16-bit domain, bandedSWA.h:84 / Q7.)
+#define BSW_QSHIFT 15
+#define BSW_QMASK  0x18000u
+#define BSW_HMASK  0x7fffu
+#define BSW_ESHIFT 17
+
+// band clamp of bandedSWA.cpp:160-168, same double arithmetic
+__device__ __forceinline__ int bsw_clamp_band(const KParams& P, int qlen)
+{
+    int w = P.w;
+    int max_ins = (int)((double)(qlen * P.mx + P.end_bonus - P.o_ins) / P.e_ins + 1.);
+    max_ins = max_ins > 1 ? max_ins : 1;
+    w = w < max_ins ? w : max_ins;
+    int max_del = (int)((double)(qlen * P.mx + P.end_bonus - P.o_del) / P.e_del + 1.);
+    max_del = max_del > 1 ? max_del : 1;
+    w = w < max_del ? w : max_del;
+    return w;
+}
+
+// Running per-pair state shared by both kernels' row epilogues.
+struct PairState {
+    int max, max_i, max_j, max_ie, gscore, max_off;
+};
+
+// Row epilogue: global max / max_off / z-drop (bandedSWA.cpp:218-228, :323-336).
+// Returns true when the row loop must stop.
+__device__ __forceinline__ bool bsw_row_update(const KParams& P, PairState& st, int i, int m, int mj)
+{
+    if (m == 0) return true;
+    if (m > st.max) {
+        st.max = m; st.max_i = i; st.max_j = mj;
+        int d = mj - i; d = d < 0 ? -d : d;
+        st.max_off = st.max_off > d ? st.max_off : d;
+        return false;
+    }
+    const int di = i - st.max_i, dj = mj - st.max_j;
+    if (P.zmode == 0) {
+        const int gap = di > dj ? di - dj : dj - di;
+        return st.max - m - gap > P.zdrop;
+    }
+    if (P.zdrop > 0) {
+        if (di > dj) return st.max - m - (di - dj) * P.e_del > P.zdrop;
+        return st.max - m - (dj - di) * P.e_ins > P.zdrop;
+    }
+    return false;
+}
+
+__device__ __forceinline__ int4 bsw_pack_result(const PairState& st)
+{
+    // 8 x int16: score, qle, tle, gtle, gscore, max_off, 0, 0
+    int4 r;
+    r.x = (st.max & 0xffff) | ((st.max_j + 1) << 16);
+    r.y = ((st.max_i + 1) & 0xffff) | ((st.max_ie + 1) << 16);
+    r.z = (st.gscore & 0xffff) | (st.max_off << 16);
+    r.w = 0;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Short-pair kernel: one pair per thread.
+//   meta[s] = {query word/byte offset, target word/byte offset, qlen | tlen << 16, h0}
+//   BYTESEQ = false: sequences are 2-bit packed, 16 bases per 32-bit word, word-aligned.
+//   BYTESEQ = true : one base code per byte (pairs that contain N, code 4).
+//   eh[j * BLOCK + tid] is thread tid's cell j (bank == tid: conflict-free for any j).
+// ---------------------------------------------------------------------------------------
+template <int BLOCK, bool BYTESEQ>
+__global__ void __launch_bounds__(BLOCK)
+bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qseq,
+                 const uint32_t* __restrict__ tseq, int4* __restrict__ res,
+                 const int* __restrict__ respos,
+                 int first, int count, const __grid_constant__ KParams P,
+                 unsigned long long* __restrict__ cell_counter)
+{
+    extern __shared__ uint32_t eh_smem[];
+    const int tid = threadIdx.x;
+    const int local = blockIdx.x * BLOCK + tid;
+    long long my_cells = 0;
+    if (local < count) {
+        const int s = first + local;
+        const int4 md = meta[s];
+        const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w;
+        uint32_t* const eh = eh_smem + tid;
+        const uint8_t* qb = reinterpret_cast<const uint8_t*>(qseq) + (BYTESEQ ? (uint32_t)md.x : 0u);
+        const uint8_t* tb = reinterpret_cast<const uint8_t*>(tseq) + (BYTESEQ ? (uint32_t)md.y : 0u);
+        const uint32_t* qw = qseq + (BYTESEQ ? 0u : (uint32_t)md.x);
+        const uint32_t* tw = tseq + (BYTESEQ ? 0u : (uint32_t)md.y);
+
+        // ---- first row (bandedSWA.cpp:155-157) with the query base folded into each cell
+        {
+            int hv = h0;
+            uint32_t qword = 0;
+            for (int j = 0; j <= qlen; ++j) {
+                uint32_t qbits = 0;
+                if (!BYTESEQ) {
+                    if ((j & 15) == 0 && j < qlen) qword = __ldg(qw + (j >> 4));
+                    qbits = (qword >> ((j & 15) * 2)) & 3u;
+                    if (j >= qlen) qbits = 0;
+                }
+                if (j == 1) hv = h0 > P.oe_ins ? h0 - P.oe_ins : 0;
+                else if (j >= 2) hv = hv > P.e_ins ? hv - P.e_ins : 0;
+                eh[j * BLOCK] = (uint32_t)hv | (qbits << BSW_QSHIFT);
+            }
+        }
+        const int w = bsw_clamp_band(P, qlen);
+
+        PairState st;
+        st.max = h0; st.max_i = -1; st.max_j = -1; st.max_ie = -1; st.gscore = -1; st.max_off = 0;
+        int beg = 0, end = qlen;
+        uint32_t tword = 0;
+        const int neg_oe_del = -P.oe_del, neg_oe_ins = -P.oe_ins;
+
+        for (int i = 0; i < tlen; ++i) {
+            int ti;
+            if (BYTESEQ) ti = __ldg(tb + i);
+            else {
+                if ((i & 15) == 0) tword = __ldg(tw + (i >> 4));
+                ti = (tword >> ((i & 15) * 2)) & 3;
+            }
+            beg = max(beg, i - w);
+            end = min(min(end, i + w + 1), qlen);
+            int h1 = 0;
+            if (beg == 0) h1 = max(h0 - (P.o_del + P.e_del * (i + 1)), 0);
+            int f = 0;
+            int mkey = 0;                                    // (row max << 16) | argmax column
+            const uint32_t tmask = (uint32_t)ti << BSW_QSHIFT;
+            uint32_t* p = eh + beg * BLOCK;
+#pragma unroll 4
+            for (int j = beg; j < end; ++j) {
+                const uint32_t wd = *p;
+                const int Hd = (int)(wd & BSW_HMASK);
+                const int e = (int)(wd >> BSW_ESHIFT);
+                int s;
+                if (BYTESEQ) {
+                    const int qj = __ldg(qb + j);
+                    s = (qj > 3 || ti > 3) ? P.ambig : (qj == ti ? P.match : P.mismatch_neg);
+                } else {
+                    s = ((wd ^ tmask) & BSW_QMASK) ? P.mismatch_neg : P.match;
+                }
+                // M = Hd ? Hd + s : 0, clamped at 0 (a negative M is equivalent to 0 in every use)
+                const int M = __viaddmin_s32_relu(Hd, s, Hd << 16);
+                const int h = __vimax3_s32(M, e, f);
+                const int en = __viaddmax_s32_relu(M, neg_oe_del, e - P.e_del);
+                f = __viaddmax_s32_relu(M, neg_oe_ins, f - P.e_ins);
+                *p = (wd & BSW_QMASK) | (uint32_t)h1 | ((uint32_t)en << BSW_ESHIFT);
+                mkey = max(mkey, (h << 16) | j);
+                h1 = h;
+                p += BLOCK;
+            }
+            if (end > beg) my_cells += end - beg;
+            // eh[end] = {h1, 0}  (bandedSWA.cpp:213); keep the query bits of that cell
+            {
+                uint32_t* pe = eh + end * BLOCK;
+                *pe = (*pe & BSW_QMASK) | (uint32_t)h1;
+            }
+            const int jfin = end > beg ? end : beg;
+            if (jfin == qlen) {                               // bandedSWA.cpp:214-217
+                if (!(st.gscore > h1)) st.max_ie = i;
+                st.gscore = max(st.gscore, h1);
+            }
+            const int m = mkey >> 16, mj = mkey & 0xffff;
+            if (bsw_row_update(P, st, i, m, mj)) break;
+            // next row's window (bandedSWA.cpp:230-233)
+            {
+                int j = beg;
+                while (j < end && (eh[j * BLOCK] & ~BSW_QMASK) == 0) ++j;
+                beg = j;
+                j = end;
+                while (j >= beg && (eh[j * BLOCK] & ~BSW_QMASK) == 0) --j;
+                end = min(j + 2, qlen);
+            }
+        }
+        res[respos ? respos[s] : s] = bsw_pack_result(st);
+    }
+    // effective-cell statistic: one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) my_cells += __shfl_down_sync(0xffffffffu, my_cells, off);
+    if ((tid & 31) == 0 && my_cells) atomicAdd(cell_counter, (unsigned long long)my_cells);
+}
+
+// ---------------------------------------------------------------------------------------
+// Dependency-free DPX throughput probe: the roofline denominator P_int.
+// Each thread keeps 8 independent VIADDMNMX chains; ops = threads * iters * 8.
+// ---------------------------------------------------------------------------------------
+__global__ void bsw_int_peak_kernel(int* out, int iters, int seed)
+{
+    int a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    int a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const int b = seed | 1, c = seed - 7;
+#pragma unroll 1
+    for (int k = 0; k < iters; ++k) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = __viaddmax_s32(a0, b, c); a1 = __viaddmax_s32(a1, b, c);
+            a2 = __viaddmax_s32(a2, b, c); a3 = __viaddmax_s32(a3, b, c);
+            a4 = __viaddmax_s32(a4, b, c); a5 = __viaddmax_s32(a5, b, c);
+            a6 = __viaddmax_s32(a6, b, c); a7 = __viaddmax_s32(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+} // namespace bsw

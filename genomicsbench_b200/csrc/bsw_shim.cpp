@@ -1,0 +1,117 @@
+// bsw_shim.cpp -- BandedPairWiseSW (include/bandedSWA.h) on top of the C ABI.
+// Mirrors the constructor / method behaviour of benchmarks/bsw/bandedSWA.cpp:51-122,
+// :254-272, :424-446, :1124-1148.  No DP arithmetic lives here: every call is a bsw_extend().
+#include "../../include/bandedSWA.h"
+#include <cstring>
+#include <chrono>
+
+namespace {
+inline int64_t ticks_now()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    return (int64_t)__rdtsc();
+#else
+    return (int64_t)std::chrono::steady_clock::now().time_since_epoch().count();
+#endif
+}
+[[noreturn]] void die(const char* what, const char* detail)
+{
+    fprintf(stderr, "bsw_b200: %s: %s\n", what, detail ? detail : "");
+    exit(EXIT_FAILURE);                    // reference behaviour on failure, bandedSWA.cpp:94-99
+}
+} // namespace
+
+BandedPairWiseSW::BandedPairWiseSW(const int o_del, const int e_del, const int o_ins,
+                                   const int e_ins, const int zdrop,
+                                   const int end_bonus, const int8_t *mat_,
+                                   const int8_t w_match, const int8_t w_mismatch, int numThreads)
+    : SW_cells(0), mat(mat_), vec_(nullptr), scalar_(nullptr), ticks_(0)
+{
+    (void)numThreads;                      // scratch sizing in the reference (:85-92); nothing to size here
+    bsw_default_params(&params_);
+    params_.o_del = o_del; params_.e_del = e_del;
+    params_.o_ins = o_ins; params_.e_ins = e_ins;
+    params_.zdrop = zdrop; params_.end_bonus = end_bonus;
+    params_.match = w_match;
+    params_.mismatch = w_mismatch;         // positive penalty; the reference negates it at :66
+    params_.ambig = DEFAULT_AMBIG;         // vector code hard-wires -1 (:69) and ignores `mat`
+    memset(&stats_, 0, sizeof(stats_));
+}
+
+BandedPairWiseSW::~BandedPairWiseSW()
+{
+    bsw_destroy(vec_);
+    bsw_destroy(scalar_);
+}
+
+bsw_engine* BandedPairWiseSW::engine(int zdrop_mode)
+{
+    bsw_engine*& slot = zdrop_mode == BSW_ZDROP_SCALAR ? scalar_ : vec_;
+    if (slot) return slot;
+    bsw_params p = params_;
+    p.zdrop_mode = zdrop_mode;
+    if (zdrop_mode == BSW_ZDROP_SCALAR && mat) {
+        // the scalar code scores through `mat` (:148-152): accept the bwa_fill_scmat shape only
+        p.ambig = mat[4];
+        for (int i = 0; i < 5; ++i)
+            for (int j = 0; j < 5; ++j) {
+                const int expect = (i == 4 || j == 4) ? p.ambig : (i == j ? p.match : -p.mismatch);
+                if (mat[i * 5 + j] != expect)
+                    die("scoring matrix", "only matrices of the bwa_fill_scmat form (match / -mismatch / ambig) are supported");
+            }
+    }
+    int err = 0;
+    slot = bsw_create(&p, &err);
+    if (!slot) die("engine creation failed", bsw_last_error(nullptr));
+    return slot;
+}
+
+void BandedPairWiseSW::run(int zdrop_mode, SeqPair* pairs, const uint8_t* ref, const uint8_t* qer,
+                           int64_t n, int32_t w)
+{
+    const int64_t t0 = ticks_now();
+    bsw_engine* e = engine(zdrop_mode);
+    if (bsw_extend(e, pairs, ref, qer, n, w) != BSW_OK) die("bsw_extend failed", bsw_last_error(e));
+    bsw_get_stats(e, &stats_);
+    SW_cells += (uint64_t)stats_.cells_effective;
+    ticks_ += ticks_now() - t0;
+}
+
+void BandedPairWiseSW::getScores16(SeqPair *pairArray, uint8_t *seqBufRef, uint8_t *seqBufQer,
+                                   int32_t numPairs, uint16_t numThreads, int32_t w)
+{
+    (void)numThreads;
+    run(BSW_ZDROP_VECTOR, pairArray, seqBufRef, seqBufQer, numPairs, w);
+}
+
+void BandedPairWiseSW::getScores8(SeqPair *pairArray, uint8_t *seqBufRef, uint8_t *seqBufQer,
+                                  int32_t numPairs, uint16_t numThreads, int32_t w)
+{
+    (void)numThreads;
+    run(BSW_ZDROP_VECTOR, pairArray, seqBufRef, seqBufQer, numPairs, w);
+}
+
+void BandedPairWiseSW::scalarBandedSWAWrapper(SeqPair *seqPairArray, uint8_t *seqBufRef,
+                                              uint8_t *seqBufQer, int numPairs, int nthreads, int32_t w)
+{
+    (void)nthreads;
+    run(BSW_ZDROP_SCALAR, seqPairArray, seqBufRef, seqBufQer, numPairs, w);
+}
+
+int BandedPairWiseSW::scalarBandedSWA(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                                      int32_t w, int h0, int *_qle, int *_tle, int *_gtle,
+                                      int *_gscore, int *_max_off)
+{
+    SeqPair sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.len1 = tlen; sp.len2 = qlen; sp.h0 = h0;
+    run(BSW_ZDROP_SCALAR, &sp, target, query, 1, w);
+    if (_qle) *_qle = sp.qle;
+    if (_tle) *_tle = sp.tle;
+    if (_gtle) *_gtle = sp.gtle;
+    if (_gscore) *_gscore = sp.gscore;
+    if (_max_off) *_max_off = sp.max_off;
+    return sp.score;
+}
+
+int64_t BandedPairWiseSW::getTicks() { return ticks_; }

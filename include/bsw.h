@@ -1,0 +1,174 @@
+/*
+ * bsw.h -- C ABI of the B200-native batched banded Smith-Waterman extension engine.
+ *
+ * This is the drop-in boundary for the one hot path of GenomicsBench `bsw`
+ * (bwa-mem2's BandedPairWiseSW::getScores16 / getScores8, i.e. ksw_extend2
+ * semantics over batches of SeqPair).  Every entry point below replaces a
+ * piece of the reference interface; the citation next to each one is the
+ * reference file:line (relative to /root/reference/benchmarks/bsw) it stands
+ * in for.  Plain pointers and sizes only: no C++ or torch types cross this line.
+ *
+ * There is NO CPU fallback behind this ABI: every bsw_extend* call runs the
+ * hand-written sm_100a kernels and fails with BSW_ERR_CUDA when no device or
+ * no usable kernel image is present.
+ */
+#ifndef BSW_B200_H
+#define BSW_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- a1: SeqPair, layout identical to bandedSWA.h:91-100 (72 bytes) ------ */
+#ifndef BSW_SEQPAIR_DEFINED
+#define BSW_SEQPAIR_DEFINED
+typedef struct dnaSeqPair {
+    int64_t idr, idq, id;       /* byte offsets of ref / query in the sequence buffers; caller's id */
+    int32_t len1, len2;         /* len1 = reference (target) length, len2 = query length          */
+    int32_t h0;                 /* seed score, > 0                                                 */
+    int32_t seqid, regid;       /* untouched                                                       */
+    int32_t score, tle, gtle, qle;  /* outputs                                                     */
+    int32_t gscore, max_off;        /* outputs                                                     */
+} SeqPair;
+#endif
+
+/* ---- error codes (the reference has none: it exit()s, bandedSWA.cpp:94-99) */
+enum {
+    BSW_OK            =  0,
+    BSW_ERR_PARAM     = -1,   /* parameter outside the supported domain                 */
+    BSW_ERR_DOMAIN    = -2,   /* a pair violates 1<=len<=32767, h0>=1, scores<32768 ... */
+    BSW_ERR_CUDA      = -3,   /* CUDA runtime / no device / kernel image missing        */
+    BSW_ERR_NOMEM     = -4,
+    BSW_ERR_STATE     = -5,   /* call sequence error (e.g. run before stage)            */
+    BSW_ERR_IO        = -6
+};
+
+/* z-drop rule selector.  The reference's vector code (ZSCORE16, bandedSWA.cpp:323-336)
+ * and its scalar code (bandedSWA.cpp:222-228) disagree when e_del/e_ins != 1 or
+ * zdrop <= 0.  getScores16/getScores8 use VECTOR,
+ * scalarBandedSWAWrapper uses SCALAR. */
+enum { BSW_ZDROP_VECTOR = 0, BSW_ZDROP_SCALAR = 1 };
+
+/* ---- a2: constructor arguments of BandedPairWiseSW (bandedSWA.cpp:51-100) -- */
+typedef struct bsw_params {
+    int32_t o_del, e_del, o_ins, e_ins;   /* gap open / extend, > 0 extend           */
+    int32_t zdrop;                        /* 1..32767; 32767 == off (vector rule)    */
+    int32_t end_bonus;
+    int32_t match;                        /* w_match  (> 0)                          */
+    int32_t mismatch;                     /* penalty, positive (ctor negates it)     */
+    int32_t ambig;                        /* score of any cell touching base 4 (N); reference vector code hard-wires -1 (bandedSWA.cpp:69) */
+    int32_t zdrop_mode;                   /* BSW_ZDROP_VECTOR | BSW_ZDROP_SCALAR     */
+    int32_t n_devices;                    /* 0 => use the current CUDA device only   */
+    int32_t devices[16];                  /* CUDA ordinals when n_devices > 0        */
+    int32_t host_threads;                 /* packer threads per engine, 0 => auto    */
+    int32_t reserved[8];
+} bsw_params;
+
+/* Per-call statistics (replaces the rdtsc counters behind getTicks(),
+ * bandedSWA.cpp:108-122, and the commented-out GCUPS print main_banded.cpp:321-323). */
+typedef struct bsw_stats {
+    int64_t pairs;               /* pairs processed by the last call                     */
+    int64_t cells_nominal;       /* sum len1*len2 (reference GCUPS convention)           */
+    int64_t cells_effective;     /* inner-loop iterations actually executed (SW_cells)   */
+    double  ms_sort;             /* host: length bucketing                               */
+    double  ms_pack;             /* host: 2-bit packing into pinned staging              */
+    double  ms_h2d;              /* device timeline: H2D copies                          */
+    double  ms_kernel;           /* device timeline: sum of DP kernel launches (events)  */
+    double  ms_d2h;              /* device timeline: D2H copies                          */
+    double  ms_scatter;          /* host: results written back into SeqPair[] in order   */
+    double  ms_total;            /* host wall clock of the whole call                    */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t kernel_launches;     /* DP kernel launches issued by the last call           */
+    int32_t n_short, n_long;     /* pairs routed to the thread-per-pair / warp-per-pair kernel */
+    int32_t reserved[5];
+} bsw_stats;
+
+typedef struct bsw_engine bsw_engine;
+
+/* ---- engine lifetime ------------------------------------------------------ */
+/* replaces: new BandedPairWiseSW(...)   main_banded.cpp:253-258, bandedSWA.cpp:51-100 */
+bsw_engine* bsw_create(const bsw_params* params, int* err);
+/* replaces: delete bsw[i]               main_banded.cpp:346-349, bandedSWA.cpp:103-106 */
+void        bsw_destroy(bsw_engine* eng);
+const char* bsw_last_error(const bsw_engine* eng);   /* also valid with eng == NULL (creation errors) */
+void        bsw_default_params(bsw_params* p);       /* bwa defaults: main_banded.cpp:49-53,250 */
+
+/* ---- the hot path ---------------------------------------------------------
+ * replaces: getScores16 / getScores8 (bandedSWA.cpp:1124-1148 / :424-446) called
+ * at main_banded.cpp:286.  Host buffers in, six result fields written in place,
+ * input order preserved; pads are never written and pair.id is never read. */
+int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref,
+               const uint8_t* seq_qer, int64_t n_pairs, int32_t w);
+
+/* Split form of the same call, so that a caller (and bench.py) can keep a batch
+ * resident in HBM and time the DP kernels alone:
+ *   stage  = bucket + 2-bit pack + H2D      (host buffers -> HBM)
+ *   run    = DP kernels only on the staged batch (repeatable)
+ *   fetch  = D2H + scatter into pairs[] in input order                       */
+int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref,
+              const uint8_t* seq_qer, int64_t n_pairs, int32_t w);
+int bsw_run_staged(bsw_engine* eng);
+int bsw_fetch(bsw_engine* eng, SeqPair* pairs, int64_t n_pairs);
+
+int bsw_get_stats(const bsw_engine* eng, bsw_stats* out);
+
+/* ---- a6 / (e): length bucketing and the multi-GPU partitioner --------------
+ * replaces: sortPairsLen / sortPairsId (bandedSWA.cpp:368-420) and the OpenMP
+ * batch loop (main_banded.cpp:279-291).  order[] receives the processing order
+ * (indices into pairs[]), sorted by (len2, len1, h0); shard_begin[0..n_shards]
+ * receives cut points into order[] that balance sum len1*min(len2, 2w+1). */
+int bsw_bucket_order(const SeqPair* pairs, int64_t n_pairs, int64_t* order);
+int bsw_partition(const SeqPair* pairs, int64_t n_pairs, int32_t w, int32_t n_shards,
+                  int64_t* order, int64_t* shard_begin);
+
+/* ---- synthetic-pair generator (the reference has no generator:
+ * its inputs come from the dumper tools/bwa/bwamem.c:741-745,788-792) --------- */
+typedef struct bsw_gen_config {
+    uint64_t seed;
+    int64_t  n_pairs;
+    int32_t  qlen_min, qlen_max;     /* len2 ~ U[min,max]                               */
+    int32_t  tail_min, tail_max;     /* random reference tail ~ U[min,max]              */
+    int32_t  h0_min, h0_max;         /* h0 ~ U[min,max]                                 */
+    int32_t  max_len1;               /* clip reference length (0 = none)                */
+    int32_t  max_score8;             /* if > 0: clip h0 so that h0 + len2*match <= it   */
+    double   error_rate;             /* total, split equally sub / ins / del            */
+    double   n_rate;                 /* probability of an ambiguous base (code 4)       */
+    int32_t  match;                  /* only used by max_score8                         */
+    int32_t  reserved[7];
+} bsw_gen_config;
+
+/* Named configs of BASELINE.json: 0 small, 1 8-bit, 2 16-bit, 3 large, 4 sweep. */
+int     bsw_gen_named_config(int32_t which, bsw_gen_config* out);
+/* Upper bounds of the buffers bsw_gen_pairs needs for this config. */
+int     bsw_gen_bounds(const bsw_gen_config* cfg, int64_t* ref_bytes, int64_t* qer_bytes);
+/* Fills pairs[0..n), seq_ref, seq_qer (one base code per byte, 0-3, 4 = N).
+ * Pairs first_pair .. first_pair+n of the config's stream are produced, so a
+ * shard of a big config can be generated without the rest.  Returns bytes used
+ * through *ref_used / *qer_used. */
+int     bsw_gen_pairs(const bsw_gen_config* cfg, int64_t first_pair, int64_t n,
+                      SeqPair* pairs, uint8_t* seq_ref, uint8_t* seq_qer,
+                      int64_t* ref_used, int64_t* qer_used);
+
+/* ---- dataset I/O: the 3-line text format of main_banded.cpp:131-185 --------- */
+int64_t bsw_count_pairs_file(const char* path);
+int     bsw_read_pairs_file(const char* path, int64_t max_pairs, SeqPair* pairs,
+                            uint8_t* seq_ref, int64_t ref_cap, uint8_t* seq_qer, int64_t qer_cap,
+                            int64_t* n_read);
+int     bsw_write_pairs_file(const char* path, const SeqPair* pairs, int64_t n_pairs,
+                             const uint8_t* seq_ref, const uint8_t* seq_qer);
+
+/* ---- measured integer/DPX peak (roofline denominator) ---------- */
+/* Runs a dependency-free __viaddmax_s32 microbenchmark on the engine's first
+ * device and returns lane-ops/s (0 on failure). */
+double  bsw_measure_int_peak(bsw_engine* eng);
+
+/* library identification: "bsw_b200 <version> sm_100a" */
+const char* bsw_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSW_B200_H */

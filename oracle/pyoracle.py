@@ -1,0 +1,131 @@
+"""ctypes access to the CPU checkers.  TEST INFRASTRUCTURE ONLY (see ksw_oracle.c).
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs -- never by genomicsbench_b200/.
+
+  Oracle      oracle/libbsw_oracle.so   from-scratch restatement (always available; built by
+                                        oracle/Makefile, travels to the GPU box prebuilt)
+  Reference   oracle/_ref/libbswref.so  the unmodified reference class (bandedSWA.cpp) behind
+                                        oracle/ref_shim.cpp; present when it was built from
+                                        /root/reference in the build container
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_SO = HERE / "libbsw_oracle.so"
+REF_SO = HERE / "_ref" / "libbswref.so"
+KSW_SO = HERE / "_ref" / "libkswref.so"
+
+
+class OracleParams(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in
+                ("o_del", "e_del", "o_ins", "e_ins", "zdrop", "end_bonus", "match", "mismatch", "ambig",
+                 "zdrop_mode")]
+
+
+def make_params(o_del=6, e_del=1, o_ins=6, e_ins=1, zdrop=100, end_bonus=5, match=1, mismatch=4,
+                ambig=-1, zdrop_mode=0) -> OracleParams:
+    return OracleParams(o_del, e_del, o_ins, e_ins, zdrop, end_bonus, match, mismatch, ambig, zdrop_mode)
+
+
+def build(quiet: bool = True) -> None:
+    """(Re)builds the checker libraries; the reference part only when /root/reference exists."""
+    subprocess.run(["make", "-C", str(HERE)], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+class Oracle:
+    def __init__(self):
+        if not ORACLE_SO.exists():
+            build()
+        self.lib = C.CDLL(str(ORACLE_SO))
+        self.lib.bsw_oracle_batch.restype = C.c_int64
+        self.lib.bsw_oracle_batch.argtypes = [C.POINTER(OracleParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_int64, C.c_int, C.c_int]
+        self.lib.bsw_oracle_pair.restype = C.c_int64
+        self.lib.bsw_oracle_pair.argtypes = [C.POINTER(OracleParams), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                             C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.bsw_oracle_row_trips.restype = C.c_int64
+        self.lib.bsw_oracle_row_trips.argtypes = [C.POINTER(OracleParams), C.c_void_p, C.c_int, C.c_void_p,
+                                                  C.c_int, C.c_int, C.c_int, C.c_void_p]
+        self.lib.bsw_oracle_max_threads.restype = C.c_int
+
+    def max_threads(self) -> int:
+        return int(self.lib.bsw_oracle_max_threads())
+
+    def batch(self, params: OracleParams, pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray,
+              w: int, nthreads: int = 0) -> int:
+        """Writes the six result fields into pairs (in place); returns effective cells."""
+        if nthreads <= 0:
+            nthreads = self.max_threads()
+        return int(self.lib.bsw_oracle_batch(C.byref(params), pairs.ctypes.data, seq_ref.ctypes.data,
+                                             seq_qer.ctypes.data, len(pairs), w, nthreads))
+
+    def pair(self, params: OracleParams, query: np.ndarray, target: np.ndarray, w: int, h0: int):
+        out = np.zeros(6, dtype=np.int32)
+        cells = self.lib.bsw_oracle_pair(C.byref(params), query.ctypes.data, len(query), target.ctypes.data,
+                                         len(target), w, h0, out.ctypes.data, None)
+        return dict(score=int(out[0]), qle=int(out[1]), tle=int(out[2]), gtle=int(out[3]),
+                    gscore=int(out[4]), max_off=int(out[5]), cells=int(cells))
+
+    def row_trips(self, params, query, target, w, h0) -> np.ndarray:
+        trips = np.zeros(len(target), dtype=np.int32)
+        self.lib.bsw_oracle_row_trips(C.byref(params), query.ctypes.data, len(query), target.ctypes.data,
+                                      len(target), w, h0, trips.ctypes.data)
+        return trips
+
+
+class Reference:
+    """The reference's own code (AVX2 getScores16 / scalarBandedSWA)."""
+
+    def __init__(self):
+        if not REF_SO.exists():
+            raise FileNotFoundError(f"{REF_SO} absent (built only where /root/reference is mounted)")
+        self.lib = C.CDLL(str(REF_SO))
+        P = C.POINTER(OracleParams)
+        self.lib.ref_getscores16.restype = C.c_double
+        self.lib.ref_getscores16.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                             C.c_int32, C.c_int32]
+        self.lib.ref_time_getscores16_inplace.restype = C.c_double
+        self.lib.ref_time_getscores16_inplace.argtypes = self.lib.ref_getscores16.argtypes
+        self.lib.ref_getscores16_solo.restype = None
+        self.lib.ref_getscores16_solo.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        self.lib.ref_scalar.restype = C.c_double
+        self.lib.ref_scalar.argtypes = [P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+        self.lib.ref_max_threads.restype = C.c_int
+        self.lib.ref_sizeof_seqpair.restype = C.c_int
+
+    @staticmethod
+    def available() -> bool:
+        return REF_SO.exists()
+
+    def max_threads(self) -> int:
+        return int(self.lib.ref_max_threads())
+
+    def getscores16(self, params, pairs, seq_ref, seq_qer, w, batch=512, nthreads=0) -> float:
+        if nthreads <= 0:
+            nthreads = self.max_threads()
+        return float(self.lib.ref_getscores16(C.byref(params), pairs.ctypes.data, seq_ref.ctypes.data,
+                                              seq_qer.ctypes.data, len(pairs), w, batch, nthreads))
+
+    def time_getscores16_inplace(self, params, pairs_padded, n, seq_ref, seq_qer, w, batch=512, nthreads=0):
+        """pairs_padded must have capacity roundup16(n)+2 (reference writes pads, reads 2 beyond)."""
+        if nthreads <= 0:
+            nthreads = self.max_threads()
+        return float(self.lib.ref_time_getscores16_inplace(C.byref(params), pairs_padded.ctypes.data,
+                                                           seq_ref.ctypes.data, seq_qer.ctypes.data, n, w,
+                                                           batch, nthreads))
+
+    def solo(self, params, pair_rec: np.ndarray, seq_ref, seq_qer, w) -> None:
+        self.lib.ref_getscores16_solo(C.byref(params), pair_rec.ctypes.data, seq_ref.ctypes.data,
+                                      seq_qer.ctypes.data, w)
+
+    def scalar(self, params, pairs, seq_ref, seq_qer, w) -> float:
+        return float(self.lib.ref_scalar(C.byref(params), pairs.ctypes.data, seq_ref.ctypes.data,
+                                         seq_qer.ctypes.data, len(pairs), w))
