@@ -188,6 +188,8 @@ def gen_pairs(cfg: BswGenConfig, first: int = 0, n: Optional[int] = None):
     rc = lib.bsw_gen_pairs(C.byref(cfg), first, n, ptr(pairs), ptr(ref), ptr(qer), C.byref(ru), C.byref(qu))
     if rc:
         raise BswError(rc, "generator failed")
+    ref[ru.value: ru.value + 64] = 0          # slack after the last sequence, never addressed by a pair
+    qer[qu.value: qu.value + 64] = 0
     return pairs, ref[: ru.value + 64], qer[: qu.value + 64]
 
 

@@ -1,0 +1,147 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (and the reference-facing class
+mirror), against (1) the golden vectors produced by the reference's AVX2 getScores16 and
+(2) the oracle on the same seeded inputs.  Bit-exact on all six SeqPair result fields."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden, results_matrix
+from oracle.pyoracle import make_params
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_kwargs(params, **extra):
+    return dict(params, **extra)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_cuda_matches_reference_golden(lib, case):
+    pairs, ref, qer, w, params, expect, _ = load_golden(case)
+    with lib.Engine(**engine_kwargs(params)) as eng:
+        eng.extend(pairs, ref, qer, w)
+        st = eng.stats()
+    got = results_matrix(pairs)
+    bad = np.nonzero((got != expect).any(axis=1))[0]
+    assert bad.size == 0, f"{case}: {bad.size} pairs differ; first {bad[:3]} got {got[bad[:3]]} want {expect[bad[:3]]}"
+    assert st["kernel_launches"] >= 1 and st["cells_effective"] > 0
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_cuda_scalar_rule_matches_scalarBandedSWA(lib, case):
+    pairs, ref, qer, w, params, _, scalar = load_golden(case)
+    with lib.Engine(**engine_kwargs(params, zdrop_mode=1)) as eng:
+        eng.extend(pairs, ref, qer, w)
+    assert np.array_equal(results_matrix(pairs), scalar)
+
+
+def test_class_mirror_reads_like_the_reference(lib):
+    """BandedPairWiseSW(o_del,e_del,o_ins,e_ins,zdrop,end_bonus,mat,w_match,w_mismatch,nthreads)
+    + getScores16(pairArray, seqBufRef, seqBufQer, numPairs, numThreads, w): main_banded.cpp:253-258,286."""
+    pairs, ref, qer, w, params, expect, scalar = load_golden("small_151bp")
+    mat = []
+    for i in range(4):                                   # bwa_fill_scmat, main_banded.cpp:73-81
+        mat += [1 if i == j else -4 for j in range(4)] + [-1]
+    mat += [-1] * 5
+    bsw = lib.BandedPairWiseSW(6, 1, 6, 1, 100, 5, mat, 1, 4, 1)
+    padded = np.zeros(len(pairs) + 16, dtype=pairs.dtype)          # reference callers over-allocate pads
+    padded[: len(pairs)] = pairs
+    padded[len(pairs):]["score"] = -77
+    bsw.getScores16(padded, ref, qer, len(pairs), 1, w)
+    assert np.array_equal(results_matrix(padded[: len(pairs)]), expect)
+    assert (padded[len(pairs):]["score"] == -77).all()             # pads are never written
+    assert bsw.SW_cells > 0
+    p8 = pairs.copy()
+    bsw.getScores8(p8, ref, qer, len(p8), 1, w)
+    assert np.array_equal(results_matrix(p8), expect)
+    ps = pairs.copy()
+    bsw.scalarBandedSWAWrapper(ps, ref, qer, len(ps), 1, w)
+    assert np.array_equal(results_matrix(ps), scalar)
+    bsw.close()
+
+
+SWEEP = [
+    ("small", {}, {}, 100, 10000),
+    ("short8", {}, {}, 100, 60000),
+    ("long16", {}, {}, 100, 6000),
+    ("large", {}, {}, 100, 30000),
+    ("sweep", {}, {"zdrop": 100}, 32, 20000),
+    ("sweep", {}, {"zdrop": 32767}, 32, 10000),
+    ("sweep", {}, {"zdrop": 100}, 500, 10000),
+    ("sweep", {}, {"zdrop": 32767}, 500, 10000),
+    ("large", {"n_rate": 0.01}, {}, 100, 10000),
+    ("large", {}, {"o_del": 5, "e_del": 2, "o_ins": 7, "e_ins": 3, "zdrop": 20}, 100, 10000),
+    ("large", {}, {"o_del": 7, "e_del": 3, "o_ins": 5, "e_ins": 2, "zdrop": 30}, 50, 10000),
+    ("sweep", {"n_rate": 0.02}, {"match": 2, "mismatch": 3, "o_del": 4, "e_del": 2, "o_ins": 4, "e_ins": 2, "zdrop": 50}, 500, 8000),
+    ("small", {}, {"end_bonus": 0, "zdrop": 10}, 16, 8000),
+    ("small", {"h0_min": 1, "h0_max": 9}, {}, 1, 8000),
+    ("small", {"h0_min": 1, "h0_max": 6}, {"zdrop": 3}, 0, 4000),
+    ("long16", {"qlen_min": 300, "qlen_max": 860, "tail_min": 0, "tail_max": 400, "h0_max": 900}, {}, 100, 1500),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(SWEEP)))
+def test_cuda_matches_oracle_on_seeded_inputs(lib, oracle, idx):
+    name, over, sc, w, n = SWEEP[idx]
+    cfg = lib.gen_named_config(name)
+    cfg.seed = 0x5EED0000 + idx
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    pairs, ref, qer = lib.gen_pairs(cfg, 0, n)
+    want = pairs.copy()
+    cells = oracle.batch(make_params(**sc), want, ref, qer, w)
+    with lib.Engine(**sc) as eng:
+        eng.extend(pairs, ref, qer, w)
+        st = eng.stats()
+    a, b = results_matrix(pairs), results_matrix(want)
+    bad = np.nonzero((a != b).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} pairs differ; first {bad[:3]}: gpu {a[bad[:3]]} oracle {b[bad[:3]]}"
+    assert st["cells_effective"] == cells                 # the SW_cells hook (bandedSWA.cpp:211) agrees too
+    assert st["cells_nominal"] == int((pairs["len1"].astype(np.int64) * pairs["len2"]).sum())
+
+
+def test_edge_cases(lib, oracle):
+    """Empty batch, single pair, 1-base sequences, ragged lengths, N-only sequences, h0 = 1."""
+    from genomicsbench_b200 import SEQPAIR_DTYPE
+    with lib.Engine() as eng:
+        empty = np.zeros(0, dtype=SEQPAIR_DTYPE)
+        eng.extend(empty, np.zeros(1, np.uint8), np.zeros(1, np.uint8), 100)
+        assert eng.stats()["pairs"] == 0
+        rng = np.random.default_rng(7)
+        lens = [(1, 1), (1, 50), (50, 1), (2, 3), (127, 128), (128, 127), (129, 129), (300, 17), (17, 300),
+                (880, 880), (5, 880), (33, 31), (64, 64), (65, 63)]
+        n = len(lens)
+        pairs = np.zeros(n, dtype=SEQPAIR_DTYPE)
+        ref = rng.integers(0, 4, size=sum(a for a, _ in lens) + 8, dtype=np.uint8)
+        qer = rng.integers(0, 4, size=sum(b for _, b in lens) + 8, dtype=np.uint8)
+        ro = qo = 0
+        for k, (l1, l2) in enumerate(lens):
+            pairs[k]["len1"], pairs[k]["len2"], pairs[k]["idr"], pairs[k]["idq"] = l1, l2, ro, qo
+            pairs[k]["h0"] = 1 if k % 3 == 0 else 40
+            m = min(l1, l2)                                # make them alignable
+            qer[qo: qo + m] = ref[ro: ro + m]
+            ro += l1; qo += l2
+        qer[pairs[4]["idq"]: pairs[4]["idq"] + 10] = 4      # a run of N
+        ref[pairs[5]["idr"]: pairs[5]["idr"] + 128] = 4     # N-only reference
+        want = pairs.copy()
+        oracle.batch(make_params(), want, ref, qer, 100)
+        eng.extend(pairs, ref, qer, 100)
+        assert np.array_equal(results_matrix(pairs), results_matrix(want))
+
+
+def test_domain_errors(lib):
+    from genomicsbench_b200 import SEQPAIR_DTYPE
+    with lib.Engine() as eng:
+        pairs = np.zeros(2, dtype=SEQPAIR_DTYPE)
+        pairs["len1"], pairs["len2"], pairs["h0"] = 10, 10, 5
+        buf = np.zeros(64, np.uint8)
+        for field, val in (("len1", 0), ("len2", 0), ("h0", 0), ("len2", 40000), ("h0", 32767)):
+            bad = pairs.copy()
+            bad[field][1] = val
+            with pytest.raises(lib.BswError) as ei:
+                eng.extend(bad, buf, buf, 100)
+            assert ei.value.code == -2
+        with pytest.raises(lib.BswError) as ei:
+            eng.run_staged()
+        assert ei.value.code == -5
+        eng.extend(pairs, buf, buf, 100)                    # engine still usable afterwards
+        assert (pairs["score"] >= 5).all()
