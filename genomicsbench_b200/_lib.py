@@ -37,7 +37,8 @@ class BswParams(C.Structure):
         ("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32), ("e_ins", C.c_int32),
         ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32),
         ("ambig", C.c_int32), ("zdrop_mode", C.c_int32), ("n_devices", C.c_int32),
-        ("devices", C.c_int32 * 16), ("host_threads", C.c_int32), ("reserved", C.c_int32 * 8),
+        ("devices", C.c_int32 * 16), ("host_threads", C.c_int32), ("long_min_qlen", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 

@@ -48,6 +48,12 @@ struct DevCtx {
     Buf<int> pos_n;
     unsigned long long* d_cells = nullptr;
     unsigned long long* h_cells = nullptr;
+    unsigned int* d_queue = nullptr;      // work queue of the long-pair kernel
+    Buf<uint32_t> scratch;                // eh[] rows of the long-pair kernel (device only)
+    int64_t n_short = 0;                  // sorted positions [0, n_short) go to the short kernel
+    int64_t n_bytes_short = 0;            // byte-staged list: [0, n_bytes_short) short pairs with N,
+    int64_t n_long = 0;                   //                   [n_bytes_short, +n_long) long pairs
+    int long_stride = 0, long_blocks = 0;
     // staged shard
     int64_t first = 0, n = 0, n_bytes_pairs = 0;
     size_t q_words = 0, t_words = 0, qb_bytes = 0, tb_bytes = 0;
@@ -64,6 +70,7 @@ struct bsw_engine {
     std::string err;
     bsw_stats stats;
     int nthreads = 1;
+    int short_max = 0;                   // longest query the short kernel takes
     // staged batch
     bool staged = false, ran = false;
     int64_t n = 0;
@@ -171,6 +178,7 @@ int validate_params(const bsw_params* p, std::string& why)
     if (p->zdrop > 32767) return bad("zdrop must be <= 32767");
     if (p->end_bonus < 0 || p->end_bonus > 16000) return bad("end_bonus out of range");
     if (p->n_devices < 0 || p->n_devices > 16) return bad("n_devices must be in 0..16");
+    if (p->long_min_qlen < 0) return bad("long_min_qlen must be >= 0");
     return BSW_OK;
 }
 
@@ -225,6 +233,7 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
     k.mx = std::max(std::max(k.match, k.mismatch_neg), k.ambig);
     k.w = 0;
     eng->nthreads = auto_threads(params->host_threads);
+    eng->short_max = params->long_min_qlen > 0 ? std::min(params->long_min_qlen - 1, SHORT_MAX_QLEN) : SHORT_MAX_QLEN;
     memset(&eng->stats, 0, sizeof(eng->stats));
 
     std::vector<int> ids;
@@ -252,6 +261,7 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
         ok = ok && cudaEventCreate(&c.ev_k0) == cudaSuccess && cudaEventCreate(&c.ev_k1) == cudaSuccess;
         ok = ok && cudaEventCreate(&c.ev_d2h0) == cudaSuccess && cudaEventCreate(&c.ev_d2h1) == cudaSuccess;
         ok = ok && cudaMalloc((void**)&c.d_cells, sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&c.d_queue, sizeof(unsigned int)) == cudaSuccess;
         ok = ok && cudaHostAlloc((void**)&c.h_cells, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
         if (!ok) {
             std::string m = std::string("device setup failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -277,6 +287,8 @@ void bsw_destroy(bsw_engine* eng)
         release(c.meta); release(c.res); release(c.meta_n); release(c.q); release(c.t);
         release(c.qb); release(c.tb); release(c.pos_n);
         if (c.d_cells) cudaFree(c.d_cells);
+        if (c.d_queue) cudaFree(c.d_queue);
+        release(c.scratch);
         if (c.h_cells) cudaFreeHost(c.h_cells);
     }
     delete eng;
@@ -360,13 +372,16 @@ int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, con
         double tp0 = now_ms();
         if (int rc = ensure(eng, c.meta, (size_t)c.n)) return rc;
         if (int rc = ensure(eng, c.res, (size_t)c.n)) return rc;
-        // word offsets (serial prefix over the sorted order)
+        // word offsets (serial prefix over the sorted order); queries longer than the short
+        // kernel's shared-memory limit sit at the end of the order and are staged as bytes only
         std::vector<uint32_t> qoff((size_t)c.n + 1), toff((size_t)c.n + 1);
         {
             uint64_t qo = 0, to = 0;
+            c.n_short = c.n;
             for (int64_t s = 0; s < c.n; ++s) {
                 const SeqPair& sp = pairs[ord[s]];
                 qoff[s] = (uint32_t)qo; toff[s] = (uint32_t)to;
+                if (sp.len2 > eng->short_max) { if (c.n_short == c.n) c.n_short = s; continue; }
                 qo += (uint64_t)(sp.len2 + 15) >> 4; to += (uint64_t)(sp.len1 + 15) >> 4;
             }
             if (qo > 0xffffffffull || to > 0xffffffffull) { eng->err = "batch too large for 32-bit word offsets"; return BSW_ERR_PARAM; }
@@ -376,7 +391,7 @@ int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, con
         if (int rc = ensure(eng, c.q, c.q_words + 4)) return rc;
         if (int rc = ensure(eng, c.t, c.t_words + 4)) return rc;
         std::vector<uint8_t> hasn((size_t)c.n, 0);
-        parallel_chunks(c.n, 2048, nt, [&](int64_t b, int64_t e, int) {
+        parallel_chunks(c.n_short, 2048, nt, [&](int64_t b, int64_t e, int) {
             for (int64_t s = b; s < e; ++s) {
                 const SeqPair& sp = pairs[ord[s]];
                 bool nq = pack2(seq_qer + sp.idq, sp.len2, c.q.h + qoff[s]);
@@ -385,9 +400,13 @@ int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, con
                 c.meta.h[s] = make_int4((int)qoff[s], (int)toff[s], sp.len2 | (sp.len1 << 16), sp.h0);
             }
         });
-        // pairs containing N: staged again as bytes and recomputed by the byte-sequence variant
+        // byte-staged pairs: short pairs containing N (recomputed by the byte-sequence variant of
+        // the short kernel) followed by all long pairs (warp-per-pair kernel, N-safe by construction)
         std::vector<int64_t> nlist;
-        for (int64_t s = 0; s < c.n; ++s) if (hasn[s]) nlist.push_back(s);
+        for (int64_t s = 0; s < c.n_short; ++s) if (hasn[s]) nlist.push_back(s);
+        c.n_bytes_short = (int64_t)nlist.size();
+        for (int64_t s = c.n_short; s < c.n; ++s) nlist.push_back(s);
+        c.n_long = c.n - c.n_short;
         c.n_bytes_pairs = (int64_t)nlist.size();
         if (!nlist.empty()) {
             if (int rc = ensure(eng, c.meta_n, nlist.size())) return rc;
@@ -397,7 +416,7 @@ int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, con
                 const SeqPair& sp = pairs[ord[nlist[k]]];
                 c.meta_n.h[k] = make_int4((int)qo, (int)to, sp.len2 | (sp.len1 << 16), sp.h0);
                 c.pos_n.h[k] = (int)nlist[k];
-                qo += (uint64_t)sp.len2; to += (uint64_t)sp.len1;
+                qo += ((uint64_t)sp.len2 + 7) & ~3ull; to += ((uint64_t)sp.len1 + 7) & ~3ull;   // 4-byte aligned, >= 4 B slack
             }
             if (qo > 0x7fffffffull || to > 0x7fffffffull) { eng->err = "too many N-containing bases in one batch"; return BSW_ERR_PARAM; }
             c.qb_bytes = qo; c.tb_bytes = to;
@@ -414,13 +433,9 @@ int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, con
         // launch plan: blocks of SHORT_BLOCK consecutive pairs, merged by shared-memory class
         {
             int64_t s = 0;
-            while (s < c.n) {
-                const int64_t blk_end = std::min<int64_t>(c.n, s + SHORT_BLOCK);
+            while (s < c.n_short) {
+                const int64_t blk_end = std::min<int64_t>(c.n_short, s + SHORT_BLOCK);
                 const int qmax = pairs[ord[blk_end - 1]].len2;       // ascending in len2
-                if (qmax > SHORT_MAX_QLEN) {
-                    eng->err = "query longer than the short-pair kernel limit and the long-pair kernel is not built";
-                    return BSW_ERR_DOMAIN;
-                }
                 const int qs = stride_for(qmax);
                 if (!c.plan.empty() && c.plan.back().qstride == qs && !c.plan.back().bytes)
                     c.plan.back().count += (int)(blk_end - s);
@@ -428,10 +443,22 @@ int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, con
                     c.plan.push_back(Launch{(int)s, (int)(blk_end - s), qs, false});
                 s = blk_end;
             }
-            if (!nlist.empty()) {
+            if (c.n_bytes_short > 0) {
                 int qmax = 0;
-                for (int64_t s2 : nlist) qmax = std::max(qmax, pairs[ord[s2]].len2);
-                c.plan.push_back(Launch{0, (int)nlist.size(), stride_for(qmax), true});
+                for (int64_t k = 0; k < c.n_bytes_short; ++k) qmax = std::max(qmax, pairs[ord[nlist[k]]].len2);
+                c.plan.push_back(Launch{0, (int)c.n_bytes_short, stride_for(qmax), true});
+            }
+            if (c.n_long > 0) {
+                const int qmax = pairs[ord[c.n - 1]].len2;
+                c.long_stride = (qmax + 12) & ~3;
+                cudaDeviceProp prop{};
+                CUDA_TRY(cudaGetDeviceProperties(&prop, c.dev));
+                int64_t blocks = std::min<int64_t>((c.n_long + LONG_WARPS - 1) / LONG_WARPS,
+                                                   (int64_t)prop.multiProcessorCount * 8);
+                const int64_t cap_words = (int64_t)(256ll << 20) / 4;       // <= 256 MB of eh rows
+                blocks = std::max<int64_t>(1, std::min(blocks, cap_words / ((int64_t)c.long_stride * LONG_WARPS)));
+                c.long_blocks = (int)blocks;
+                if (int rc = ensure(eng, c.scratch, (size_t)blocks * LONG_WARPS * c.long_stride, false)) return rc;
             }
         }
 
@@ -450,7 +477,8 @@ int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, con
             S.h2d_bytes += (int64_t)(20 * nlist.size() + c.qb_bytes + c.tb_bytes);
         }
         CUDA_TRY(cudaEventRecord(c.ev_h2d1, st));
-        S.n_short += (int32_t)c.n;
+        S.n_short += (int32_t)c.n_short;
+        S.n_long += (int32_t)c.n_long;
     }
     for (DevCtx& c : eng->devs) {
         if (c.n == 0) continue;
@@ -497,6 +525,13 @@ static int launch_device(bsw_engine* eng, DevCtx& c)
         bsw_short_kernel<SHORT_BLOCK, true><<<grid, SHORT_BLOCK, smem, c.st[0]>>>(
             c.meta_n.d, reinterpret_cast<const uint32_t*>(c.qb.d), reinterpret_cast<const uint32_t*>(c.tb.d),
             c.res.d, c.pos_n.d, L.first, L.count, eng->kp, c.d_cells);
+        eng->stats.kernel_launches++;
+    }
+    if (c.n_long > 0) {
+        CUDA_TRY(cudaMemsetAsync(c.d_queue, 0, sizeof(unsigned int), c.st[0]));
+        bsw_long_kernel<<<c.long_blocks, LONG_WARPS * 32, 0, c.st[0]>>>(
+            c.meta_n.d + c.n_bytes_short, c.qb.d, c.tb.d, c.res.d, c.pos_n.d + c.n_bytes_short,
+            (int)c.n_long, eng->kp, c.scratch.d, c.long_stride, c.d_queue, c.d_cells);
         eng->stats.kernel_launches++;
     }
     CUDA_TRY(cudaEventRecord(c.ev_k1, c.st[0]));

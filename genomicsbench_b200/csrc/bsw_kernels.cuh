@@ -209,6 +209,171 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qse
 }
 
 // ---------------------------------------------------------------------------------------
+// Long-pair kernel: one pair per warp, row sweep.
+//   Each DP row's window [beg, end) is cut into chunks of 128 cells; lane l owns 4 consecutive
+//   cells of the chunk.  M and E are elementwise in the previous row; F is the max-plus prefix
+//   F(j+1) = max(F(j) - e_ins, M(j) - oe_ins, 0): every lane sweeps its 4 cells with F_in = 0,
+//   a 5-step __shfl_up_sync scan combines the lanes' outgoing values (decay 4*e_ins per lane),
+//   and each cell takes max(local, F_in - k*e_ins).  The diagonal H hand-off between lanes
+//   and chunks is one __shfl_up_sync.  Rows stay strictly sequential because the window,
+//   the m == 0 exit and z-drop need the complete previous row (SURVEY.md finding 0.6).
+//   Sequences are one base per byte (codes 0-4), 4-byte aligned; eh[] (h | e << 16 per cell)
+//   lives in a per-warp global scratch row that stays L1/L2 resident.
+//   Pairs are pulled from an atomic queue, longest first.
+// ---------------------------------------------------------------------------------------
+constexpr int LONG_WARPS = 4;
+
+__global__ void __launch_bounds__(LONG_WARPS * 32)
+bsw_long_kernel(const int4* __restrict__ meta, const uint8_t* __restrict__ qbytes,
+                const uint8_t* __restrict__ tbytes, int4* __restrict__ res,
+                const int* __restrict__ respos, int count, const __grid_constant__ KParams P,
+                uint32_t* __restrict__ scratch, int scratch_stride, unsigned int* __restrict__ queue,
+                unsigned long long* __restrict__ cell_counter)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = blockIdx.x * LONG_WARPS + (threadIdx.x >> 5);
+    uint32_t* const eh = scratch + (size_t)gwarp * scratch_stride;
+    const int e_ins4 = 4 * P.e_ins;
+    long long my_cells = 0;
+
+    for (;;) {
+        unsigned k = 0;
+        if (lane == 0) k = atomicAdd(queue, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= (unsigned)count) break;
+        const int s = count - 1 - (int)k;                  // ascending in len2 -> longest first
+        const int4 md = meta[s];
+        const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w;
+        const uint8_t* qb = qbytes + (uint32_t)md.x;
+        const uint8_t* tb = tbytes + (uint32_t)md.y;
+
+        // first row, closed form of bandedSWA.cpp:155-157: eh[j].h = max(h0 - oe_ins - (j-1)*e_ins, 0)
+        for (int j = lane; j <= qlen + 4; j += 32) {
+            int hv = 0;
+            if (j == 0) hv = h0;
+            else if (j <= qlen) hv = max(h0 - P.oe_ins - (j - 1) * P.e_ins, 0);
+            eh[j] = (uint32_t)hv;
+        }
+        __syncwarp();
+        const int w = bsw_clamp_band(P, qlen);
+        PairState st;
+        st.max = h0; st.max_i = -1; st.max_j = -1; st.max_ie = -1; st.gscore = -1; st.max_off = 0;
+        int beg = 0, end = qlen;
+
+        for (int i = 0; i < tlen; ++i) {
+            const int ti = __ldg(tb + i);
+            beg = max(beg, i - w);
+            end = min(min(end, i + w + 1), qlen);
+            const int h1_init = beg == 0 ? max(h0 - (P.o_del + P.e_del * (i + 1)), 0) : 0;
+            int f_carry = 0, h_carry = h1_init;
+            unsigned mkey = 0;
+            int h_end = -1;                                 // H(i, end-1), found by its owner lane
+            if (end > beg) {
+                for (int cbase = beg & ~3; cbase <= end; cbase += 128) {
+                    const int j0 = cbase + 4 * lane;
+                    uint4 wd = make_uint4(0, 0, 0, 0);
+                    uint32_t qw = 0;
+                    if (j0 <= end) {
+                        wd = *reinterpret_cast<const uint4*>(eh + j0);
+                        if (j0 < qlen) qw = __ldg(reinterpret_cast<const uint32_t*>(qb + j0));
+                    }
+                    const uint32_t wds[4] = {wd.x, wd.y, wd.z, wd.w};
+                    int M[4], E[4], g[5];
+                    g[0] = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int j = j0 + c;
+                        const bool in = j >= beg && j < end;
+                        const int Hd = in ? (int)(wds[c] & 0xffffu) : 0;
+                        E[c] = in ? (int)(wds[c] >> 16) : 0;
+                        const int qk = (int)((qw >> (8 * c)) & 0xffu);
+                        int sc = qk == ti ? P.match : P.mismatch_neg;
+                        if ((qk | ti) > 3) sc = P.ambig;
+                        M[c] = __viaddmin_s32_relu(Hd, sc, Hd << 16);
+                        g[c + 1] = __viaddmax_s32_relu(M[c], -P.oe_ins, g[c] - P.e_ins);
+                    }
+                    // inclusive max-plus scan of the lanes' outgoing F (decay 4*e_ins per lane)
+                    int x = g[4];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int y = __shfl_up_sync(FULL, x, d);
+                        if (lane >= d) x = max(x, y - e_ins4 * d);
+                    }
+                    int fin = __shfl_up_sync(FULL, x, 1);
+                    fin = lane == 0 ? f_carry : max(fin, f_carry - e_ins4 * lane);
+                    int H[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int F = max(g[c], fin - c * P.e_ins);
+                        H[c] = __vimax3_s32(M[c], E[c], F);
+                    }
+                    int hprev = __shfl_up_sync(FULL, H[3], 1);
+                    if (lane == 0) hprev = h_carry;
+                    // new cells: h = H(i, j-1), e = E(i+1, j); cell `end` gets {H(i,end-1), 0}
+                    uint32_t nw[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int j = j0 + c;
+                        const int hp = c == 0 ? hprev : H[c - 1];
+                        const int en = __viaddmax_s32_relu(M[c], -P.oe_del, E[c] - P.e_del);
+                        uint32_t v = wds[c];
+                        if (j >= beg && j < end) {
+                            v = (uint32_t)hp | ((uint32_t)en << 16);
+                            mkey = max(mkey, ((unsigned)H[c] << 16) | (unsigned)j);
+                            if (j == end - 1) h_end = H[c];
+                        } else if (j == end) {
+                            v = (uint32_t)hp;
+                        }
+                        nw[c] = v;
+                    }
+                    if (j0 <= end) *reinterpret_cast<uint4*>(eh + j0) = make_uint4(nw[0], nw[1], nw[2], nw[3]);
+                    f_carry = max(__shfl_sync(FULL, x, 31), f_carry - e_ins4 * 32);
+                    h_carry = __shfl_sync(FULL, H[3], 31);
+                }
+                if (lane == 0) my_cells += end - beg;
+            } else if (lane == 0) {
+                eh[end] = (uint32_t)h1_init;               // bandedSWA.cpp:213 with an empty window
+            }
+            __syncwarp();
+            mkey = __reduce_max_sync(FULL, mkey);
+            const int h1 = end > beg ? __reduce_max_sync(FULL, h_end) : h1_init;
+            const int jfin = end > beg ? end : beg;
+            if (jfin == qlen) {
+                if (!(st.gscore > h1)) st.max_ie = i;
+                st.gscore = max(st.gscore, h1);
+            }
+            const int m = (int)(mkey >> 16), mj = (int)(mkey & 0xffffu);
+            if (bsw_row_update(P, st, i, m, mj)) break;
+            // next row's window (bandedSWA.cpp:230-233), 32 cells per probe
+            {
+                int j = beg;
+                while (j < end) {
+                    const int idx = j + lane;
+                    const uint32_t v = idx < end ? eh[idx] : 1u;
+                    const unsigned b = __ballot_sync(FULL, v != 0);
+                    if (b) { j += __ffs(b) - 1; break; }
+                    j += 32;
+                }
+                beg = j;
+                j = end;
+                while (j >= beg) {
+                    const int idx = j - lane;
+                    const uint32_t v = idx >= beg ? eh[idx] : 1u;
+                    const unsigned b = __ballot_sync(FULL, v != 0);
+                    if (b) { j -= __ffs(b) - 1; break; }
+                    j -= 32;
+                }
+                end = min(j + 2, qlen);
+            }
+        }
+        if (lane == 0) res[respos ? respos[s] : s] = bsw_pack_result(st);
+        __syncwarp();
+    }
+    if (lane == 0 && my_cells) atomicAdd(cell_counter, (unsigned long long)my_cells);
+}
+
+// ---------------------------------------------------------------------------------------
 // Dependency-free DPX throughput probe: the roofline denominator P_int.
 // Each thread keeps 8 independent VIADDMNMX chains; ops = threads * iters * 8.
 // ---------------------------------------------------------------------------------------

@@ -64,7 +64,10 @@ typedef struct bsw_params {
     int32_t n_devices;                    /* 0 => use the current CUDA device only   */
     int32_t devices[16];                  /* CUDA ordinals when n_devices > 0        */
     int32_t host_threads;                 /* packer threads per engine, 0 => auto    */
-    int32_t reserved[8];
+    int32_t long_min_qlen;                /* queries of at least this length use the warp-per-pair
+                                             kernel; 0 => default (881, the short kernel's shared-
+                                             memory limit + 1); 1 routes every pair to it          */
+    int32_t reserved[7];
 } bsw_params;
 
 /* Per-call statistics (replaces the rdtsc counters behind getTicks(),

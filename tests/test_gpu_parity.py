@@ -27,6 +27,19 @@ def test_cuda_matches_reference_golden(lib, case):
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_long_kernel_matches_reference_golden(lib, case):
+    """Every golden case again with all pairs routed to the warp-per-pair kernel."""
+    pairs, ref, qer, w, params, expect, _ = load_golden(case)
+    with lib.Engine(**engine_kwargs(params, long_min_qlen=1)) as eng:
+        eng.extend(pairs, ref, qer, w)
+        st = eng.stats()
+    got = results_matrix(pairs)
+    bad = np.nonzero((got != expect).any(axis=1))[0]
+    assert bad.size == 0, f"{case}: {bad.size} pairs differ; first {bad[:3]} got {got[bad[:3]]} want {expect[bad[:3]]}"
+    assert st["n_long"] == len(pairs) and st["n_short"] == 0
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_cuda_scalar_rule_matches_scalarBandedSWA(lib, case):
     pairs, ref, qer, w, params, _, scalar = load_golden(case)
     with lib.Engine(**engine_kwargs(params, zdrop_mode=1)) as eng:
@@ -97,6 +110,14 @@ def test_cuda_matches_oracle_on_seeded_inputs(lib, oracle, idx):
     assert bad.size == 0, f"{bad.size} pairs differ; first {bad[:3]}: gpu {a[bad[:3]]} oracle {b[bad[:3]]}"
     assert st["cells_effective"] == cells                 # the SW_cells hook (bandedSWA.cpp:211) agrees too
     assert st["cells_nominal"] == int((pairs["len1"].astype(np.int64) * pairs["len2"]).sum())
+    # same inputs, split between the two kernels at a mid length: results and cell count unchanged
+    mid = int(np.median(pairs["len2"])) + 1
+    again = pairs.copy()
+    with lib.Engine(**sc, long_min_qlen=mid) as eng:
+        eng.extend(again, ref, qer, w)
+        st2 = eng.stats()
+    assert np.array_equal(results_matrix(again), b)
+    assert st2["cells_effective"] == cells and st2["n_long"] > 0
 
 
 def test_edge_cases(lib, oracle):
