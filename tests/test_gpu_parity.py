@@ -111,7 +111,7 @@ def test_cuda_matches_oracle_on_seeded_inputs(lib, oracle, idx):
     assert st["cells_effective"] == cells                 # the SW_cells hook (bandedSWA.cpp:211) agrees too
     assert st["cells_nominal"] == int((pairs["len1"].astype(np.int64) * pairs["len2"]).sum())
     # same inputs, split between the two kernels at a mid length: results and cell count unchanged
-    mid = int(np.median(pairs["len2"])) + 1
+    mid = max(1, int(np.median(pairs["len2"])))          # len2 >= mid -> warp-per-pair kernel
     again = pairs.copy()
     with lib.Engine(**sc, long_min_qlen=mid) as eng:
         eng.extend(again, ref, qer, w)
