@@ -6,6 +6,12 @@
 #include <vector>
 #include <algorithm>
 #include <chrono>
+#include <atomic>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
+#include <cstdlib>
+#include <new>
 #include "../../include/bsw.h"
 
 namespace bsw {
@@ -24,26 +30,103 @@ inline int auto_threads(int requested)
     return (int)std::min<unsigned>(hc, 32u);
 }
 
-// Static block-cyclic parallel loop over [0, n) in chunks of `grain`; fn(begin, end, tid).
-template <class F>
-void parallel_chunks(int64_t n, int64_t grain, int nthreads, F&& fn)
-{
-    if (n <= 0) return;
-    if (grain < 1) grain = 1;
-    const int64_t nchunks = (n + grain - 1) / grain;
-    nthreads = (int)std::min<int64_t>(std::max(nthreads, 1), nchunks);
-    if (nthreads == 1) { fn((int64_t)0, n, 0); return; }
-    std::vector<std::thread> th;
-    th.reserve(nthreads);
-    for (int t = 0; t < nthreads; ++t)
-        th.emplace_back([=, &fn]() {
-            for (int64_t c = t; c < nchunks; c += nthreads) {
-                const int64_t b = c * grain, e = std::min(n, b + grain);
-                fn(b, e, t);
+// Persistent worker pool: run(nchunks, fn) executes fn(chunk, tid) for every chunk in
+// [0, nchunks), chunks handed out dynamically; the calling thread works too (tid 0).
+class ThreadPool {
+public:
+    explicit ThreadPool(int nthreads) : n_(std::max(nthreads, 1))
+    {
+        for (int t = 1; t < n_; ++t) workers_.emplace_back([this, t] { loop(t); });
+    }
+    ~ThreadPool()
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        for (auto& w : workers_) w.join();
+    }
+    int size() const { return n_; }
+
+    template <class F>
+    void run(int64_t nchunks, F&& fn)
+    {
+        if (nchunks <= 0) return;
+        if (n_ == 1 || nchunks == 1) {
+            for (int64_t c = 0; c < nchunks; ++c) fn(c, 0);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(run_m_);       // one parallel region at a time
+        std::function<void(int64_t, int)> f = std::ref(fn);
+        {
+            std::lock_guard<std::mutex> g(m_);
+            job_ = &f;
+            total_ = nchunks;
+            next_.store(0, std::memory_order_relaxed);
+            pending_ = n_ - 1;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        work(f, 0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+    // Convenience: contiguous ranges [b, e) of `grain` items; fn(b, e, tid).
+    template <class F>
+    void for_range(int64_t n, int64_t grain, F&& fn)
+    {
+        if (n <= 0) return;
+        grain = std::max<int64_t>(grain, 1);
+        const int64_t nchunks = (n + grain - 1) / grain;
+        run(nchunks, [&](int64_t c, int tid) { fn(c * grain, std::min(n, (c + 1) * grain), tid); });
+    }
+
+private:
+    void work(std::function<void(int64_t, int)>& f, int tid)
+    {
+        for (;;) {
+            const int64_t c = next_.fetch_add(1, std::memory_order_relaxed);
+            if (c >= total_) break;
+            f(c, tid);
+        }
+    }
+    void loop(int tid)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void(int64_t, int)>* f;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (stop_) return;
+                f = job_;
             }
-        });
-    for (auto& x : th) x.join();
-}
+            if (f) work(*f, tid);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) done_cv_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> workers_;
+    std::mutex m_, run_m_;
+    std::condition_variable cv_, done_cv_;
+    std::function<void(int64_t, int)>* job_ = nullptr;
+    std::atomic<int64_t> next_{0};
+    int64_t total_ = 0;
+    int pending_ = 0;
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
+
+// Process-wide pool for the host utilities that have no engine (bsw_bucket_order, generator).
+ThreadPool& global_pool();
 
 // splitmix64: the generator's PRNG.
 struct SplitMix64 {
@@ -56,13 +139,56 @@ struct SplitMix64 {
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         return z ^ (z >> 31);
     }
-    // uniform integer in [lo, hi]
-    inline int32_t range(int32_t lo, int32_t hi)
+    inline int32_t range(int32_t lo, int32_t hi)     // uniform integer in [lo, hi]
     {
         if (hi <= lo) return lo;
         return lo + (int32_t)(next() % (uint64_t)(hi - lo + 1));
     }
     inline double unit() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
 };
+
+// ---- bucketing (bsw_host.cpp) ----------------------------------------------------------
+// A batch in processing order: position s holds caller index idx[s]; len2/len1/h0 of that
+// pair are kept alongside so later passes never touch the caller's array out of order.
+// Grow-only uninitialised array: reused across calls so that steady-state batches pay neither
+// the zero-fill of std::vector nor fresh page faults.
+template <class T>
+struct RawBuf {
+    T* p = nullptr; size_t cap = 0;
+    RawBuf() = default;
+    RawBuf(const RawBuf&) = delete;
+    RawBuf& operator=(const RawBuf&) = delete;
+    ~RawBuf() { free(p); }
+    void reserve(size_t n)
+    {
+        if (n <= cap) return;
+        free(p);
+        cap = n + n / 8 + 64;
+        p = static_cast<T*>(malloc(cap * sizeof(T)));
+        if (!p) { cap = 0; throw std::bad_alloc(); }
+    }
+    void swap(RawBuf& o) { std::swap(p, o.p); std::swap(cap, o.cap); }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+};
+
+struct SortedBatch {
+    int64_t n = 0;
+    // caller (input) order: everything later passes need from the 72-byte SeqPair records, so the
+    // caller's array is read exactly once, sequentially
+    RawBuf<uint64_t> offr, offq;    // idr / idq
+    RawBuf<uint16_t> in_len2, in_len1, in_h0;
+    // processing order
+    RawBuf<uint32_t> idx;           // processing order -> caller index
+    RawBuf<uint16_t> len2, len1, h0;
+    RawBuf<uint64_t> tmpA, tmpB;    // radix-sort scratch: (key32 << 32) | idx
+    int64_t cells_nominal = 0;
+    bool domain_ok = true;
+};
+
+// Validates the domain, accumulates sum len1*len2 and sorts by (len2, h0, len1).
+void build_sorted_batch(ThreadPool& pool, const SeqPair* pairs, int64_t n, int32_t match, SortedBatch& out);
 
 } // namespace bsw

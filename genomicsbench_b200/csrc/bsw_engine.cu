@@ -2,19 +2,26 @@
 //
 // Stands in for BandedPairWiseSW's batch wrapper smithWatermanBatchWrapper16
 // (benchmarks/bsw/bandedSWA.cpp:1150-1431): where the reference pads to the SIMD width, sorts by
-// len1, transposes AoS->SoA per 16 pairs and calls the AVX kernel, this engine buckets by
-// (len2, len1, h0), packs sequences to 2 bits/base straight into pinned staging, copies
-// asynchronously to HBM, launches the sm_100a kernels per length class and scatters the six
-// result fields back into the caller's SeqPair[] in input order.
+// len1, transposes AoS->SoA per 16 pairs and calls the AVX kernel, this engine
+//   1. buckets the batch by (len2, h0, len1)                       (bsw_host.cpp)
+//   2. cuts the processing order into chunks and, per chunk, packs sequences to 2 bits/base
+//      straight into pinned staging, copies them to HBM asynchronously, launches the sm_100a
+//      kernels per shared-memory class and copies the packed results back -- chunk k's GPU work
+//      overlaps the packing of chunk k+1 and the scatter of chunk k-1
+//   3. scatters the six result fields into the caller's SeqPair[] in input order.
+// Pairs that contain N (code 4) and pairs whose query exceeds the short kernel's shared-memory
+// limit are staged as bytes and run by the byte variant of the short kernel / the warp-per-pair
+// long kernel after the last chunk.
 #include "bsw_common.h"
 #include "bsw_kernels.cuh"
 #include <cstdio>
 #include <cstring>
 #include <string>
-#include <mutex>
+#include <memory>
+#include <deque>
 
 namespace bsw {
-void bucket_order(const SeqPair* pairs, int64_t n, int64_t* order, int nthreads);
+void partition_blocks(const SortedBatch& sb, int32_t w, int32_t n_shards, std::vector<std::vector<int64_t>>& blocks_of);
 }
 using namespace bsw;
 
@@ -22,7 +29,8 @@ namespace {
 
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
 constexpr int SHORT_MAX_QLEN = 880;       // (qlen+1) * SHORT_BLOCK * 4 B must fit 227 KB
-constexpr int NSTREAMS = 4;
+constexpr int NSTREAMS = 4;               // compute streams per device
+constexpr int MAX_CHUNKS = 16;
 
 std::string g_create_error;
 std::mutex g_err_mutex;
@@ -30,7 +38,6 @@ std::mutex g_err_mutex;
 struct Launch {
     int first, count;     // range in the shard's processing order
     int qstride;          // shared-memory rows per thread (>= qmax + 1)
-    bool bytes;           // N-containing pairs: byte sequences
 };
 
 template <class T>
@@ -38,26 +45,41 @@ struct Buf {              // grow-only device + pinned-host buffer pair
     T* d = nullptr; T* h = nullptr; size_t cap = 0;
 };
 
+struct Chunk {
+    int64_t s0 = 0, s1 = 0;               // range in the shard's processing order
+    size_t q0 = 0, q1 = 0, t0 = 0, t1 = 0; // word ranges in the packed sequence buffers
+    std::vector<Launch> plan;
+    cudaEvent_t ev_h2d{}, ev_done{};
+    bool scattered = false;
+};
+
 struct DevCtx {
     int dev = 0;
-    cudaStream_t st[NSTREAMS] = {};
-    cudaEvent_t ev_h2d0{}, ev_h2d1{}, ev_k0{}, ev_k1{}, ev_d2h0{}, ev_d2h1{}, ev_join[NSTREAMS] = {};
-    Buf<int4> meta, res, meta_n;
+    int sms = 148;
+    cudaStream_t st_copy{}, st_d2h{}, st[NSTREAMS] = {};
+    cudaEvent_t ev_a{}, ev_b{}, ev_k0{}, ev_k1{}, ev_join[NSTREAMS] = {};
+    Chunk chunks[MAX_CHUNKS];
+    int nchunks = 0;
+    Buf<int4> meta, res, meta_n, res_n;
     Buf<uint32_t> q, t;
     Buf<uint8_t> qb, tb;
-    Buf<int> pos_n;
+    std::vector<uint32_t> pos_n;          // byte-staged pair k -> position in the shard order
+    std::vector<uint8_t> hasn;            // per position: pair contains an N
+    std::vector<uint32_t> qoff, toff;     // word offsets per position (+1)
     unsigned long long* d_cells = nullptr;
     unsigned long long* h_cells = nullptr;
     unsigned int* d_queue = nullptr;      // work queue of the long-pair kernel
     Buf<uint32_t> scratch;                // eh[] rows of the long-pair kernel (device only)
-    int64_t n_short = 0;                  // sorted positions [0, n_short) go to the short kernel
-    int64_t n_bytes_short = 0;            // byte-staged list: [0, n_bytes_short) short pairs with N,
-    int64_t n_long = 0;                   //                   [n_bytes_short, +n_long) long pairs
+    // the shard of the sorted batch this device owns (copied views, processing order)
+    RawBuf<uint32_t> idx;
+    RawBuf<uint16_t> len2, len1, h0;
+    int64_t n = 0;                        // pairs in the shard
+    int64_t n_short = 0;                  // positions [0, n_short) go to the short kernel
+    int64_t n_bytes_short = 0;            // byte list: [0, n_bytes_short) short pairs with N,
+    int64_t n_long = 0;                   //            [n_bytes_short, +n_long) long pairs
+    int qmax_bytes_short = 0;
     int long_stride = 0, long_blocks = 0;
-    // staged shard
-    int64_t first = 0, n = 0, n_bytes_pairs = 0;
-    size_t q_words = 0, t_words = 0, qb_bytes = 0, tb_bytes = 0;
-    std::vector<Launch> plan;
+    size_t qb_bytes = 0, tb_bytes = 0;
     bool attr_set = false;
 };
 
@@ -66,17 +88,16 @@ struct DevCtx {
 struct bsw_engine {
     bsw_params p;
     KParams kp;
-    std::vector<DevCtx> devs;
+    std::deque<DevCtx> devs;
+    std::unique_ptr<ThreadPool> pool;
     std::string err;
     bsw_stats stats;
-    int nthreads = 1;
-    int short_max = 0;                   // longest query the short kernel takes
+    int short_max = SHORT_MAX_QLEN;       // longest query the short kernel takes
     // staged batch
     bool staged = false, ran = false;
     int64_t n = 0;
     int32_t w = 0;
-    std::vector<int64_t> order;          // processing order -> caller index
-    std::vector<int64_t> shard_begin;
+    SortedBatch sb;
 };
 
 namespace {
@@ -113,7 +134,7 @@ void release(Buf<T>& b)
 }
 
 // 2-bit packing of n base codes (one per byte) into 16-bases-per-word little-endian words.
-// Returns true if a code > 3 (N) was seen; such bases are packed as 0.
+// Returns true if a code > 3 (N) was seen; such bases are packed as (code & 3).
 inline bool pack2(const uint8_t* src, int n, uint32_t* dst)
 {
     uint64_t bad = 0;
@@ -141,9 +162,8 @@ inline bool pack2(const uint8_t* src, int n, uint32_t* dst)
     return bad != 0;
 }
 
-const int kStrideSteps[] = {9, 17, 25, 33, 41, 49, 57, 65, 73, 81, 89, 97, 105, 113, 121, 129, 145, 153, 161,
-                            177, 193, 209, 225, 241, 257, 273, 289, 305, 321, 353, 385, 417, 449, 513,
-                            577, 641, 705, 769, 833, SHORT_MAX_QLEN + 1};
+const int kStrideSteps[] = {17, 33, 49, 65, 81, 97, 113, 129, 153, 177, 201, 225, 257, 289, 321, 353,
+                            385, 449, 513, 577, 641, 705, 769, 833, SHORT_MAX_QLEN + 1};
 
 inline int stride_for(int qmax)
 {
@@ -182,11 +202,318 @@ int validate_params(const bsw_params* p, std::string& why)
     return BSW_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// per-shard preparation: offsets, chunking, launch plans, buffer sizing
+// ------------------------------------------------------------------------------------------
+int prepare_shard(bsw_engine* eng, DevCtx& c, bool pipelined)
+{
+    CUDA_TRY(cudaSetDevice(c.dev));
+    if (int rc = set_kernel_attrs(eng, c)) return rc;
+    c.nchunks = 0;
+    c.n_short = c.n_bytes_short = c.n_long = 0; c.qb_bytes = c.tb_bytes = 0; c.pos_n.clear();
+    if (c.n == 0) return BSW_OK;
+    // queries longer than the short kernel's limit sit at the end of the (len2-ascending) order
+    c.n_short = std::upper_bound(c.len2.data(), c.len2.data() + c.n, (uint16_t)eng->short_max) - c.len2.data();
+    c.n_long = c.n - c.n_short;
+    c.qoff.resize((size_t)c.n_short + 1); c.toff.resize((size_t)c.n_short + 1);
+    uint64_t qo = 0, to = 0;
+    for (int64_t s = 0; s < c.n_short; ++s) {
+        c.qoff[s] = (uint32_t)qo; c.toff[s] = (uint32_t)to;
+        qo += (uint32_t)(c.len2[s] + 15) >> 4; to += (uint32_t)(c.len1[s] + 15) >> 4;
+    }
+    if (qo > 0xffffffffull || to > 0xffffffffull) { eng->err = "batch too large for 32-bit word offsets"; return BSW_ERR_PARAM; }
+    c.qoff[c.n_short] = (uint32_t)qo; c.toff[c.n_short] = (uint32_t)to;
+    if (int rc = ensure(eng, c.meta, (size_t)c.n_short + 1)) return rc;
+    if (int rc = ensure(eng, c.res, (size_t)c.n_short + 1)) return rc;
+    if (int rc = ensure(eng, c.q, qo + 4)) return rc;
+    if (int rc = ensure(eng, c.t, to + 4)) return rc;
+    c.hasn.assign((size_t)c.n_short, 0);
+
+    // chunks: equal shares of the estimated work, cut at block boundaries
+    int want = 1;
+    if (pipelined && c.n_short >= 4 * 16384) want = (int)std::min<int64_t>(8, c.n_short / 65536 + 1);
+    std::vector<int64_t> cuts{0};
+    if (want > 1) {
+        const int64_t nblk = (c.n_short + SHORT_BLOCK - 1) / SHORT_BLOCK;
+        std::vector<double> pre((size_t)nblk + 1, 0.0);
+        const double band = 2.0 * eng->w + 1;
+        for (int64_t b = 0; b < nblk; ++b) {
+            const int64_t s = std::min(c.n_short - 1, b * SHORT_BLOCK + SHORT_BLOCK - 1);
+            const int64_t cnt = std::min<int64_t>(SHORT_BLOCK, c.n_short - b * SHORT_BLOCK);
+            pre[b + 1] = pre[b] + (double)cnt * (64.0 + c.len1[s] * std::min<double>(c.len2[s], band) +
+                                                 40.0 * (c.len1[s] + c.len2[s]));
+        }
+        for (int k = 1; k < want; ++k) {
+            const double target = pre[nblk] * k / want;
+            const int64_t b = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
+            const int64_t cut = std::min(c.n_short, b * SHORT_BLOCK);
+            if (cut > cuts.back()) cuts.push_back(cut);
+        }
+    }
+    if (c.n_short > cuts.back()) cuts.push_back(c.n_short);
+    c.nchunks = (int)cuts.size() - 1;
+    for (int k = 0; k < c.nchunks; ++k) {
+        Chunk& ch = c.chunks[k];
+        ch.s0 = cuts[k]; ch.s1 = cuts[k + 1];
+        ch.q0 = c.qoff[ch.s0]; ch.q1 = c.qoff[ch.s1]; ch.t0 = c.toff[ch.s0]; ch.t1 = c.toff[ch.s1];
+        ch.scattered = false;
+        ch.plan.clear();
+        for (int64_t s = ch.s0; s < ch.s1;) {
+            const int64_t e = std::min(ch.s1, s + SHORT_BLOCK);
+            const int qs = stride_for(c.len2[e - 1]);                 // ascending in len2
+            if (!ch.plan.empty() && ch.plan.back().qstride == qs) ch.plan.back().count += (int)(e - s);
+            else ch.plan.push_back(Launch{(int)s, (int)(e - s), qs});
+            s = e;
+        }
+    }
+    return BSW_OK;
+}
+
+// pack one chunk of a shard into pinned staging (host threads), flag N-containing pairs
+void pack_chunk(bsw_engine* eng, DevCtx& c, const Chunk& ch, const SeqPair* pairs, const uint8_t* seq_ref,
+                const uint8_t* seq_qer)
+{
+    (void)pairs;
+    const uint32_t* idx = c.idx.data();
+    const uint64_t* offr = eng->sb.offr.data();
+    const uint64_t* offq = eng->sb.offq.data();
+    eng->pool->for_range(ch.s1 - ch.s0, 1024, [&](int64_t b, int64_t e, int) {
+        b += ch.s0; e += ch.s0;
+        for (int64_t s = b; s < e; ++s) {
+            if (s + 16 < e) { __builtin_prefetch(&offq[idx[s + 16]], 0, 0); __builtin_prefetch(&offr[idx[s + 16]], 0, 0); }
+            if (s + 4 < e) {
+                const uint32_t nx = idx[s + 4];
+                __builtin_prefetch(seq_qer + offq[nx], 0, 0);
+                __builtin_prefetch(seq_ref + offr[nx], 0, 0);
+                __builtin_prefetch(seq_ref + offr[nx] + 64, 0, 0);
+            }
+            const uint32_t i = idx[s];
+            const int l2 = c.len2[s], l1 = c.len1[s];
+            const bool nq = pack2(seq_qer + offq[i], l2, c.q.h + c.qoff[s]);
+            const bool nr = pack2(seq_ref + offr[i], l1, c.t.h + c.toff[s]);
+            const int flag = (nq | nr) ? BSW_META_NFLAG : 0;
+            c.hasn[s] = (uint8_t)(flag != 0);
+            c.meta.h[s] = make_int4((int)c.qoff[s], (int)c.toff[s], l2 | (l1 << 16), c.h0[s] | flag);
+        }
+    });
+}
+
+int h2d_chunk(bsw_engine* eng, DevCtx& c, Chunk& ch)
+{
+    cudaStream_t st = c.st_copy;
+    CUDA_TRY(cudaMemcpyAsync(c.meta.d + ch.s0, c.meta.h + ch.s0, sizeof(int4) * (size_t)(ch.s1 - ch.s0), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.q.d + ch.q0, c.q.h + ch.q0, sizeof(uint32_t) * (ch.q1 - ch.q0), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.t.d + ch.t0, c.t.h + ch.t0, sizeof(uint32_t) * (ch.t1 - ch.t0), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(ch.ev_h2d, st));
+    eng->stats.h2d_bytes += (int64_t)(sizeof(int4) * (size_t)(ch.s1 - ch.s0) + 4 * ((ch.q1 - ch.q0) + (ch.t1 - ch.t0)));
+    return BSW_OK;
+}
+
+// launches of one chunk, spread over the compute streams; longest class first
+int launch_chunk(bsw_engine* eng, DevCtx& c, Chunk& ch, bool wait_h2d)
+{
+    int li = 0;
+    bool used[NSTREAMS] = {};
+    for (int k = (int)ch.plan.size() - 1; k >= 0; --k, ++li) {
+        const Launch& L = ch.plan[k];
+        const int si = li % NSTREAMS;
+        cudaStream_t st = c.st[si];
+        if (wait_h2d && !used[si]) CUDA_TRY(cudaStreamWaitEvent(st, ch.ev_h2d, 0));
+        used[si] = true;
+        const int grid = (L.count + SHORT_BLOCK - 1) / SHORT_BLOCK;
+        const size_t smem = (size_t)L.qstride * SHORT_BLOCK * sizeof(uint32_t);
+        bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, smem, st>>>(
+            c.meta.d, c.q.d, c.t.d, c.res.d, L.first, L.count, eng->kp, c.d_cells);
+        eng->stats.kernel_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return BSW_OK;
+}
+
+int d2h_chunk(bsw_engine* eng, DevCtx& c, Chunk& ch)
+{
+    for (int s = 0; s < NSTREAMS; ++s) {
+        CUDA_TRY(cudaEventRecord(c.ev_join[s], c.st[s]));
+        CUDA_TRY(cudaStreamWaitEvent(c.st_d2h, c.ev_join[s], 0));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c.res.h + ch.s0, c.res.d + ch.s0, sizeof(int4) * (size_t)(ch.s1 - ch.s0), cudaMemcpyDeviceToHost, c.st_d2h));
+    CUDA_TRY(cudaEventRecord(ch.ev_done, c.st_d2h));
+    eng->stats.d2h_bytes += (int64_t)(sizeof(int4) * (size_t)(ch.s1 - ch.s0));
+    return BSW_OK;
+}
+
+inline void write_result(SeqPair& sp, const int4 v)
+{
+    sp.score = (int16_t)(v.x & 0xffff);  sp.qle = (int16_t)(v.x >> 16);
+    sp.tle = (int16_t)(v.y & 0xffff);    sp.gtle = (int16_t)(v.y >> 16);
+    sp.gscore = (int16_t)(v.z & 0xffff); sp.max_off = (int16_t)(v.z >> 16);
+}
+
+void scatter_chunk(bsw_engine* eng, DevCtx& c, Chunk& ch, SeqPair* pairs)
+{
+    const uint32_t* idx = c.idx.data();
+    const int4* r = c.res.h;
+    eng->pool->for_range(ch.s1 - ch.s0, 4096, [&](int64_t b, int64_t e, int) {
+        b += ch.s0; e += ch.s0;
+        for (int64_t s = b; s < e; ++s) {
+            if (s + 8 < e) __builtin_prefetch(&pairs[idx[s + 8]].score, 1, 0);
+            if (!c.hasn[s]) write_result(pairs[idx[s]], r[s]);
+        }
+    });
+    ch.scattered = true;
+}
+
+// byte-staged pairs: short pairs with N + all long pairs.  Staging (host) and H2D.
+int stage_bytes(bsw_engine* eng, DevCtx& c, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer)
+{
+    (void)pairs;
+    c.pos_n.clear();
+    c.qmax_bytes_short = 0;
+    for (int64_t s = 0; s < c.n_short; ++s)
+        if (c.hasn[s]) { c.pos_n.push_back((uint32_t)s); c.qmax_bytes_short = std::max<int>(c.qmax_bytes_short, c.len2[s]); }
+    c.n_bytes_short = (int64_t)c.pos_n.size();
+    for (int64_t s = c.n_short; s < c.n; ++s) c.pos_n.push_back((uint32_t)s);
+    const size_t nb = c.pos_n.size();
+    if (nb == 0) return BSW_OK;
+    if (int rc = ensure(eng, c.meta_n, nb)) return rc;
+    if (int rc = ensure(eng, c.res_n, nb)) return rc;
+    uint64_t qo = 0, to = 0;
+    for (size_t k = 0; k < nb; ++k) {
+        const uint32_t s = c.pos_n[k];
+        c.meta_n.h[k] = make_int4((int)qo, (int)to, c.len2[s] | (c.len1[s] << 16), c.h0[s]);
+        qo += ((uint64_t)c.len2[s] + 7) & ~3ull; to += ((uint64_t)c.len1[s] + 7) & ~3ull;   // 4-byte aligned, >= 4 B slack
+    }
+    if (qo > 0x7fffffffull || to > 0x7fffffffull) { eng->err = "too many byte-staged bases in one batch"; return BSW_ERR_PARAM; }
+    c.qb_bytes = qo; c.tb_bytes = to;
+    if (int rc = ensure(eng, c.qb, c.qb_bytes + 16)) return rc;
+    if (int rc = ensure(eng, c.tb, c.tb_bytes + 16)) return rc;
+    eng->pool->for_range((int64_t)nb, 256, [&](int64_t b, int64_t e, int) {
+        for (int64_t k = b; k < e; ++k) {
+            const uint32_t s = c.pos_n[k], i = c.idx[s];
+            memcpy(c.qb.h + c.meta_n.h[k].x, seq_qer + eng->sb.offq[i], (size_t)c.len2[s]);
+            memcpy(c.tb.h + c.meta_n.h[k].y, seq_ref + eng->sb.offr[i], (size_t)c.len1[s]);
+        }
+    });
+    if (c.n_long > 0) {
+        const int qmax = c.len2[c.n - 1];
+        c.long_stride = (qmax + 12) & ~3;
+        int64_t blocks = std::min<int64_t>((c.n_long + LONG_WARPS - 1) / LONG_WARPS, (int64_t)c.sms * 8);
+        const int64_t cap_words = (int64_t)(256ll << 20) / 4;       // <= 256 MB of eh rows
+        blocks = std::max<int64_t>(1, std::min(blocks, cap_words / ((int64_t)c.long_stride * LONG_WARPS)));
+        c.long_blocks = (int)blocks;
+        if (int rc = ensure(eng, c.scratch, (size_t)blocks * LONG_WARPS * c.long_stride, false)) return rc;
+    }
+    cudaStream_t st = c.st_copy;
+    CUDA_TRY(cudaMemcpyAsync(c.meta_n.d, c.meta_n.h, sizeof(int4) * nb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.qb.d, c.qb.h, c.qb_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.tb.d, c.tb.h, c.tb_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(c.ev_a, st));
+    eng->stats.h2d_bytes += (int64_t)(sizeof(int4) * nb + c.qb_bytes + c.tb_bytes);
+    return BSW_OK;
+}
+
+int launch_bytes(bsw_engine* eng, DevCtx& c, bool wait_h2d)
+{
+    if (c.pos_n.empty()) return BSW_OK;
+    cudaStream_t st = c.st[0];
+    if (wait_h2d) CUDA_TRY(cudaStreamWaitEvent(st, c.ev_a, 0));
+    if (c.n_bytes_short > 0) {
+        const int grid = (int)((c.n_bytes_short + SHORT_BLOCK - 1) / SHORT_BLOCK);
+        const size_t smem = (size_t)stride_for(c.qmax_bytes_short) * SHORT_BLOCK * sizeof(uint32_t);
+        bsw_short_kernel<SHORT_BLOCK, true><<<grid, SHORT_BLOCK, smem, st>>>(
+            c.meta_n.d, reinterpret_cast<const uint32_t*>(c.qb.d), reinterpret_cast<const uint32_t*>(c.tb.d),
+            c.res_n.d, 0, (int)c.n_bytes_short, eng->kp, c.d_cells);
+        eng->stats.kernel_launches++;
+    }
+    if (c.n_long > 0) {
+        CUDA_TRY(cudaMemsetAsync(c.d_queue, 0, sizeof(unsigned int), st));
+        bsw_long_kernel<<<c.long_blocks, LONG_WARPS * 32, 0, st>>>(
+            c.meta_n.d + c.n_bytes_short, c.qb.d, c.tb.d, c.res_n.d + c.n_bytes_short, (int)c.n_long, eng->kp,
+            c.scratch.d, c.long_stride, c.d_queue, c.d_cells);
+        eng->stats.kernel_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return BSW_OK;
+}
+
+int d2h_bytes(bsw_engine* eng, DevCtx& c)
+{
+    if (c.pos_n.empty()) return BSW_OK;
+    CUDA_TRY(cudaEventRecord(c.ev_join[0], c.st[0]));
+    CUDA_TRY(cudaStreamWaitEvent(c.st_d2h, c.ev_join[0], 0));
+    CUDA_TRY(cudaMemcpyAsync(c.res_n.h, c.res_n.d, sizeof(int4) * c.pos_n.size(), cudaMemcpyDeviceToHost, c.st_d2h));
+    eng->stats.d2h_bytes += (int64_t)(sizeof(int4) * c.pos_n.size());
+    return BSW_OK;
+}
+
+void scatter_bytes(bsw_engine* eng, DevCtx& c, SeqPair* pairs)
+{
+    eng->pool->for_range((int64_t)c.pos_n.size(), 4096, [&](int64_t b, int64_t e, int) {
+        for (int64_t k = b; k < e; ++k) write_result(pairs[c.idx[c.pos_n[k]]], c.res_n.h[k]);
+    });
+}
+
+// Splits the sorted batch across the engine's devices (views copied per shard).
+int build_shards(bsw_engine* eng)
+{
+    SortedBatch& sb = eng->sb;
+    const int ndev = (int)eng->devs.size();
+    if (ndev == 1) {
+        DevCtx& c = eng->devs[0];
+        c.n = sb.n;
+        c.idx.swap(sb.idx); c.len2.swap(sb.len2); c.len1.swap(sb.len1); c.h0.swap(sb.h0);
+        return BSW_OK;
+    }
+    std::vector<std::vector<int64_t>> blocks_of;
+    partition_blocks(sb, eng->w, ndev, blocks_of);
+    for (int g = 0; g < ndev; ++g) {
+        DevCtx& c = eng->devs[g];
+        size_t cnt = 0;
+        for (int64_t b : blocks_of[g]) cnt += (size_t)(std::min(sb.n, b * 1024 + 1024) - b * 1024);
+        c.idx.reserve(cnt); c.len2.reserve(cnt); c.len1.reserve(cnt); c.h0.reserve(cnt);
+        size_t pos = 0;
+        for (int64_t b : blocks_of[g]) {
+            const int64_t lo = b * 1024, hi = std::min(sb.n, lo + 1024);
+            const size_t m = (size_t)(hi - lo);
+            memcpy(c.idx.data() + pos, sb.idx.data() + lo, m * sizeof(uint32_t));
+            memcpy(c.len2.data() + pos, sb.len2.data() + lo, m * sizeof(uint16_t));
+            memcpy(c.len1.data() + pos, sb.len1.data() + lo, m * sizeof(uint16_t));
+            memcpy(c.h0.data() + pos, sb.h0.data() + lo, m * sizeof(uint16_t));
+            pos += m;
+        }
+        c.n = (int64_t)cnt;
+    }
+    return BSW_OK;
+}
+
+int begin_batch(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
+                int64_t n, int32_t w)
+{
+    eng->err.clear();
+    eng->staged = false; eng->ran = false;
+    if (n < 0 || w < 0 || (n > 0 && (!pairs || !seq_ref || !seq_qer))) { eng->err = "bad arguments"; return BSW_ERR_PARAM; }
+    if (n > 0x7fffffff) { eng->err = "more than 2^31-1 pairs per call"; return BSW_ERR_PARAM; }
+    bsw_stats& S = eng->stats;
+    memset(&S, 0, sizeof(S));
+    S.pairs = n;
+    eng->n = n; eng->w = w; eng->kp.w = w;
+    const double t0 = now_ms();
+    build_sorted_batch(*eng->pool, pairs, n, eng->p.match, eng->sb);
+    if (!eng->sb.domain_ok) {
+        eng->err = "pair outside the domain: need 1<=len1,len2<=32767, h0>=1, h0+len2*match<=32767, offsets>=0 (bandedSWA.h:84, SURVEY 8b)";
+        return BSW_ERR_DOMAIN;
+    }
+    S.cells_nominal = eng->sb.cells_nominal;
+    if (int rc = build_shards(eng)) return rc;
+    S.ms_sort = now_ms() - t0;
+    return BSW_OK;
+}
+
 } // namespace
 
 extern "C" {
 
-const char* bsw_version(void) { return "bsw_b200 0.1 sm_100a"; }
+const char* bsw_version(void) { return "bsw_b200 0.2 sm_100a"; }
 
 void bsw_default_params(bsw_params* p)
 {
@@ -232,7 +559,7 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
     k.zdrop = params->zdrop; k.end_bonus = params->end_bonus; k.zmode = params->zdrop_mode;
     k.mx = std::max(std::max(k.match, k.mismatch_neg), k.ambig);
     k.w = 0;
-    eng->nthreads = auto_threads(params->host_threads);
+    eng->pool.reset(new ThreadPool(auto_threads(params->host_threads)));
     eng->short_max = params->long_min_qlen > 0 ? std::min(params->long_min_qlen - 1, SHORT_MAX_QLEN) : SHORT_MAX_QLEN;
     memset(&eng->stats, 0, sizeof(eng->stats));
 
@@ -253,13 +580,19 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
             return fail(BSW_ERR_CUDA, std::string("device ") + prop.name +
                                       " is not sm_100: this library carries sm_100a code only");
         }
+        c.sms = prop.multiProcessorCount;
+        ok = ok && cudaStreamCreateWithFlags(&c.st_copy, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&c.st_d2h, cudaStreamNonBlocking) == cudaSuccess;
         for (int s = 0; ok && s < NSTREAMS; ++s) {
             ok = cudaStreamCreateWithFlags(&c.st[s], cudaStreamNonBlocking) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&c.ev_join[s], cudaEventDisableTiming) == cudaSuccess;
         }
-        ok = ok && cudaEventCreate(&c.ev_h2d0) == cudaSuccess && cudaEventCreate(&c.ev_h2d1) == cudaSuccess;
+        for (int k2 = 0; ok && k2 < MAX_CHUNKS; ++k2) {
+            ok = cudaEventCreateWithFlags(&c.chunks[k2].ev_h2d, cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&c.chunks[k2].ev_done, cudaEventDisableTiming) == cudaSuccess;
+        }
+        ok = ok && cudaEventCreate(&c.ev_a) == cudaSuccess && cudaEventCreate(&c.ev_b) == cudaSuccess;
         ok = ok && cudaEventCreate(&c.ev_k0) == cudaSuccess && cudaEventCreate(&c.ev_k1) == cudaSuccess;
-        ok = ok && cudaEventCreate(&c.ev_d2h0) == cudaSuccess && cudaEventCreate(&c.ev_d2h1) == cudaSuccess;
         ok = ok && cudaMalloc((void**)&c.d_cells, sizeof(unsigned long long)) == cudaSuccess;
         ok = ok && cudaMalloc((void**)&c.d_queue, sizeof(unsigned int)) == cudaSuccess;
         ok = ok && cudaHostAlloc((void**)&c.h_cells, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
@@ -278,17 +611,22 @@ void bsw_destroy(bsw_engine* eng)
     if (!eng) return;
     for (DevCtx& c : eng->devs) {
         cudaSetDevice(c.dev);
+        cudaDeviceSynchronize();
+        for (cudaStream_t s : {c.st_copy, c.st_d2h}) if (s) cudaStreamDestroy(s);
         for (int s = 0; s < NSTREAMS; ++s) {
-            if (c.st[s]) { cudaStreamSynchronize(c.st[s]); cudaStreamDestroy(c.st[s]); }
+            if (c.st[s]) cudaStreamDestroy(c.st[s]);
             if (c.ev_join[s]) cudaEventDestroy(c.ev_join[s]);
         }
-        for (cudaEvent_t e : {c.ev_h2d0, c.ev_h2d1, c.ev_k0, c.ev_k1, c.ev_d2h0, c.ev_d2h1})
+        for (Chunk& ch : c.chunks) {
+            if (ch.ev_h2d) cudaEventDestroy(ch.ev_h2d);
+            if (ch.ev_done) cudaEventDestroy(ch.ev_done);
+        }
+        for (cudaEvent_t e : {c.ev_a, c.ev_b, c.ev_k0, c.ev_k1})
             if (e) cudaEventDestroy(e);
-        release(c.meta); release(c.res); release(c.meta_n); release(c.q); release(c.t);
-        release(c.qb); release(c.tb); release(c.pos_n);
+        release(c.meta); release(c.res); release(c.meta_n); release(c.res_n); release(c.q); release(c.t);
+        release(c.qb); release(c.tb); release(c.scratch);
         if (c.d_cells) cudaFree(c.d_cells);
         if (c.d_queue) cudaFree(c.d_queue);
-        release(c.scratch);
         if (c.h_cells) cudaFreeHost(c.h_cells);
     }
     delete eng;
@@ -302,241 +640,42 @@ int bsw_get_stats(const bsw_engine* eng, bsw_stats* out)
 }
 
 // ------------------------------------------------------------------------------------------
-// stage: validate, bucket, partition across devices, pack into pinned staging, async H2D
+// resident form: stage (host -> HBM), run (kernels only, repeatable), fetch (HBM -> SeqPair[])
 // ------------------------------------------------------------------------------------------
 int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
               int64_t n, int32_t w)
 {
     if (!eng) return BSW_ERR_PARAM;
-    eng->err.clear();
-    eng->staged = false; eng->ran = false;
-    if (n < 0 || w < 0 || (n > 0 && (!pairs || !seq_ref || !seq_qer))) { eng->err = "bad arguments"; return BSW_ERR_PARAM; }
-    if (n > 0x7fffffff) { eng->err = "more than 2^31-1 pairs per call"; return BSW_ERR_PARAM; }
     const double t_begin = now_ms();
+    if (int rc = begin_batch(eng, pairs, seq_ref, seq_qer, n, w)) return rc;
     bsw_stats& S = eng->stats;
-    memset(&S, 0, sizeof(S));
-    S.pairs = n;
-    eng->n = n; eng->w = w;
-    eng->kp.w = w;
-    const int nt = eng->nthreads;
-    const int ndev = (int)eng->devs.size();
-
-    // ---- domain check + nominal cells
-    {
-        std::vector<int64_t> nominal((size_t)nt + 1, 0);
-        std::vector<int> bad((size_t)nt + 1, 0);
-        const int match = eng->p.match;
-        parallel_chunks(n, 1 << 14, nt, [&](int64_t b, int64_t e, int t) {
-            int64_t acc = 0; int bd = 0;
-            for (int64_t k = b; k < e; ++k) {
-                const SeqPair& sp = pairs[k];
-                if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.h0 < 1 ||
-                    (int64_t)sp.h0 + (int64_t)sp.len2 * match > 32767 || sp.idr < 0 || sp.idq < 0) bd = 1;
-                acc += (int64_t)sp.len1 * sp.len2;
-            }
-            nominal[t] += acc; bad[t] |= bd;
-        });
-        for (int t = 0; t <= nt; ++t) {
-            S.cells_nominal += nominal[t];
-            if (bad[t]) {
-                eng->err = "pair outside the domain: need 1<=len1,len2<=32767, h0>=1, h0+len2*match<=32767 (bandedSWA.h:84, SURVEY 8b)";
-                return BSW_ERR_DOMAIN;
-            }
-        }
-    }
-
-    // ---- bucket + partition
-    double t0 = now_ms();
-    eng->order.resize((size_t)n);
-    eng->shard_begin.assign((size_t)ndev + 1, 0);
-    if (ndev == 1) {
-        bucket_order(pairs, n, eng->order.data(), nt);
-        eng->shard_begin[1] = n;
-    } else {
-        int rc = bsw_partition(pairs, n, w, ndev, eng->order.data(), eng->shard_begin.data());
-        if (rc != BSW_OK) { eng->err = "partition failed"; return rc; }
-    }
-    S.ms_sort = now_ms() - t0;
-
-    // ---- per device: offsets, pack, H2D
-    for (int d = 0; d < ndev; ++d) {
-        DevCtx& c = eng->devs[d];
-        CUDA_TRY(cudaSetDevice(c.dev));
-        if (int rc = set_kernel_attrs(eng, c)) return rc;
-        c.first = eng->shard_begin[d];
-        c.n = eng->shard_begin[d + 1] - c.first;
-        c.plan.clear();
-        c.n_bytes_pairs = 0; c.q_words = c.t_words = c.qb_bytes = c.tb_bytes = 0;
+    for (DevCtx& c : eng->devs) {
+        if (int rc = prepare_shard(eng, c, false)) return rc;
         if (c.n == 0) continue;
-        const int64_t* ord = eng->order.data() + c.first;
-        double tp0 = now_ms();
-        if (int rc = ensure(eng, c.meta, (size_t)c.n)) return rc;
-        if (int rc = ensure(eng, c.res, (size_t)c.n)) return rc;
-        // word offsets (serial prefix over the sorted order); queries longer than the short
-        // kernel's shared-memory limit sit at the end of the order and are staged as bytes only
-        std::vector<uint32_t> qoff((size_t)c.n + 1), toff((size_t)c.n + 1);
-        {
-            uint64_t qo = 0, to = 0;
-            c.n_short = c.n;
-            for (int64_t s = 0; s < c.n; ++s) {
-                const SeqPair& sp = pairs[ord[s]];
-                qoff[s] = (uint32_t)qo; toff[s] = (uint32_t)to;
-                if (sp.len2 > eng->short_max) { if (c.n_short == c.n) c.n_short = s; continue; }
-                qo += (uint64_t)(sp.len2 + 15) >> 4; to += (uint64_t)(sp.len1 + 15) >> 4;
-            }
-            if (qo > 0xffffffffull || to > 0xffffffffull) { eng->err = "batch too large for 32-bit word offsets"; return BSW_ERR_PARAM; }
-            qoff[c.n] = (uint32_t)qo; toff[c.n] = (uint32_t)to;
-            c.q_words = qo; c.t_words = to;
+        const double tp = now_ms();
+        CUDA_TRY(cudaEventRecord(c.ev_a, c.st_copy));
+        for (int k = 0; k < c.nchunks; ++k) {
+            pack_chunk(eng, c, c.chunks[k], pairs, seq_ref, seq_qer);
+            if (int rc = h2d_chunk(eng, c, c.chunks[k])) return rc;
         }
-        if (int rc = ensure(eng, c.q, c.q_words + 4)) return rc;
-        if (int rc = ensure(eng, c.t, c.t_words + 4)) return rc;
-        std::vector<uint8_t> hasn((size_t)c.n, 0);
-        parallel_chunks(c.n_short, 2048, nt, [&](int64_t b, int64_t e, int) {
-            for (int64_t s = b; s < e; ++s) {
-                const SeqPair& sp = pairs[ord[s]];
-                bool nq = pack2(seq_qer + sp.idq, sp.len2, c.q.h + qoff[s]);
-                bool nr = pack2(seq_ref + sp.idr, sp.len1, c.t.h + toff[s]);
-                hasn[s] = (uint8_t)(nq | nr);
-                c.meta.h[s] = make_int4((int)qoff[s], (int)toff[s], sp.len2 | (sp.len1 << 16), sp.h0);
-            }
-        });
-        // byte-staged pairs: short pairs containing N (recomputed by the byte-sequence variant of
-        // the short kernel) followed by all long pairs (warp-per-pair kernel, N-safe by construction)
-        std::vector<int64_t> nlist;
-        for (int64_t s = 0; s < c.n_short; ++s) if (hasn[s]) nlist.push_back(s);
-        c.n_bytes_short = (int64_t)nlist.size();
-        for (int64_t s = c.n_short; s < c.n; ++s) nlist.push_back(s);
-        c.n_long = c.n - c.n_short;
-        c.n_bytes_pairs = (int64_t)nlist.size();
-        if (!nlist.empty()) {
-            if (int rc = ensure(eng, c.meta_n, nlist.size())) return rc;
-            if (int rc = ensure(eng, c.pos_n, nlist.size())) return rc;
-            uint64_t qo = 0, to = 0;
-            for (size_t k = 0; k < nlist.size(); ++k) {
-                const SeqPair& sp = pairs[ord[nlist[k]]];
-                c.meta_n.h[k] = make_int4((int)qo, (int)to, sp.len2 | (sp.len1 << 16), sp.h0);
-                c.pos_n.h[k] = (int)nlist[k];
-                qo += ((uint64_t)sp.len2 + 7) & ~3ull; to += ((uint64_t)sp.len1 + 7) & ~3ull;   // 4-byte aligned, >= 4 B slack
-            }
-            if (qo > 0x7fffffffull || to > 0x7fffffffull) { eng->err = "too many N-containing bases in one batch"; return BSW_ERR_PARAM; }
-            c.qb_bytes = qo; c.tb_bytes = to;
-            if (int rc = ensure(eng, c.qb, c.qb_bytes + 16)) return rc;
-            if (int rc = ensure(eng, c.tb, c.tb_bytes + 16)) return rc;
-            for (size_t k = 0; k < nlist.size(); ++k) {
-                const SeqPair& sp = pairs[ord[nlist[k]]];
-                memcpy(c.qb.h + c.meta_n.h[k].x, seq_qer + sp.idq, (size_t)sp.len2);
-                memcpy(c.tb.h + c.meta_n.h[k].y, seq_ref + sp.idr, (size_t)sp.len1);
-            }
-        }
-        S.ms_pack += now_ms() - tp0;
-
-        // launch plan: blocks of SHORT_BLOCK consecutive pairs, merged by shared-memory class
-        {
-            int64_t s = 0;
-            while (s < c.n_short) {
-                const int64_t blk_end = std::min<int64_t>(c.n_short, s + SHORT_BLOCK);
-                const int qmax = pairs[ord[blk_end - 1]].len2;       // ascending in len2
-                const int qs = stride_for(qmax);
-                if (!c.plan.empty() && c.plan.back().qstride == qs && !c.plan.back().bytes)
-                    c.plan.back().count += (int)(blk_end - s);
-                else
-                    c.plan.push_back(Launch{(int)s, (int)(blk_end - s), qs, false});
-                s = blk_end;
-            }
-            if (c.n_bytes_short > 0) {
-                int qmax = 0;
-                for (int64_t k = 0; k < c.n_bytes_short; ++k) qmax = std::max(qmax, pairs[ord[nlist[k]]].len2);
-                c.plan.push_back(Launch{0, (int)c.n_bytes_short, stride_for(qmax), true});
-            }
-            if (c.n_long > 0) {
-                const int qmax = pairs[ord[c.n - 1]].len2;
-                c.long_stride = (qmax + 12) & ~3;
-                cudaDeviceProp prop{};
-                CUDA_TRY(cudaGetDeviceProperties(&prop, c.dev));
-                int64_t blocks = std::min<int64_t>((c.n_long + LONG_WARPS - 1) / LONG_WARPS,
-                                                   (int64_t)prop.multiProcessorCount * 8);
-                const int64_t cap_words = (int64_t)(256ll << 20) / 4;       // <= 256 MB of eh rows
-                blocks = std::max<int64_t>(1, std::min(blocks, cap_words / ((int64_t)c.long_stride * LONG_WARPS)));
-                c.long_blocks = (int)blocks;
-                if (int rc = ensure(eng, c.scratch, (size_t)blocks * LONG_WARPS * c.long_stride, false)) return rc;
-            }
-        }
-
-        // async H2D on stream 0
-        cudaStream_t st = c.st[0];
-        CUDA_TRY(cudaEventRecord(c.ev_h2d0, st));
-        CUDA_TRY(cudaMemcpyAsync(c.meta.d, c.meta.h, sizeof(int4) * (size_t)c.n, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c.q.d, c.q.h, sizeof(uint32_t) * c.q_words, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c.t.d, c.t.h, sizeof(uint32_t) * c.t_words, cudaMemcpyHostToDevice, st));
-        S.h2d_bytes += (int64_t)(sizeof(int4) * (size_t)c.n + 4 * (c.q_words + c.t_words));
-        if (!nlist.empty()) {
-            CUDA_TRY(cudaMemcpyAsync(c.meta_n.d, c.meta_n.h, sizeof(int4) * nlist.size(), cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(c.pos_n.d, c.pos_n.h, sizeof(int) * nlist.size(), cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(c.qb.d, c.qb.h, c.qb_bytes, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(c.tb.d, c.tb.h, c.tb_bytes, cudaMemcpyHostToDevice, st));
-            S.h2d_bytes += (int64_t)(20 * nlist.size() + c.qb_bytes + c.tb_bytes);
-        }
-        CUDA_TRY(cudaEventRecord(c.ev_h2d1, st));
-        S.n_short += (int32_t)c.n_short;
-        S.n_long += (int32_t)c.n_long;
+        CUDA_TRY(cudaEventRecord(c.ev_b, c.st_copy));
+        S.ms_pack += now_ms() - tp;
     }
     for (DevCtx& c : eng->devs) {
         if (c.n == 0) continue;
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaStreamSynchronize(c.st[0]));
-        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_h2d0, c.ev_h2d1));
+        CUDA_TRY(cudaStreamSynchronize(c.st_copy));
+        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_a, c.ev_b));
         S.ms_h2d = std::max(S.ms_h2d, (double)ms);
+        const double tp = now_ms();
+        if (int rc = stage_bytes(eng, c, pairs, seq_ref, seq_qer)) return rc;
+        CUDA_TRY(cudaStreamSynchronize(c.st_copy));
+        S.ms_pack += now_ms() - tp;
+        S.n_short += (int32_t)c.n_short;
+        S.n_long += (int32_t)c.n_long;
     }
     eng->staged = true;
     S.ms_total = now_ms() - t_begin;
-    return BSW_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// run: DP kernels only, on every device's staged shard; repeatable
-// ------------------------------------------------------------------------------------------
-static int launch_device(bsw_engine* eng, DevCtx& c)
-{
-    CUDA_TRY(cudaSetDevice(c.dev));
-    CUDA_TRY(cudaMemsetAsync(c.d_cells, 0, sizeof(unsigned long long), c.st[0]));
-    CUDA_TRY(cudaEventRecord(c.ev_k0, c.st[0]));
-    for (int s = 1; s < NSTREAMS; ++s) CUDA_TRY(cudaStreamWaitEvent(c.st[s], c.ev_k0, 0));
-    int li = 0;
-    // longest class first so the tail of the grid is made of the cheapest blocks
-    for (int k = (int)c.plan.size() - 1; k >= 0; --k, ++li) {
-        const Launch& L = c.plan[k];
-        cudaStream_t st = c.st[L.bytes ? 0 : li % NSTREAMS];
-        const int grid = (L.count + SHORT_BLOCK - 1) / SHORT_BLOCK;
-        const size_t smem = (size_t)L.qstride * SHORT_BLOCK * sizeof(uint32_t);
-        if (L.bytes)
-            continue;   // byte-variant launches go last, see below
-        bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, smem, st>>>(
-            c.meta.d, c.q.d, c.t.d, c.res.d, nullptr, L.first, L.count, eng->kp, c.d_cells);
-        eng->stats.kernel_launches++;
-    }
-    for (int s = 1; s < NSTREAMS; ++s) {
-        CUDA_TRY(cudaEventRecord(c.ev_join[s], c.st[s]));
-        CUDA_TRY(cudaStreamWaitEvent(c.st[0], c.ev_join[s], 0));
-    }
-    for (const Launch& L : c.plan) {
-        if (!L.bytes) continue;
-        const int grid = (L.count + SHORT_BLOCK - 1) / SHORT_BLOCK;
-        const size_t smem = (size_t)L.qstride * SHORT_BLOCK * sizeof(uint32_t);
-        bsw_short_kernel<SHORT_BLOCK, true><<<grid, SHORT_BLOCK, smem, c.st[0]>>>(
-            c.meta_n.d, reinterpret_cast<const uint32_t*>(c.qb.d), reinterpret_cast<const uint32_t*>(c.tb.d),
-            c.res.d, c.pos_n.d, L.first, L.count, eng->kp, c.d_cells);
-        eng->stats.kernel_launches++;
-    }
-    if (c.n_long > 0) {
-        CUDA_TRY(cudaMemsetAsync(c.d_queue, 0, sizeof(unsigned int), c.st[0]));
-        bsw_long_kernel<<<c.long_blocks, LONG_WARPS * 32, 0, c.st[0]>>>(
-            c.meta_n.d + c.n_bytes_short, c.qb.d, c.tb.d, c.res.d, c.pos_n.d + c.n_bytes_short,
-            (int)c.n_long, eng->kp, c.scratch.d, c.long_stride, c.d_queue, c.d_cells);
-        eng->stats.kernel_launches++;
-    }
-    CUDA_TRY(cudaEventRecord(c.ev_k1, c.st[0]));
-    CUDA_TRY(cudaMemcpyAsync(c.h_cells, c.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.st[0]));
-    CUDA_TRY(cudaGetLastError());
     return BSW_OK;
 }
 
@@ -546,73 +685,140 @@ int bsw_run_staged(bsw_engine* eng)
     if (!eng->staged) { eng->err = "bsw_run_staged before bsw_stage"; return BSW_ERR_STATE; }
     bsw_stats& S = eng->stats;
     S.kernel_launches = 0; S.ms_kernel = 0; S.cells_effective = 0;
-    for (DevCtx& c : eng->devs)
-        if (c.n) { if (int rc = launch_device(eng, c)) return rc; }
+    for (DevCtx& c : eng->devs) {
+        if (c.n == 0) continue;
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaMemsetAsync(c.d_cells, 0, sizeof(unsigned long long), c.st[0]));
+        CUDA_TRY(cudaEventRecord(c.ev_k0, c.st[0]));
+        for (int s = 1; s < NSTREAMS; ++s) CUDA_TRY(cudaStreamWaitEvent(c.st[s], c.ev_k0, 0));
+        for (int k = c.nchunks - 1; k >= 0; --k)
+            if (int rc = launch_chunk(eng, c, c.chunks[k], false)) return rc;
+        for (int s = 1; s < NSTREAMS; ++s) {
+            CUDA_TRY(cudaEventRecord(c.ev_join[s], c.st[s]));
+            CUDA_TRY(cudaStreamWaitEvent(c.st[0], c.ev_join[s], 0));
+        }
+        if (int rc = launch_bytes(eng, c, false)) return rc;
+        CUDA_TRY(cudaEventRecord(c.ev_k1, c.st[0]));
+        CUDA_TRY(cudaMemcpyAsync(c.h_cells, c.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.st[0]));
+    }
     for (DevCtx& c : eng->devs) {
         if (c.n == 0) continue;
         CUDA_TRY(cudaSetDevice(c.dev));
         CUDA_TRY(cudaStreamSynchronize(c.st[0]));
         float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_k0, c.ev_k1));
         S.ms_kernel = std::max(S.ms_kernel, (double)ms);
-        // N-containing pairs are computed twice (2-bit pass result is overwritten); count them once
         S.cells_effective += (int64_t)*c.h_cells;
     }
     eng->ran = true;
     return BSW_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// fetch: D2H of the packed results, scatter into the caller's array in input order
-// ------------------------------------------------------------------------------------------
 int bsw_fetch(bsw_engine* eng, SeqPair* pairs, int64_t n)
 {
     if (!eng) return BSW_ERR_PARAM;
     if (!eng->ran) { eng->err = "bsw_fetch before bsw_run_staged"; return BSW_ERR_STATE; }
     if (n != eng->n || (n > 0 && !pairs)) { eng->err = "bsw_fetch: pair count differs from the staged batch"; return BSW_ERR_PARAM; }
     bsw_stats& S = eng->stats;
-    S.d2h_bytes = 0; S.ms_d2h = 0;
+    S.d2h_bytes = 0; S.ms_d2h = 0; S.ms_scatter = 0;
     for (DevCtx& c : eng->devs) {
         if (c.n == 0) continue;
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaEventRecord(c.ev_d2h0, c.st[0]));
-        CUDA_TRY(cudaMemcpyAsync(c.res.h, c.res.d, sizeof(int4) * (size_t)c.n, cudaMemcpyDeviceToHost, c.st[0]));
-        CUDA_TRY(cudaEventRecord(c.ev_d2h1, c.st[0]));
-        S.d2h_bytes += (int64_t)(sizeof(int4) * (size_t)c.n);
+        CUDA_TRY(cudaEventRecord(c.ev_a, c.st_d2h));
+        for (int k = 0; k < c.nchunks; ++k) if (int rc = d2h_chunk(eng, c, c.chunks[k])) return rc;
+        if (int rc = d2h_bytes(eng, c)) return rc;
+        CUDA_TRY(cudaEventRecord(c.ev_b, c.st_d2h));
     }
-    double ts = 0;
     for (DevCtx& c : eng->devs) {
         if (c.n == 0) continue;
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaStreamSynchronize(c.st[0]));
-        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_d2h0, c.ev_d2h1));
+        CUDA_TRY(cudaStreamSynchronize(c.st_d2h));
+        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_a, c.ev_b));
         S.ms_d2h = std::max(S.ms_d2h, (double)ms);
         const double t0 = now_ms();
-        const int64_t* ord = eng->order.data() + c.first;
-        const int4* r = c.res.h;
-        parallel_chunks(c.n, 1 << 13, eng->nthreads, [&](int64_t b, int64_t e, int) {
-            for (int64_t s = b; s < e; ++s) {
-                SeqPair& sp = pairs[ord[s]];
-                const int4 v = r[s];
-                sp.score = (int16_t)(v.x & 0xffff);  sp.qle = (int16_t)(v.x >> 16);
-                sp.tle = (int16_t)(v.y & 0xffff);    sp.gtle = (int16_t)(v.y >> 16);
-                sp.gscore = (int16_t)(v.z & 0xffff); sp.max_off = (int16_t)(v.z >> 16);
-            }
-        });
-        ts += now_ms() - t0;
+        for (int k = 0; k < c.nchunks; ++k) scatter_chunk(eng, c, c.chunks[k], pairs);
+        scatter_bytes(eng, c, pairs);
+        S.ms_scatter += now_ms() - t0;
     }
-    S.ms_scatter = ts;
     return BSW_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// the hot path: host buffers in, results in place.  Chunk pipeline (see the file header).
+// ------------------------------------------------------------------------------------------
 int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
                int64_t n, int32_t w)
 {
     if (!eng) return BSW_ERR_PARAM;
-    const double t0 = now_ms();
-    if (int rc = bsw_stage(eng, pairs, seq_ref, seq_qer, n, w)) return rc;
-    if (int rc = bsw_run_staged(eng)) return rc;
-    if (int rc = bsw_fetch(eng, pairs, n)) return rc;
-    eng->stats.ms_total = now_ms() - t0;
+    const double t_begin = now_ms();
+    if (int rc = begin_batch(eng, pairs, seq_ref, seq_qer, n, w)) return rc;
+    bsw_stats& S = eng->stats;
+    for (DevCtx& c : eng->devs) {
+        if (int rc = prepare_shard(eng, c, true)) return rc;
+        if (c.n == 0) continue;
+        CUDA_TRY(cudaMemsetAsync(c.d_cells, 0, sizeof(unsigned long long), c.st_copy));
+        CUDA_TRY(cudaEventRecord(c.ev_k0, c.st_copy));
+        for (int s = 0; s < NSTREAMS; ++s) CUDA_TRY(cudaStreamWaitEvent(c.st[s], c.ev_k0, 0));
+    }
+    // longest chunk first on every device; the devices' pipelines are interleaved chunk by chunk
+    int max_chunks = 0;
+    for (DevCtx& c : eng->devs) max_chunks = std::max(max_chunks, c.nchunks);
+    for (int step = 0; step < max_chunks; ++step) {
+        for (DevCtx& c : eng->devs) {
+            const int k = c.nchunks - 1 - step;
+            if (k < 0) continue;
+            CUDA_TRY(cudaSetDevice(c.dev));
+            double t0 = now_ms();
+            pack_chunk(eng, c, c.chunks[k], pairs, seq_ref, seq_qer);
+            S.ms_pack += now_ms() - t0;
+            if (int rc = h2d_chunk(eng, c, c.chunks[k])) return rc;
+            if (int rc = launch_chunk(eng, c, c.chunks[k], true)) return rc;
+            if (int rc = d2h_chunk(eng, c, c.chunks[k])) return rc;
+            // scatter whatever already came back while the GPU works on this chunk
+            t0 = now_ms();
+            for (int j = c.nchunks - 1; j > k; --j) {
+                Chunk& done = c.chunks[j];
+                if (!done.scattered && cudaEventQuery(done.ev_done) == cudaSuccess) scatter_chunk(eng, c, done, pairs);
+            }
+            S.ms_scatter += now_ms() - t0;
+        }
+    }
+    for (DevCtx& c : eng->devs) {
+        if (c.n == 0) continue;
+        CUDA_TRY(cudaSetDevice(c.dev));
+        const double t0 = now_ms();
+        if (int rc = stage_bytes(eng, c, pairs, seq_ref, seq_qer)) return rc;
+        S.ms_pack += now_ms() - t0;
+        if (int rc = launch_bytes(eng, c, true)) return rc;
+        if (int rc = d2h_bytes(eng, c)) return rc;
+        for (int s = 0; s < NSTREAMS; ++s) {
+            CUDA_TRY(cudaEventRecord(c.ev_join[s], c.st[s]));
+            CUDA_TRY(cudaStreamWaitEvent(c.st_d2h, c.ev_join[s], 0));
+        }
+        CUDA_TRY(cudaEventRecord(c.ev_k1, c.st_d2h));
+        CUDA_TRY(cudaMemcpyAsync(c.h_cells, c.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.st_d2h));
+        S.n_short += (int32_t)c.n_short;
+        S.n_long += (int32_t)c.n_long;
+    }
+    for (DevCtx& c : eng->devs) {
+        if (c.n == 0) continue;
+        CUDA_TRY(cudaSetDevice(c.dev));
+        for (int k = c.nchunks - 1; k >= 0; --k) {
+            Chunk& ch = c.chunks[k];
+            if (ch.scattered) continue;
+            CUDA_TRY(cudaEventSynchronize(ch.ev_done));
+            const double t0 = now_ms();
+            scatter_chunk(eng, c, ch, pairs);
+            S.ms_scatter += now_ms() - t0;
+        }
+        CUDA_TRY(cudaStreamSynchronize(c.st_d2h));
+        const double t0 = now_ms();
+        scatter_bytes(eng, c, pairs);
+        S.ms_scatter += now_ms() - t0;
+        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_k0, c.ev_k1));
+        S.ms_kernel = std::max(S.ms_kernel, (double)ms);      // first H2D .. last kernel, copies overlapped
+        S.cells_effective += (int64_t)*c.h_cells;
+    }
+    S.ms_total = now_ms() - t_begin;
     return BSW_OK;
 }
 
@@ -621,9 +827,7 @@ double bsw_measure_int_peak(bsw_engine* eng)
     if (!eng || eng->devs.empty()) return 0.0;
     DevCtx& c = eng->devs[0];
     if (cudaSetDevice(c.dev) != cudaSuccess) return 0.0;
-    cudaDeviceProp prop{};
-    if (cudaGetDeviceProperties(&prop, c.dev) != cudaSuccess) return 0.0;
-    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;
+    const int threads = 256, blocks = c.sms * 8, iters = 4096;
     int* d_out = nullptr;
     if (cudaMalloc((void**)&d_out, sizeof(int) * (size_t)threads * blocks) != cudaSuccess) return 0.0;
     cudaEvent_t e0, e1;

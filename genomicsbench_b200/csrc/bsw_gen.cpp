@@ -104,9 +104,9 @@ int bsw_gen_pairs(const bsw_gen_config* c, int64_t first, int64_t n, SeqPair* pa
 {
     if (!c || !pairs || !seq_ref || !seq_qer || n < 0 || first < 0) return BSW_ERR_PARAM;
     if (c->qlen_min < 1 || c->qlen_max < c->qlen_min || c->qlen_max > 32767) return BSW_ERR_PARAM;
-    const int nt = auto_threads(0);
+    ThreadPool& pool = global_pool();
     // pass 1: lengths (same RNG path as pass 2)
-    parallel_chunks(n, 4096, nt, [&](int64_t b, int64_t e, int) {
+    pool.for_range(n, 4096, [&](int64_t b, int64_t e, int) {
         for (int64_t k = b; k < e; ++k) {
             PairDraw d = draw_pair(*c, first + k, nullptr, nullptr);
             SeqPair& sp = pairs[k];
@@ -122,7 +122,7 @@ int bsw_gen_pairs(const bsw_gen_config* c, int64_t first, int64_t n, SeqPair* pa
         ro += pairs[k].len1; qo += pairs[k].len2;
     }
     // pass 2: bases
-    parallel_chunks(n, 4096, nt, [&](int64_t b, int64_t e, int) {
+    pool.for_range(n, 4096, [&](int64_t b, int64_t e, int) {
         for (int64_t k = b; k < e; ++k)
             draw_pair(*c, first + k, seq_qer + pairs[k].idq, seq_ref + pairs[k].idr);
     });

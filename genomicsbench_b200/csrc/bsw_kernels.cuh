@@ -35,6 +35,9 @@ struct KParams {
 #define BSW_QMASK  0x18000u
 #define BSW_HMASK  0x7fffu
 #define BSW_ESHIFT 17
+// meta.w = h0 | BSW_META_NFLAG when the pair contains an N: the 2-bit variant skips it (the
+// byte variant recomputes it from the byte-staged copy)
+#define BSW_META_NFLAG (1 << 30)
 
 // band clamp of bandedSWA.cpp:160-168, same double arithmetic
 __device__ __forceinline__ int bsw_clamp_band(const KParams& P, int qlen)
@@ -99,7 +102,6 @@ template <int BLOCK, bool BYTESEQ>
 __global__ void __launch_bounds__(BLOCK)
 bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qseq,
                  const uint32_t* __restrict__ tseq, int4* __restrict__ res,
-                 const int* __restrict__ respos,
                  int first, int count, const __grid_constant__ KParams P,
                  unsigned long long* __restrict__ cell_counter)
 {
@@ -107,9 +109,14 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qse
     const int tid = threadIdx.x;
     const int local = blockIdx.x * BLOCK + tid;
     long long my_cells = 0;
-    if (local < count) {
-        const int s = first + local;
-        const int4 md = meta[s];
+    int4 md = make_int4(0, 0, 0, 0);
+    const int s = first + local;
+    bool run = local < count;
+    if (run) {
+        md = meta[s];
+        if (!BYTESEQ && (md.w & BSW_META_NFLAG)) run = false;
+    }
+    if (run) {
         const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w;
         uint32_t* const eh = eh_smem + tid;
         const uint8_t* qb = reinterpret_cast<const uint8_t*>(qseq) + (BYTESEQ ? (uint32_t)md.x : 0u);
@@ -201,7 +208,7 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qse
                 end = min(j + 2, qlen);
             }
         }
-        res[respos ? respos[s] : s] = bsw_pack_result(st);
+        res[s] = bsw_pack_result(st);
     }
     // effective-cell statistic: one atomic per warp
     for (int off = 16; off > 0; off >>= 1) my_cells += __shfl_down_sync(0xffffffffu, my_cells, off);
@@ -226,7 +233,7 @@ constexpr int LONG_WARPS = 4;
 __global__ void __launch_bounds__(LONG_WARPS * 32)
 bsw_long_kernel(const int4* __restrict__ meta, const uint8_t* __restrict__ qbytes,
                 const uint8_t* __restrict__ tbytes, int4* __restrict__ res,
-                const int* __restrict__ respos, int count, const __grid_constant__ KParams P,
+                int count, const __grid_constant__ KParams P,
                 uint32_t* __restrict__ scratch, int scratch_stride, unsigned int* __restrict__ queue,
                 unsigned long long* __restrict__ cell_counter)
 {
@@ -367,7 +374,7 @@ bsw_long_kernel(const int4* __restrict__ meta, const uint8_t* __restrict__ qbyte
                 end = min(j + 2, qlen);
             }
         }
-        if (lane == 0) res[respos ? respos[s] : s] = bsw_pack_result(st);
+        if (lane == 0) res[s] = bsw_pack_result(st);
         __syncwarp();
     }
     if (lane == 0 && my_cells) atomicAdd(cell_counter, (unsigned long long)my_cells);

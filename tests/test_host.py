@@ -46,7 +46,7 @@ def test_bucket_order_is_sorted_permutation(lib):
     p, _, _ = lib.gen_pairs(lib.gen_named_config("large"), 0, 20000)
     order = lib.bucket_order(p)
     assert np.array_equal(np.sort(order), np.arange(len(p)))
-    key = (p["len2"][order].astype(np.int64) << 30) | (p["len1"][order].astype(np.int64) << 15) | p["h0"][order]
+    key = (p["len2"][order].astype(np.int64) << 30) | (p["h0"][order].astype(np.int64) << 15) | p["len1"][order]
     assert (np.diff(key) >= 0).all()
     assert len(lib.bucket_order(p[:0])) == 0
 
