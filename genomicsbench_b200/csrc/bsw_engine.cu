@@ -28,7 +28,7 @@ using namespace bsw;
 namespace {
 
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
-constexpr int SHORT_MAX_QLEN = 880;       // (qlen+1) * SHORT_BLOCK * 4 B must fit 227 KB
+constexpr int SHORT_MAX_QLEN = 832;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
 constexpr int NSTREAMS = 4;               // compute streams per device
 constexpr int MAX_CHUNKS = 16;
 
@@ -162,13 +162,23 @@ inline bool pack2(const uint8_t* src, int n, uint32_t* dst)
     return bad != 0;
 }
 
-const int kStrideSteps[] = {17, 33, 49, 65, 81, 97, 113, 129, 153, 177, 201, 225, 257, 289, 321, 353,
-                            385, 449, 513, 577, 641, 705, 769, 833, SHORT_MAX_QLEN + 1};
-
+// Shared-memory rows per thread come in steps (one launch per step present in a chunk): fine
+// steps where occupancy is most sensitive to them, coarser ones for long queries.
 inline int stride_for(int qmax)
 {
-    for (int s : kStrideSteps) if (s >= qmax + 1) return s;
-    return -1;
+    const int need = qmax + 8;                    // + one prefetched group (bsw_kernels.cuh)
+    if (need > SHORT_MAX_QLEN + 8) return -1;
+    int s;
+    if (need <= 136) s = (need + 7) & ~7;
+    else if (need <= 520) s = (need + 15) & ~15;
+    else s = (need + 31) & ~31;
+    return std::min(s, SHORT_MAX_QLEN + 8);
+}
+
+// dynamic shared memory of one short-kernel block: eh words + the 2-bit query byte plane
+inline size_t short_smem_bytes(int qstride)
+{
+    return (size_t)qstride * SHORT_BLOCK * sizeof(uint32_t) + (size_t)((qstride + 3) / 4) * SHORT_BLOCK;
 }
 
 int set_kernel_attrs(bsw_engine* eng, DevCtx& c)
@@ -321,9 +331,9 @@ int launch_chunk(bsw_engine* eng, DevCtx& c, Chunk& ch, bool wait_h2d)
         if (wait_h2d && !used[si]) CUDA_TRY(cudaStreamWaitEvent(st, ch.ev_h2d, 0));
         used[si] = true;
         const int grid = (L.count + SHORT_BLOCK - 1) / SHORT_BLOCK;
-        const size_t smem = (size_t)L.qstride * SHORT_BLOCK * sizeof(uint32_t);
+        const size_t smem = short_smem_bytes(L.qstride);
         bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, smem, st>>>(
-            c.meta.d, c.q.d, c.t.d, c.res.d, L.first, L.count, eng->kp, c.d_cells);
+            c.meta.d, c.q.d, c.t.d, c.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
         eng->stats.kernel_launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -419,10 +429,10 @@ int launch_bytes(bsw_engine* eng, DevCtx& c, bool wait_h2d)
     if (wait_h2d) CUDA_TRY(cudaStreamWaitEvent(st, c.ev_a, 0));
     if (c.n_bytes_short > 0) {
         const int grid = (int)((c.n_bytes_short + SHORT_BLOCK - 1) / SHORT_BLOCK);
-        const size_t smem = (size_t)stride_for(c.qmax_bytes_short) * SHORT_BLOCK * sizeof(uint32_t);
-        bsw_short_kernel<SHORT_BLOCK, true><<<grid, SHORT_BLOCK, smem, st>>>(
+        const int qstride = stride_for(c.qmax_bytes_short);
+        bsw_short_kernel<SHORT_BLOCK, true><<<grid, SHORT_BLOCK, short_smem_bytes(qstride), st>>>(
             c.meta_n.d, reinterpret_cast<const uint32_t*>(c.qb.d), reinterpret_cast<const uint32_t*>(c.tb.d),
-            c.res_n.d, 0, (int)c.n_bytes_short, eng->kp, c.d_cells);
+            c.res_n.d, 0, (int)c.n_bytes_short, qstride, eng->kp, c.d_cells);
         eng->stats.kernel_launches++;
     }
     if (c.n_long > 0) {
@@ -558,7 +568,7 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
     k.oe_del = k.o_del + k.e_del; k.oe_ins = k.o_ins + k.e_ins;
     k.zdrop = params->zdrop; k.end_bonus = params->end_bonus; k.zmode = params->zdrop_mode;
     k.mx = std::max(std::max(k.match, k.mismatch_neg), k.ambig);
-    k.w = 0;
+    k.w = 0; k.kone = 1;
     eng->pool.reset(new ThreadPool(auto_threads(params->host_threads)));
     eng->short_max = params->long_min_qlen > 0 ? std::min(params->long_min_qlen - 1, SHORT_MAX_QLEN) : SHORT_MAX_QLEN;
     memset(&eng->stats, 0, sizeof(eng->stats));

@@ -27,14 +27,12 @@ struct KParams {
     int zmode;          // BSW_ZDROP_VECTOR / BSW_ZDROP_SCALAR
     int mx;             // max entry of the scoring matrix (band clamp, bandedSWA.cpp:160-168)
     int w;              // caller's band width
+    int kone;           // the constant 1, kept opaque to the compiler (argmax-key addends stay in registers)
 };
 
-// Packed shared-memory cell of the short kernel:  [31:17] e   [16:15] query base   [14:0] h
-// (h, e < 32768 is the reference's own 16-bit domain, bandedSWA.h:84 / Q7.)
-#define BSW_QSHIFT 15
-#define BSW_QMASK  0x18000u
-#define BSW_HMASK  0x7fffu
-#define BSW_ESHIFT 17
+// Shared-memory cell of the short kernel: one 32-bit word per DP column,  [31:16] e  [15:0] h
+// (h, e < 32768 is the reference's own 16-bit domain, bandedSWA.h:84 / Q7), so both halves are
+// read with 16-bit loads and need no unpacking on the ALU pipe.
 // meta.w = h0 | BSW_META_NFLAG when the pair contains an N: the 2-bit variant skips it (the
 // byte variant recomputes it from the byte-staged copy)
 #define BSW_META_NFLAG (1 << 30)
@@ -50,6 +48,36 @@ __device__ __forceinline__ int bsw_clamp_band(const KParams& P, int qlen)
     max_del = max_del > 1 ? max_del : 1;
     w = w < max_del ? w : max_del;
     return w;
+}
+
+// a * b + c on the FMA pipe (IMAD): keeps adds / shifts / re-packs off the ALU pipe, which bounds
+// these kernels (VIADDMNMX, VIMNMX3, LOP3, SHF, SEL all issue there at half rate).
+__device__ __forceinline__ int bsw_mad(int a, int b, int c)
+{
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// Shared-memory accessors of the short kernel's row sweep.  The two halves of a cell are read as
+// two LDS.U16 (LSU pipe) -- left to the compiler they are fused into LDS.32 + LOP3 + PRMT, two
+// instructions on the ALU pipe that bounds the kernel.  "memory" keeps them ordered against the
+// plain C++ accesses to the same array; among themselves they stay in program order (volatile).
+__device__ __forceinline__ int bsw_lds_u16(uint32_t saddr)
+{
+    int v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t bsw_lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bsw_sts_u32(uint32_t saddr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
 }
 
 // Running per-pair state shared by both kernels' row epilogues.
@@ -96,13 +124,26 @@ __device__ __forceinline__ int4 bsw_pack_result(const PairState& st)
 //   meta[s] = {query word/byte offset, target word/byte offset, qlen | tlen << 16, h0}
 //   BYTESEQ = false: sequences are 2-bit packed, 16 bases per 32-bit word, word-aligned.
 //   BYTESEQ = true : one base code per byte (pairs that contain N, code 4).
-//   eh[j * BLOCK + tid] is thread tid's cell j (bank == tid: conflict-free for any j).
+//   Shared memory of a block (qstride = cells per thread >= qlen + 8: the pipelined sweep reads one
+//   group past the last full one):
+//     eh [j * BLOCK + tid]            cell j of thread tid: e << 16 | h  (bank == lane for any j)
+//     qpk[(j >> 2) * BLOCK + tid]     byte holding query bases j..j+3, 2 bits each (2-bit variant)
+//   Row sweep: columns are processed in groups of 4 aligned to j % 4 == 0, so one byte load
+//   brings the four query bases of a group and the match tests are single LOP3s with immediate
+//   masks.  Columns left of `beg` are dead for the rest of the pair (beg never decreases), so
+//   the <= 3 columns between the group boundary and beg are zeroed and swept like live ones:
+//   they produce h = e = f = 0, exactly the state the reference enters column beg with when
+//   beg > 0.  The <= 3 columns right of the last full group run through the scalar tail loop.
+//   Instruction budget per cell (the ALU pipe issues 2 warp-instructions/clk/SM and bounds this
+//   kernel, scripts/int_pipe_probe.cu): ALU = match test, select, M, h, E', F' (+ half of the two
+//   dual-issue ops); FMA pipe = cap, the gap decrement, the cell re-pack and the argmax key;
+//   LSU = 2 x LDS.U16 + STS.32 (+ 1/4 LDS.U8).
 // ---------------------------------------------------------------------------------------
 template <int BLOCK, bool BYTESEQ>
 __global__ void __launch_bounds__(BLOCK)
 bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qseq,
                  const uint32_t* __restrict__ tseq, int4* __restrict__ res,
-                 int first, int count, const __grid_constant__ KParams P,
+                 int first, int count, int qstride, const __grid_constant__ KParams P,
                  unsigned long long* __restrict__ cell_counter)
 {
     extern __shared__ uint32_t eh_smem[];
@@ -119,25 +160,30 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qse
     if (run) {
         const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w;
         uint32_t* const eh = eh_smem + tid;
+        uint8_t* const qpk = reinterpret_cast<uint8_t*>(eh_smem + qstride * BLOCK) + tid;
+        const uint32_t eh_sa = (uint32_t)__cvta_generic_to_shared(eh);
+        const uint32_t qpk_sa = (uint32_t)__cvta_generic_to_shared(qpk);
         const uint8_t* qb = reinterpret_cast<const uint8_t*>(qseq) + (BYTESEQ ? (uint32_t)md.x : 0u);
         const uint8_t* tb = reinterpret_cast<const uint8_t*>(tseq) + (BYTESEQ ? (uint32_t)md.y : 0u);
         const uint32_t* qw = qseq + (BYTESEQ ? 0u : (uint32_t)md.x);
         const uint32_t* tw = tseq + (BYTESEQ ? 0u : (uint32_t)md.y);
 
-        // ---- first row (bandedSWA.cpp:155-157) with the query base folded into each cell
+        // ---- first row (bandedSWA.cpp:155-157); the query goes to its byte plane
         {
             int hv = h0;
-            uint32_t qword = 0;
             for (int j = 0; j <= qlen; ++j) {
-                uint32_t qbits = 0;
-                if (!BYTESEQ) {
-                    if ((j & 15) == 0 && j < qlen) qword = __ldg(qw + (j >> 4));
-                    qbits = (qword >> ((j & 15) * 2)) & 3u;
-                    if (j >= qlen) qbits = 0;
-                }
                 if (j == 1) hv = h0 > P.oe_ins ? h0 - P.oe_ins : 0;
                 else if (j >= 2) hv = hv > P.e_ins ? hv - P.e_ins : 0;
-                eh[j * BLOCK] = (uint32_t)hv | (qbits << BSW_QSHIFT);
+                eh[j * BLOCK] = (uint32_t)hv;
+            }
+            if (!BYTESEQ) {
+                const int nw = (qlen + 15) >> 4;
+                for (int k = 0; k < nw; ++k) {
+                    const uint32_t v = __ldg(qw + k);
+                    uint8_t* d = qpk + 4 * k * BLOCK;
+                    d[0] = (uint8_t)v; d[BLOCK] = (uint8_t)(v >> 8);
+                    d[2 * BLOCK] = (uint8_t)(v >> 16); d[3 * BLOCK] = (uint8_t)(v >> 24);
+                }
             }
         }
         const int w = bsw_clamp_band(P, qlen);
@@ -146,7 +192,10 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qse
         st.max = h0; st.max_i = -1; st.max_j = -1; st.max_ie = -1; st.gscore = -1; st.max_off = 0;
         int beg = 0, end = qlen;
         uint32_t tword = 0;
-        const int neg_oe_del = -P.oe_del, neg_oe_ins = -P.oe_ins;
+        const int neg_oe_del = -P.oe_del, neg_oe_ins = -P.oe_ins, neg_e_del = -P.e_del, neg_e_ins = -P.e_ins;
+        const int c_match = P.match, c_mis = P.mismatch_neg;
+        // argmax-key addends kept in registers so that the key is one IMAD (h * 65536 + k)
+        const int k1 = P.kone, k2 = 2 * P.kone, k3 = 3 * P.kone;
 
         for (int i = 0; i < tlen; ++i) {
             int ti;
@@ -161,36 +210,90 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qse
             if (beg == 0) h1 = max(h0 - (P.o_del + P.e_del * (i + 1)), 0);
             int f = 0;
             int mkey = 0;                                    // (row max << 16) | argmax column
-            const uint32_t tmask = (uint32_t)ti << BSW_QSHIFT;
-            uint32_t* p = eh + beg * BLOCK;
-#pragma unroll 4
-            for (int j = beg; j < end; ++j) {
+            // DP recurrence of one cell given its diagonal H (Hd), E (e) and match score (sc);
+            // writes the cell back as {h = H(i, j-1), e = E(i+1, j)}  (bandedSWA.cpp:196-210)
+#define BSW_CELL_CORE(STORE, HD, EE, SC, KEYADD)                                                     \
+            {                                                                                        \
+                /* M = Hd ? Hd + s : 0, clamped at 0 (a negative M is equivalent to 0 in every use) */ \
+                const int M = __viaddmin_s32_relu((HD), (SC), bsw_mad((HD), 65536, 0));              \
+                const int h = __vimax3_s32(M, (EE), f);                                              \
+                const int en = __viaddmax_s32_relu(M, neg_oe_del, bsw_mad((EE), 1, neg_e_del));      \
+                f = __viaddmax_s32_relu(M, neg_oe_ins, f + neg_e_ins);                               \
+                STORE((uint32_t)bsw_mad(en, 65536, h1));                                             \
+                mkey = max(mkey, bsw_mad(h, 65536, (KEYADD)));                                       \
+                h1 = h;                                                                              \
+            }
+            int j;
+            if (BYTESEQ) {
+                j = beg;
+            } else {
+                // zero the dead columns between the group boundary and beg, then sweep full groups
+                j = beg & ~3;
+                if (j + 0 < beg) eh[(j + 0) * BLOCK] = 0u;
+                if (j + 1 < beg) eh[(j + 1) * BLOCK] = 0u;
+                if (j + 2 < beg) eh[(j + 2) * BLOCK] = 0u;
+                const uint32_t trep = (uint32_t)ti * 0x55u;
+                uint32_t sa = eh_sa + (uint32_t)j * (4 * BLOCK);
+                uint32_t qa = qpk_sa + (uint32_t)(j >> 2) * BLOCK;
+                // software pipeline: group g+1 is loaded while group g is computed (the row buffer
+                // is padded, so the load past the last full group stays inside this thread's column)
+                int h_0 = bsw_lds_u16(sa), e_0 = bsw_lds_u16(sa + 2);
+                int h_1 = bsw_lds_u16(sa + 4 * BLOCK), e_1 = bsw_lds_u16(sa + 4 * BLOCK + 2);
+                int h_2 = bsw_lds_u16(sa + 8 * BLOCK), e_2 = bsw_lds_u16(sa + 8 * BLOCK + 2);
+                int h_3 = bsw_lds_u16(sa + 12 * BLOCK), e_3 = bsw_lds_u16(sa + 12 * BLOCK + 2);
+                uint32_t qv = bsw_lds_u8(qa);
+                for (; j + 4 <= end; j += 4) {
+                    const uint32_t x = qv ^ trep;
+                    const uint32_t sn = sa + 16 * BLOCK;
+                    const int nh_0 = bsw_lds_u16(sn), ne_0 = bsw_lds_u16(sn + 2);
+                    const int nh_1 = bsw_lds_u16(sn + 4 * BLOCK), ne_1 = bsw_lds_u16(sn + 4 * BLOCK + 2);
+                    const int nh_2 = bsw_lds_u16(sn + 8 * BLOCK), ne_2 = bsw_lds_u16(sn + 8 * BLOCK + 2);
+                    const int nh_3 = bsw_lds_u16(sn + 12 * BLOCK), ne_3 = bsw_lds_u16(sn + 12 * BLOCK + 2);
+                    qa += BLOCK;
+                    qv = bsw_lds_u8(qa);
+                    int mk4;
+                    {
+                        int mkey = 0;
+#define BSW_ST0(V) bsw_sts_u32(sa, (V))
+#define BSW_ST1(V) bsw_sts_u32(sa + 4 * BLOCK, (V))
+#define BSW_ST2(V) bsw_sts_u32(sa + 8 * BLOCK, (V))
+#define BSW_ST3(V) bsw_sts_u32(sa + 12 * BLOCK, (V))
+                        BSW_CELL_CORE(BSW_ST0, h_0, e_0, (x & 0x03u) ? c_mis : c_match, 0)
+                        BSW_CELL_CORE(BSW_ST1, h_1, e_1, (x & 0x0cu) ? c_mis : c_match, k1)
+                        BSW_CELL_CORE(BSW_ST2, h_2, e_2, (x & 0x30u) ? c_mis : c_match, k2)
+                        BSW_CELL_CORE(BSW_ST3, h_3, e_3, (x & 0xc0u) ? c_mis : c_match, k3)
+#undef BSW_ST0
+#undef BSW_ST1
+#undef BSW_ST2
+#undef BSW_ST3
+                        mk4 = mkey;
+                    }
+                    mkey = max(mkey, mk4 + j);                // same order: j + k < 65536 never carries
+                    h_0 = nh_0; e_0 = ne_0; h_1 = nh_1; e_1 = ne_1;
+                    h_2 = nh_2; e_2 = ne_2; h_3 = nh_3; e_3 = ne_3;
+                    sa = sn;
+                }
+            }
+            // scalar tail (2-bit variant: <= 3 columns) / whole window (byte variant)
+            for (; j < end; ++j) {
+                uint32_t* p = eh + j * BLOCK;
                 const uint32_t wd = *p;
-                const int Hd = (int)(wd & BSW_HMASK);
-                const int e = (int)(wd >> BSW_ESHIFT);
-                int s;
+                int sc;
                 if (BYTESEQ) {
                     const int qj = __ldg(qb + j);
-                    s = (qj > 3 || ti > 3) ? P.ambig : (qj == ti ? P.match : P.mismatch_neg);
+                    sc = (qj > 3 || ti > 3) ? P.ambig : (qj == ti ? c_match : c_mis);
                 } else {
-                    s = ((wd ^ tmask) & BSW_QMASK) ? P.mismatch_neg : P.match;
+                    const int qj = ((int)qpk[(j >> 2) * BLOCK] >> ((j & 3) * 2)) & 3;
+                    sc = qj == ti ? c_match : c_mis;
                 }
-                // M = Hd ? Hd + s : 0, clamped at 0 (a negative M is equivalent to 0 in every use)
-                const int M = __viaddmin_s32_relu(Hd, s, Hd << 16);
-                const int h = __vimax3_s32(M, e, f);
-                const int en = __viaddmax_s32_relu(M, neg_oe_del, e - P.e_del);
-                f = __viaddmax_s32_relu(M, neg_oe_ins, f - P.e_ins);
-                *p = (wd & BSW_QMASK) | (uint32_t)h1 | ((uint32_t)en << BSW_ESHIFT);
-                mkey = max(mkey, (h << 16) | j);
-                h1 = h;
-                p += BLOCK;
+#define BSW_STP(V) *p = (V)
+                BSW_CELL_CORE(BSW_STP, (int)(wd & 0xffffu), (int)(wd >> 16), sc, j)
+#undef BSW_STP
             }
+#undef BSW_CELL_CORE
             if (end > beg) my_cells += end - beg;
-            // eh[end] = {h1, 0}  (bandedSWA.cpp:213); keep the query bits of that cell
-            {
-                uint32_t* pe = eh + end * BLOCK;
-                *pe = (*pe & BSW_QMASK) | (uint32_t)h1;
-            }
+            // eh[end] = {h1, 0}  (bandedSWA.cpp:213)
+            eh[end * BLOCK] = (uint32_t)h1;
             const int jfin = end > beg ? end : beg;
             if (jfin == qlen) {                               // bandedSWA.cpp:214-217
                 if (!(st.gscore > h1)) st.max_ie = i;
@@ -200,12 +303,12 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qse
             if (bsw_row_update(P, st, i, m, mj)) break;
             // next row's window (bandedSWA.cpp:230-233)
             {
-                int j = beg;
-                while (j < end && (eh[j * BLOCK] & ~BSW_QMASK) == 0) ++j;
-                beg = j;
-                j = end;
-                while (j >= beg && (eh[j * BLOCK] & ~BSW_QMASK) == 0) --j;
-                end = min(j + 2, qlen);
+                int jj = beg;
+                while (jj < end && eh[jj * BLOCK] == 0u) ++jj;
+                beg = jj;
+                jj = end;
+                while (jj >= beg && eh[jj * BLOCK] == 0u) --jj;
+                end = min(jj + 2, qlen);
             }
         }
         res[s] = bsw_pack_result(st);
