@@ -18,7 +18,7 @@ from ._lib import (ABI, BSW_ZDROP_SCALAR, BSW_ZDROP_VECTOR, RESULT_FIELDS, SEQPA
 __all__ = [
     "BandedPairWiseSW", "Engine", "BswError", "SEQPAIR_DTYPE", "RESULT_FIELDS", "default_params",
     "gen_named_config", "gen_pairs", "bucket_order", "partition", "read_pairs_file",
-    "write_pairs_file", "load_library", "NAMED_CONFIGS",
+    "write_pairs_file", "load_library", "NAMED_CONFIGS", "pinned_empty", "pinned_copy",
 ]
 
 NAMED_CONFIGS = {"small": 0, "short8": 1, "long16": 2, "large": 3, "sweep": 4}
@@ -157,6 +157,42 @@ class BandedPairWiseSW:
             if e is not None:
                 e.close()
         self._vec = self._scalar = None
+
+
+# ---------------------------------------------------------------------------------------
+# pinned host buffers (bsw_host_alloc): numpy views the engine can DMA directly
+# ---------------------------------------------------------------------------------------
+class _PinnedBlock:
+    """Owns one bsw_host_alloc allocation; freed when the last numpy view of it dies."""
+
+    def __init__(self, nbytes: int):
+        self._lib = load_library()
+        self.ptr = self._lib.bsw_host_alloc(max(int(nbytes), 1))
+        if not self.ptr:
+            raise BswError(-4, f"bsw_host_alloc({nbytes}) failed (no CUDA device or out of pinned memory)")
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self._lib.bsw_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked memory: buffers like this take the engine's direct route.
+    The block is freed when the array (and every view of it) is garbage-collected."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    blk = _PinnedBlock(n * dtype.itemsize + 64)
+    raw = (C.c_ubyte * max(n * dtype.itemsize, 1)).from_address(blk.ptr)
+    raw._owner = blk                                  # arr.base -> raw -> blk
+    return np.frombuffer(raw, dtype=dtype, count=n).reshape(shape)
+
+
+def pinned_copy(a: np.ndarray) -> np.ndarray:
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
 
 
 # ---------------------------------------------------------------------------------------

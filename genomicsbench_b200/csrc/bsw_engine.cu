@@ -1,85 +1,91 @@
-// bsw_engine.cu -- engine object, host pipeline and kernel launches behind the C ABI (include/bsw.h).
+// bsw_engine.cu -- engine object, chunk pipeline and kernel launches behind the C ABI (include/bsw.h).
 //
 // Stands in for BandedPairWiseSW's batch wrapper smithWatermanBatchWrapper16
-// (benchmarks/bsw/bandedSWA.cpp:1150-1431): where the reference pads to the SIMD width, sorts by
-// len1, transposes AoS->SoA per 16 pairs and calls the AVX kernel, this engine
-//   1. buckets the batch by (len2, h0, len1)                       (bsw_host.cpp)
-//   2. cuts the processing order into chunks and, per chunk, packs sequences to 2 bits/base
-//      straight into pinned staging, copies them to HBM asynchronously, launches the sm_100a
-//      kernels per shared-memory class and copies the packed results back -- chunk k's GPU work
-//      overlaps the packing of chunk k+1 and the scatter of chunk k-1
-//   3. scatters the six result fields into the caller's SeqPair[] in input order.
-// Pairs that contain N (code 4) and pairs whose query exceeds the short kernel's shared-memory
-// limit are staged as bytes and run by the byte variant of the short kernel / the warp-per-pair
-// long kernel after the last chunk.
+// (benchmarks/bsw/bandedSWA.cpp:1150-1431).  Where the reference pads to the SIMD width, sorts by
+// len1, transposes AoS->SoA per 16 pairs and calls the AVX kernel, this engine cuts the batch into
+// chunks of consecutive pairs and runs every chunk through a device-side pipeline:
+//
+//   host buffers pinned (bsw_host_alloc / bsw_host_register, "direct" route):
+//     DMA of the raw SeqPair records -> bsw_scan_pairs (validate, 16-byte descriptors, summary)
+//     -> DMA of the byte range the chunk's sequences span (or zero-copy reads when that range is
+//     sparse) -> bsw_pack_pairs (2 bits/base) -> bsw_bucket_* (counting sort by len2|h0|len1)
+//     -> bsw_short_kernel per shared-memory class -> bsw_writeback into the device copy of the
+//     records -> DMA of the records back.  The host touches no payload byte.
+//   pageable host buffers ("staged" route):
+//     host threads stream over the chunk once, in input order: descriptors + the sequences'
+//     bytes gathered into pinned staging, H2D, then the same device stages; results come back by
+//     D2H and a second streaming pass writes them into the caller's records.
+//
+// Chunk c+1 is prepared and copied while chunk c computes and chunk c-1 drains.  Pairs that
+// contain N (code 4) or whose query exceeds the short kernel's shared-memory limit are listed by
+// the pack kernel and run by the byte-reading kernels before the chunk's results leave.
 #include "bsw_common.h"
 #include "bsw_kernels.cuh"
+#include "bsw_prep.cuh"
 #include <cstdio>
 #include <cstring>
 #include <string>
 #include <memory>
 #include <deque>
+#include <climits>
 
-namespace bsw {
-void partition_blocks(const SortedBatch& sb, int32_t w, int32_t n_shards, std::vector<std::vector<int64_t>>& blocks_of);
-}
 using namespace bsw;
 
 namespace {
 
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
 constexpr int SHORT_MAX_QLEN = 832;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
-constexpr int NSTREAMS = 4;               // compute streams per device
-constexpr int MAX_CHUNKS = 16;
+constexpr int NSTREAMS = 4;               // DP compute streams per device
+constexpr int NSLOTS = 3;                 // chunks in flight per device (prepare / compute / drain)
+constexpr int64_t CHUNK_EXTEND = 1 << 18; // pairs per chunk of bsw_extend (overlap vs bucketing quality)
+constexpr int64_t CHUNK_STAGE = 1 << 20;  // pairs per chunk of bsw_stage (resident: best bucketing)
+constexpr int BUCKET_BITS = 18;           // bins of the counting sort (1 MB table)
+constexpr long long OFF_BIAS = 1ll << 30; // bias of ChunkInfo::min_* / max_* (bsw_prep.cuh)
 
 std::string g_create_error;
 std::mutex g_err_mutex;
 
 struct Launch {
-    int first, count;     // range in the shard's processing order
-    int qstride;          // shared-memory rows per thread (>= qmax + 1)
+    int first, count;     // range in the chunk's processing order
+    int qstride;          // shared-memory rows per thread
 };
 
 template <class T>
-struct Buf {              // grow-only device + pinned-host buffer pair
-    T* d = nullptr; T* h = nullptr; size_t cap = 0;
+struct Buf {              // grow-only device buffer with an optional pinned-host twin
+    T* d = nullptr; T* h = nullptr; size_t cap = 0; size_t hcap = 0;
 };
 
-struct Chunk {
-    int64_t s0 = 0, s1 = 0;               // range in the shard's processing order
-    size_t q0 = 0, q1 = 0, t0 = 0, t1 = 0; // word ranges in the packed sequence buffers
+struct Slot {
+    // buffers
+    Buf<uint8_t> raw_pairs;               // device copy of the caller's records (direct route)
+    Buf<int4> desc, meta, res;            // per pair: byte-offset descriptor, word-offset descriptor, result
+    Buf<uint32_t> perm, rank, bins, nlist, llist, qpk, tpk, scratch;
+    Buf<uint8_t> qraw, rraw;              // sequence bytes (device; pinned twin = staging of the staged route)
+    ChunkInfo* d_info = nullptr; ChunkInfo* h_info = nullptr;
+    unsigned int* d_queue = nullptr;
+    cudaStream_t st{};
+    cudaEvent_t ev_info{}, ev_dp{}, ev_out{}, ev_fork{}, ev_k0{}, ev_k1{};
+    // chunk state
+    int64_t a = 0; int n = 0;             // pairs [a, a + n) of the batch
+    bool direct = false;
+    const uint8_t* qbase = nullptr;       // device-visible address of descriptor offset 0 (query / reference)
+    const uint8_t* rbase = nullptr;
+    ChunkInfo info;                       // host copy used for planning
     std::vector<Launch> plan;
-    cudaEvent_t ev_h2d{}, ev_done{};
-    bool scattered = false;
+    int n_sorted = 0;                     // short pairs (in perm)
+    unsigned n_nlist = 0, n_llist = 0; int qmax_n = 0;
+    int long_stride = 0, long_blocks = 0;
 };
 
 struct DevCtx {
     int dev = 0;
     int sms = 148;
-    cudaStream_t st_copy{}, st_d2h{}, st[NSTREAMS] = {};
-    cudaEvent_t ev_a{}, ev_b{}, ev_k0{}, ev_k1{}, ev_join[NSTREAMS] = {};
-    Chunk chunks[MAX_CHUNKS];
-    int nchunks = 0;
-    Buf<int4> meta, res, meta_n, res_n;
-    Buf<uint32_t> q, t;
-    Buf<uint8_t> qb, tb;
-    std::vector<uint32_t> pos_n;          // byte-staged pair k -> position in the shard order
-    std::vector<uint8_t> hasn;            // per position: pair contains an N
-    std::vector<uint32_t> qoff, toff;     // word offsets per position (+1)
+    cudaStream_t cs[NSTREAMS] = {};
+    cudaEvent_t ev_join[NSTREAMS] = {};
+    cudaEvent_t ev_t0{}, ev_t1{};         // device timeline of bsw_run_staged
+    std::deque<Slot> slots;
     unsigned long long* d_cells = nullptr;
     unsigned long long* h_cells = nullptr;
-    unsigned int* d_queue = nullptr;      // work queue of the long-pair kernel
-    Buf<uint32_t> scratch;                // eh[] rows of the long-pair kernel (device only)
-    // the shard of the sorted batch this device owns (copied views, processing order)
-    RawBuf<uint32_t> idx;
-    RawBuf<uint16_t> len2, len1, h0;
-    int64_t n = 0;                        // pairs in the shard
-    int64_t n_short = 0;                  // positions [0, n_short) go to the short kernel
-    int64_t n_bytes_short = 0;            // byte list: [0, n_bytes_short) short pairs with N,
-    int64_t n_long = 0;                   //            [n_bytes_short, +n_long) long pairs
-    int qmax_bytes_short = 0;
-    int long_stride = 0, long_blocks = 0;
-    size_t qb_bytes = 0, tb_bytes = 0;
     bool attr_set = false;
 };
 
@@ -93,11 +99,11 @@ struct bsw_engine {
     std::string err;
     bsw_stats stats;
     int short_max = SHORT_MAX_QLEN;       // longest query the short kernel takes
-    // staged batch
+    // staged batch (bsw_stage / bsw_run_staged / bsw_fetch)
     bool staged = false, ran = false;
     int64_t n = 0;
     int32_t w = 0;
-    SortedBatch sb;
+    std::vector<std::pair<int, int>> staged_chunks;   // (device, slot) per chunk, batch order
 };
 
 namespace {
@@ -112,16 +118,22 @@ namespace {
     } while (0)
 
 template <class T>
-int ensure(bsw_engine* eng, Buf<T>& b, size_t need, bool host = true)
+int ensure(bsw_engine* eng, Buf<T>& b, size_t need, bool host = false)
 {
-    if (need <= b.cap) return BSW_OK;
-    size_t cap = std::max(need + need / 4, (size_t)1024);
-    if (b.d) cudaFree(b.d);
-    if (b.h) cudaFreeHost(b.h);
-    b.d = nullptr; b.h = nullptr; b.cap = 0;
-    CUDA_TRY(cudaMalloc((void**)&b.d, cap * sizeof(T)));
-    if (host) CUDA_TRY(cudaHostAlloc((void**)&b.h, cap * sizeof(T), cudaHostAllocDefault));
-    b.cap = cap;
+    if (need > b.cap) {
+        const size_t cap = std::max(need + need / 4, (size_t)1024);
+        if (b.d) cudaFree(b.d);
+        b.d = nullptr; b.cap = 0;
+        CUDA_TRY(cudaMalloc((void**)&b.d, cap * sizeof(T)));
+        b.cap = cap;
+    }
+    if (host && need > b.hcap) {
+        const size_t cap = std::max(need + need / 4, (size_t)1024);
+        if (b.h) cudaFreeHost(b.h);
+        b.h = nullptr; b.hcap = 0;
+        CUDA_TRY(cudaHostAlloc((void**)&b.h, cap * sizeof(T), cudaHostAllocDefault));
+        b.hcap = cap;
+    }
     return BSW_OK;
 }
 
@@ -130,36 +142,7 @@ void release(Buf<T>& b)
 {
     if (b.d) cudaFree(b.d);
     if (b.h) cudaFreeHost(b.h);
-    b.d = nullptr; b.h = nullptr; b.cap = 0;
-}
-
-// 2-bit packing of n base codes (one per byte) into 16-bases-per-word little-endian words.
-// Returns true if a code > 3 (N) was seen; such bases are packed as (code & 3).
-inline bool pack2(const uint8_t* src, int n, uint32_t* dst)
-{
-    uint64_t bad = 0;
-    int i = 0, wi = 0;
-    for (; i + 16 <= n; i += 16, ++wi) {
-        uint64_t a, b;
-        memcpy(&a, src + i, 8); memcpy(&b, src + i + 8, 8);
-        bad |= (a | b) & 0xFCFCFCFCFCFCFCFCull;
-        a &= 0x0303030303030303ull; b &= 0x0303030303030303ull;
-        a = (a | (a >> 6)) & 0x000F000F000F000Full;  a = (a | (a >> 12)) & 0x000000FF000000FFull;
-        a = (a | (a >> 24)) & 0xFFFFull;
-        b = (b | (b >> 6)) & 0x000F000F000F000Full;  b = (b | (b >> 12)) & 0x000000FF000000FFull;
-        b = (b | (b >> 24)) & 0xFFFFull;
-        dst[wi] = (uint32_t)(a | (b << 16));
-    }
-    if (i < n) {
-        uint32_t wv = 0;
-        for (int k = 0; i < n; ++i, ++k) {
-            const uint8_t c = src[i];
-            bad |= c & 0xFC;
-            wv |= (uint32_t)(c & 3) << (2 * k);
-        }
-        dst[wi] = wv;
-    }
-    return bad != 0;
+    b.d = nullptr; b.h = nullptr; b.cap = b.hcap = 0;
 }
 
 // Shared-memory rows per thread come in steps (one launch per step present in a chunk): fine
@@ -179,6 +162,13 @@ inline int stride_for(int qmax)
 inline size_t short_smem_bytes(int qstride)
 {
     return (size_t)qstride * SHORT_BLOCK * sizeof(uint32_t) + (size_t)((qstride + 3) / 4) * SHORT_BLOCK;
+}
+
+inline int bits_for(uint32_t range)      // bits needed to hold values 0..range
+{
+    int b = 0;
+    while (range) { ++b; range >>= 1; }
+    return b;
 }
 
 int set_kernel_attrs(bsw_engine* eng, DevCtx& c)
@@ -212,143 +202,327 @@ int validate_params(const bsw_params* p, std::string& why)
     return BSW_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// per-shard preparation: offsets, chunking, launch plans, buffer sizing
-// ------------------------------------------------------------------------------------------
-int prepare_shard(bsw_engine* eng, DevCtx& c, bool pipelined)
+void init_info(ChunkInfo& I)
 {
-    CUDA_TRY(cudaSetDevice(c.dev));
-    if (int rc = set_kernel_attrs(eng, c)) return rc;
-    c.nchunks = 0;
-    c.n_short = c.n_bytes_short = c.n_long = 0; c.qb_bytes = c.tb_bytes = 0; c.pos_n.clear();
-    if (c.n == 0) return BSW_OK;
-    // queries longer than the short kernel's limit sit at the end of the (len2-ascending) order
-    c.n_short = std::upper_bound(c.len2.data(), c.len2.data() + c.n, (uint16_t)eng->short_max) - c.len2.data();
-    c.n_long = c.n - c.n_short;
-    c.qoff.resize((size_t)c.n_short + 1); c.toff.resize((size_t)c.n_short + 1);
-    uint64_t qo = 0, to = 0;
-    for (int64_t s = 0; s < c.n_short; ++s) {
-        c.qoff[s] = (uint32_t)qo; c.toff[s] = (uint32_t)to;
-        qo += (uint32_t)(c.len2[s] + 15) >> 4; to += (uint32_t)(c.len1[s] + 15) >> 4;
-    }
-    if (qo > 0xffffffffull || to > 0xffffffffull) { eng->err = "batch too large for 32-bit word offsets"; return BSW_ERR_PARAM; }
-    c.qoff[c.n_short] = (uint32_t)qo; c.toff[c.n_short] = (uint32_t)to;
-    if (int rc = ensure(eng, c.meta, (size_t)c.n_short + 1)) return rc;
-    if (int rc = ensure(eng, c.res, (size_t)c.n_short + 1)) return rc;
-    if (int rc = ensure(eng, c.q, qo + 4)) return rc;
-    if (int rc = ensure(eng, c.t, to + 4)) return rc;
-    c.hasn.assign((size_t)c.n_short, 0);
+    memset(&I, 0, sizeof(I));
+    I.min_r = I.min_q = ~0ull;
+    I.mn[0] = I.mn[1] = I.mn[2] = INT_MAX;
+}
 
-    // chunks: equal shares of the estimated work, cut at block boundaries
-    int want = 1;
-    if (pipelined && c.n_short >= 4 * 16384) want = (int)std::min<int64_t>(8, c.n_short / 65536 + 1);
-    std::vector<int64_t> cuts{0};
-    if (want > 1) {
-        const int64_t nblk = (c.n_short + SHORT_BLOCK - 1) / SHORT_BLOCK;
-        std::vector<double> pre((size_t)nblk + 1, 0.0);
-        const double band = 2.0 * eng->w + 1;
-        for (int64_t b = 0; b < nblk; ++b) {
-            const int64_t s = std::min(c.n_short - 1, b * SHORT_BLOCK + SHORT_BLOCK - 1);
-            const int64_t cnt = std::min<int64_t>(SHORT_BLOCK, c.n_short - b * SHORT_BLOCK);
-            pre[b + 1] = pre[b] + (double)cnt * (64.0 + c.len1[s] * std::min<double>(c.len2[s], band) +
-                                                 40.0 * (c.len1[s] + c.len2[s]));
-        }
-        for (int k = 1; k < want; ++k) {
-            const double target = pre[nblk] * k / want;
-            const int64_t b = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
-            const int64_t cut = std::min(c.n_short, b * SHORT_BLOCK);
-            if (cut > cuts.back()) cuts.push_back(cut);
-        }
+// true when the pointer is pinned / registered host memory the device can DMA and map
+bool is_pinned(const void* p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int slot_create(bsw_engine* eng, Slot& s)
+{
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&s.ev_info, &s.ev_dp, &s.ev_out, &s.ev_fork})
+        CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreate(&s.ev_k0));
+    CUDA_TRY(cudaEventCreate(&s.ev_k1));
+    CUDA_TRY(cudaMalloc((void**)&s.d_info, sizeof(ChunkInfo)));
+    CUDA_TRY(cudaHostAlloc((void**)&s.h_info, sizeof(ChunkInfo), cudaHostAllocDefault));
+    CUDA_TRY(cudaMalloc((void**)&s.d_queue, sizeof(unsigned int)));
+    return BSW_OK;
+}
+
+void slot_destroy(Slot& s)
+{
+    if (s.st) cudaStreamDestroy(s.st);
+    for (cudaEvent_t e : {s.ev_info, s.ev_dp, s.ev_out, s.ev_fork, s.ev_k0, s.ev_k1})
+        if (e) cudaEventDestroy(e);
+    release(s.raw_pairs); release(s.desc); release(s.meta); release(s.res); release(s.perm); release(s.rank);
+    release(s.bins); release(s.nlist); release(s.llist); release(s.qpk); release(s.tpk); release(s.scratch);
+    release(s.qraw); release(s.rraw);
+    if (s.d_info) cudaFree(s.d_info);
+    if (s.h_info) cudaFreeHost(s.h_info);
+    if (s.d_queue) cudaFree(s.d_queue);
+}
+
+int get_slot(bsw_engine* eng, DevCtx& c, int k, Slot** out)
+{
+    while ((int)c.slots.size() <= k) {
+        c.slots.emplace_back();
+        if (int rc = slot_create(eng, c.slots.back())) return rc;
     }
-    if (c.n_short > cuts.back()) cuts.push_back(c.n_short);
-    c.nchunks = (int)cuts.size() - 1;
-    for (int k = 0; k < c.nchunks; ++k) {
-        Chunk& ch = c.chunks[k];
-        ch.s0 = cuts[k]; ch.s1 = cuts[k + 1];
-        ch.q0 = c.qoff[ch.s0]; ch.q1 = c.qoff[ch.s1]; ch.t0 = c.toff[ch.s0]; ch.t1 = c.toff[ch.s1];
-        ch.scattered = false;
-        ch.plan.clear();
-        for (int64_t s = ch.s0; s < ch.s1;) {
-            const int64_t e = std::min(ch.s1, s + SHORT_BLOCK);
-            const int qs = stride_for(c.len2[e - 1]);                 // ascending in len2
-            if (!ch.plan.empty() && ch.plan.back().qstride == qs) ch.plan.back().count += (int)(e - s);
-            else ch.plan.push_back(Launch{(int)s, (int)(e - s), qs});
-            s = e;
+    *out = &c.slots[(size_t)k];
+    return BSW_OK;
+}
+
+inline int grid_for(const DevCtx& c, int n, int per_block)
+{
+    return std::max(1, std::min((n + per_block - 1) / per_block, c.sms * 8));
+}
+
+// ------------------------------------------------------------------------------------------
+// stage A, direct route: records DMA + scan; the summary comes back through ev_info
+// ------------------------------------------------------------------------------------------
+int direct_begin(bsw_engine* eng, DevCtx& c, Slot& s, const SeqPair* pairs)
+{
+    const size_t bytes = (size_t)s.n * sizeof(SeqPair);
+    if (int rc = ensure(eng, s.raw_pairs, bytes)) return rc;
+    if (int rc = ensure(eng, s.desc, (size_t)s.n)) return rc;
+    init_info(*s.h_info);
+    CUDA_TRY(cudaMemcpyAsync(s.d_info, s.h_info, sizeof(ChunkInfo), cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(s.raw_pairs.d, pairs + s.a, bytes, cudaMemcpyHostToDevice, s.st));
+    const long long base0_r = pairs[s.a].idr, base0_q = pairs[s.a].idq;     // one record read by the host
+    bsw_scan_pairs<<<grid_for(c, s.n, 256), 256, 0, s.st>>>(
+        reinterpret_cast<const SeqPair*>(s.raw_pairs.d), s.n, base0_r, base0_q, eng->p.match, eng->short_max,
+        s.desc.d, s.d_info);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(s.h_info, s.d_info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, s.st));
+    CUDA_TRY(cudaEventRecord(s.ev_info, s.st));
+    eng->stats.h2d_bytes += (int64_t)bytes;
+    eng->stats.kernel_launches++;
+    return BSW_OK;
+}
+
+// stage B, direct route: sequences to the device (DMA of the spanned range, or mapped reads)
+int direct_sequences(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer)
+{
+    CUDA_TRY(cudaEventSynchronize(s.ev_info));
+    s.info = *s.h_info;
+    if (s.info.bad) return BSW_ERR_DOMAIN;
+    const long long base0_r = pairs[s.a].idr, base0_q = pairs[s.a].idq;
+    struct Side { const uint8_t* host; long long base0; unsigned long long mn, mx, bases; Buf<uint8_t>* buf; const uint8_t** out; };
+    Side sides[2] = {{seq_qer, base0_q, s.info.min_q, s.info.max_q, s.info.qbases, &s.qraw, &s.qbase},
+                     {seq_ref, base0_r, s.info.min_r, s.info.max_r, s.info.tbases, &s.rraw, &s.rbase}};
+    for (Side& sd : sides) {
+        const long long lo = sd.base0 + ((long long)sd.mn - OFF_BIAS);       // absolute byte offsets [lo, hi)
+        const long long hi = sd.base0 + ((long long)sd.mx - OFF_BIAS);
+        const unsigned long long span = (unsigned long long)(hi - lo);
+        const bool dense = span <= 2 * sd.bases + (1ull << 20);
+        if (dense) {
+            const long long lo_al = lo & ~15ll;                             // keep the source's 16-byte phase
+            const size_t bytes = (size_t)(hi - lo_al);
+            if (int rc = ensure(eng, *sd.buf, bytes + 64)) return rc;
+            CUDA_TRY(cudaMemcpyAsync(sd.buf->d, sd.host + lo_al, bytes, cudaMemcpyHostToDevice, s.st));
+            *sd.out = sd.buf->d + (sd.base0 - lo_al);
+            eng->stats.h2d_bytes += (int64_t)bytes;
+        } else {
+            void* dp = nullptr;
+            CUDA_TRY(cudaHostGetDevicePointer(&dp, const_cast<uint8_t*>(sd.host), 0));
+            *sd.out = static_cast<const uint8_t*>(dp) + sd.base0;
+            eng->stats.h2d_bytes += (int64_t)sd.bases;
         }
     }
     return BSW_OK;
 }
 
-// pack one chunk of a shard into pinned staging (host threads), flag N-containing pairs
-void pack_chunk(bsw_engine* eng, DevCtx& c, const Chunk& ch, const SeqPair* pairs, const uint8_t* seq_ref,
-                const uint8_t* seq_qer)
+// ------------------------------------------------------------------------------------------
+// stage A+B, staged route: one streaming host pass builds descriptors + gathers the bytes
+// ------------------------------------------------------------------------------------------
+int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer)
 {
-    (void)pairs;
-    const uint32_t* idx = c.idx.data();
-    const uint64_t* offr = eng->sb.offr.data();
-    const uint64_t* offq = eng->sb.offq.data();
-    eng->pool->for_range(ch.s1 - ch.s0, 1024, [&](int64_t b, int64_t e, int) {
-        b += ch.s0; e += ch.s0;
-        for (int64_t s = b; s < e; ++s) {
-            if (s + 16 < e) { __builtin_prefetch(&offq[idx[s + 16]], 0, 0); __builtin_prefetch(&offr[idx[s + 16]], 0, 0); }
-            if (s + 4 < e) {
-                const uint32_t nx = idx[s + 4];
-                __builtin_prefetch(seq_qer + offq[nx], 0, 0);
-                __builtin_prefetch(seq_ref + offr[nx], 0, 0);
-                __builtin_prefetch(seq_ref + offr[nx] + 64, 0, 0);
+    const double t0 = now_ms();
+    const SeqPair* P = pairs + s.a;
+    const int n = s.n;
+    const int match = eng->p.match, short_max = eng->short_max;
+    // pass 1: validate + byte totals per block of 4096 pairs
+    const int BLK = 4096;
+    const int nblk = (n + BLK - 1) / BLK;
+    std::vector<uint64_t> qsum((size_t)nblk + 1, 0), rsum((size_t)nblk + 1, 0);
+    std::vector<ChunkInfo> part((size_t)eng->pool->size());
+    for (ChunkInfo& I : part) init_info(I);
+    eng->pool->run(nblk, [&](int64_t b, int t) {
+        ChunkInfo& I = part[(size_t)t];
+        uint64_t q = 0, r = 0;
+        const int lo = (int)b * BLK, hi = std::min(n, lo + BLK);
+        for (int k = lo; k < hi; ++k) {
+            const SeqPair& sp = P[k];
+            if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.h0 < 1 ||
+                (int64_t)sp.h0 + (int64_t)sp.len2 * match > 32767 || sp.idr < 0 || sp.idq < 0) { I.bad++; continue; }
+            q += (uint64_t)sp.len2; r += (uint64_t)sp.len1;
+            I.nominal += (unsigned long long)sp.len1 * (unsigned long long)sp.len2;
+            I.hist[std::min(sp.len2, LEN_HIST - 1)]++;
+            I.qmax_all = std::max(I.qmax_all, sp.len2);
+            I.qbases += (unsigned long long)sp.len2; I.tbases += (unsigned long long)sp.len1;
+            if (sp.len2 <= short_max) {
+                I.n_short++;
+                I.mn[0] = std::min(I.mn[0], sp.len2); I.mx[0] = std::max(I.mx[0], sp.len2);
+                I.mn[1] = std::min(I.mn[1], sp.h0);   I.mx[1] = std::max(I.mx[1], sp.h0);
+                I.mn[2] = std::min(I.mn[2], sp.len1); I.mx[2] = std::max(I.mx[2], sp.len1);
             }
-            const uint32_t i = idx[s];
-            const int l2 = c.len2[s], l1 = c.len1[s];
-            const bool nq = pack2(seq_qer + offq[i], l2, c.q.h + c.qoff[s]);
-            const bool nr = pack2(seq_ref + offr[i], l1, c.t.h + c.toff[s]);
-            const int flag = (nq | nr) ? BSW_META_NFLAG : 0;
-            c.hasn[s] = (uint8_t)(flag != 0);
-            c.meta.h[s] = make_int4((int)c.qoff[s], (int)c.toff[s], l2 | (l1 << 16), c.h0[s] | flag);
+        }
+        qsum[(size_t)b + 1] = q; rsum[(size_t)b + 1] = r;
+    });
+    ChunkInfo& I = s.info;
+    init_info(I);
+    for (const ChunkInfo& p : part) {
+        I.bad += p.bad; I.nominal += p.nominal; I.n_short += p.n_short; I.qbases += p.qbases; I.tbases += p.tbases;
+        I.qmax_all = std::max(I.qmax_all, p.qmax_all);
+        for (int f = 0; f < 3; ++f) { I.mn[f] = std::min(I.mn[f], p.mn[f]); I.mx[f] = std::max(I.mx[f], p.mx[f]); }
+        for (int k = 0; k < LEN_HIST; ++k) I.hist[k] += p.hist[k];
+    }
+    if (I.bad) return BSW_ERR_DOMAIN;
+    for (int b = 0; b < nblk; ++b) { qsum[(size_t)b + 1] += qsum[(size_t)b]; rsum[(size_t)b + 1] += rsum[(size_t)b]; }
+    const uint64_t qtot = qsum[(size_t)nblk], rtot = rsum[(size_t)nblk];
+    if (qtot > 0x3fffffffull || rtot > 0x3fffffffull) { eng->err = "chunk too large for 32-bit byte offsets"; return BSW_ERR_PARAM; }
+    if (int rc = ensure(eng, s.desc, (size_t)n, true)) return rc;
+    if (int rc = ensure(eng, s.qraw, (size_t)qtot + 64, true)) return rc;
+    if (int rc = ensure(eng, s.rraw, (size_t)rtot + 64, true)) return rc;
+    // pass 2: gather the bytes, write descriptors (offsets into the staging buffers)
+    eng->pool->run(nblk, [&](int64_t b, int) {
+        uint64_t q = qsum[(size_t)b], r = rsum[(size_t)b];
+        const int lo = (int)b * BLK, hi = std::min(n, lo + BLK);
+        for (int k = lo; k < hi; ++k) {
+            const SeqPair& sp = P[k];
+            if (k + 4 < hi) {
+                __builtin_prefetch(seq_qer + P[k + 4].idq, 0, 0);
+                __builtin_prefetch(seq_ref + P[k + 4].idr, 0, 0);
+                __builtin_prefetch(seq_ref + P[k + 4].idr + 64, 0, 0);
+            }
+            memcpy(s.qraw.h + q, seq_qer + sp.idq, (size_t)sp.len2);
+            memcpy(s.rraw.h + r, seq_ref + sp.idr, (size_t)sp.len1);
+            s.desc.h[k] = make_int4((int)q, (int)r, sp.len2 | (sp.len1 << 16), sp.h0);
+            q += (uint64_t)sp.len2; r += (uint64_t)sp.len1;
         }
     });
-}
-
-int h2d_chunk(bsw_engine* eng, DevCtx& c, Chunk& ch)
-{
-    cudaStream_t st = c.st_copy;
-    CUDA_TRY(cudaMemcpyAsync(c.meta.d + ch.s0, c.meta.h + ch.s0, sizeof(int4) * (size_t)(ch.s1 - ch.s0), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.q.d + ch.q0, c.q.h + ch.q0, sizeof(uint32_t) * (ch.q1 - ch.q0), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.t.d + ch.t0, c.t.h + ch.t0, sizeof(uint32_t) * (ch.t1 - ch.t0), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaEventRecord(ch.ev_h2d, st));
-    eng->stats.h2d_bytes += (int64_t)(sizeof(int4) * (size_t)(ch.s1 - ch.s0) + 4 * ((ch.q1 - ch.q0) + (ch.t1 - ch.t0)));
+    memset(s.qraw.h + qtot, 0, 64); memset(s.rraw.h + rtot, 0, 64);
+    eng->stats.ms_pack += now_ms() - t0;
+    // H2D
+    init_info(*s.h_info);
+    CUDA_TRY(cudaMemcpyAsync(s.d_info, s.h_info, sizeof(ChunkInfo), cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(s.desc.d, s.desc.h, sizeof(int4) * (size_t)n, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(s.qraw.d, s.qraw.h, (size_t)qtot + 64, cudaMemcpyHostToDevice, s.st));
+    CUDA_TRY(cudaMemcpyAsync(s.rraw.d, s.rraw.h, (size_t)rtot + 64, cudaMemcpyHostToDevice, s.st));
+    s.qbase = s.qraw.d; s.rbase = s.rraw.d;
+    eng->stats.h2d_bytes += (int64_t)(sizeof(int4) * (size_t)n + qtot + rtot + 128);
     return BSW_OK;
 }
 
-// launches of one chunk, spread over the compute streams; longest class first
-int launch_chunk(bsw_engine* eng, DevCtx& c, Chunk& ch, bool wait_h2d)
+// ------------------------------------------------------------------------------------------
+// stage C (both routes): pack, bucket, launch plan
+// ------------------------------------------------------------------------------------------
+int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
 {
+    const ChunkInfo& I = s.info;
+    const int n = s.n;
+    s.n_sorted = I.n_short;
+    const size_t qwords = (size_t)(I.qbases / 16) + (size_t)I.n_short + 8;
+    const size_t twords = (size_t)(I.tbases / 16) + (size_t)I.n_short + 8;
+    if (int rc = ensure(eng, s.meta, (size_t)n)) return rc;
+    if (int rc = ensure(eng, s.res, (size_t)n, !s.direct)) return rc;
+    if (int rc = ensure(eng, s.qpk, qwords)) return rc;
+    if (int rc = ensure(eng, s.tpk, twords)) return rc;
+    if (int rc = ensure(eng, s.perm, (size_t)n)) return rc;
+    if (int rc = ensure(eng, s.rank, (size_t)n)) return rc;
+    if (int rc = ensure(eng, s.nlist, (size_t)n)) return rc;
+    if (int rc = ensure(eng, s.llist, (size_t)n)) return rc;
+    bsw_pack_pairs<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, s.qbase, s.rbase, eng->short_max, s.meta.d,
+                                                          s.qpk.d, s.tpk.d, s.nlist.d, s.llist.d, s.d_info);
+    eng->stats.kernel_launches++;
+    s.plan.clear();
+    if (I.n_short > 0) {
+        BucketKey K;
+        K.mn2 = I.mn[0]; K.mnh = I.mn[1]; K.mn1 = I.mn[2];
+        const int b_l2 = bits_for((uint32_t)(I.mx[0] - I.mn[0]));
+        K.b_h0 = bits_for((uint32_t)(I.mx[1] - I.mn[1]));
+        K.b_l1 = bits_for((uint32_t)(I.mx[2] - I.mn[2]));
+        const int total = b_l2 + K.b_h0 + K.b_l1;
+        K.drop = std::max(0, total - BUCKET_BITS);          // only ever eats h0 / len1 bits: b_l2 <= 10
+        K.short_max = eng->short_max;
+        const int nbins = 1 << (total - K.drop);
+        const int ntiles = (nbins + SCAN_TILE - 1) / SCAN_TILE;           // <= 256
+        if (int rc = ensure(eng, s.bins, (size_t)nbins + 1024)) return rc;   // bins, then the tile totals
+        uint32_t* totals = s.bins.d + nbins;
+        CUDA_TRY(cudaMemsetAsync(s.bins.d, 0, sizeof(uint32_t) * (size_t)nbins, s.st));
+        bsw_bucket_count<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, K, s.bins.d, s.rank.d);
+        bsw_bucket_scan_tiles<<<ntiles, 256, 0, s.st>>>(s.bins.d, nbins, totals);
+        bsw_bucket_scan_totals<<<1, 1024, 0, s.st>>>(totals, ntiles);
+        bsw_bucket_scatter<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d);
+        eng->stats.kernel_launches += 4;
+        // launch plan: the processing order ascends in len2, so the shared-memory classes are
+        // prefix ranges of it, read off the len2 histogram
+        int pos = 0;
+        for (int l = I.mn[0]; l <= std::min(I.mx[0], eng->short_max); ++l) {
+            const int cnt = (int)I.hist[l];
+            if (!cnt) continue;
+            const int qs = stride_for(l);
+            if (!s.plan.empty() && s.plan.back().qstride == qs) s.plan.back().count += cnt;
+            else s.plan.push_back(Launch{pos, cnt, qs});
+            pos += cnt;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    // the pack kernel's counters (pairs for the byte kernels) travel back with the chunk
+    CUDA_TRY(cudaMemcpyAsync(s.h_info, s.d_info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, s.st));
+    return BSW_OK;
+}
+
+// DP launches of a chunk: fan out over the device's compute streams, longest class first
+int launch_dp(bsw_engine* eng, DevCtx& c, Slot& s)
+{
+    if (s.plan.empty()) return BSW_OK;
+    CUDA_TRY(cudaEventRecord(s.ev_fork, s.st));
+    const int nl = (int)s.plan.size();
+    const int used = std::min(nl, NSTREAMS);
+    for (int k = 0; k < used; ++k) CUDA_TRY(cudaStreamWaitEvent(c.cs[k], s.ev_fork, 0));
     int li = 0;
-    bool used[NSTREAMS] = {};
-    for (int k = (int)ch.plan.size() - 1; k >= 0; --k, ++li) {
-        const Launch& L = ch.plan[k];
-        const int si = li % NSTREAMS;
-        cudaStream_t st = c.st[si];
-        if (wait_h2d && !used[si]) CUDA_TRY(cudaStreamWaitEvent(st, ch.ev_h2d, 0));
-        used[si] = true;
+    for (int k = nl - 1; k >= 0; --k, ++li) {
+        const Launch& L = s.plan[(size_t)k];
+        cudaStream_t st = c.cs[li % NSTREAMS];
         const int grid = (L.count + SHORT_BLOCK - 1) / SHORT_BLOCK;
-        const size_t smem = short_smem_bytes(L.qstride);
-        bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, smem, st>>>(
-            c.meta.d, c.q.d, c.t.d, c.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
+        bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, short_smem_bytes(L.qstride), st>>>(
+            s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
+        eng->stats.kernel_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    for (int k = 0; k < used; ++k) {
+        CUDA_TRY(cudaEventRecord(c.ev_join[k], c.cs[k]));
+        CUDA_TRY(cudaStreamWaitEvent(s.st, c.ev_join[k], 0));
+    }
+    return BSW_OK;
+}
+
+// byte-reading kernels for the pairs the pack kernel listed (N-containing / long); counts known
+int launch_bytes(bsw_engine* eng, DevCtx& c, Slot& s)
+{
+    if (s.n_nlist > 0) {
+        const int qstride = stride_for(s.qmax_n);
+        const int grid = (int)((s.n_nlist + SHORT_BLOCK - 1) / SHORT_BLOCK);
+        bsw_short_kernel<SHORT_BLOCK, true><<<grid, SHORT_BLOCK, short_smem_bytes(qstride), s.st>>>(
+            s.desc.d, s.nlist.d, reinterpret_cast<const uint32_t*>(s.qbase), reinterpret_cast<const uint32_t*>(s.rbase),
+            s.res.d, 0, (int)s.n_nlist, qstride, eng->kp, c.d_cells);
+        eng->stats.kernel_launches++;
+    }
+    if (s.n_llist > 0) {
+        s.long_stride = (s.info.qmax_all + 12) & ~3;
+        int64_t blocks = std::min<int64_t>(((int64_t)s.n_llist + LONG_WARPS - 1) / LONG_WARPS, (int64_t)c.sms * 8);
+        const int64_t cap_words = (int64_t)(256ll << 20) / 4;       // <= 256 MB of eh rows
+        blocks = std::max<int64_t>(1, std::min(blocks, cap_words / ((int64_t)s.long_stride * LONG_WARPS)));
+        s.long_blocks = (int)blocks;
+        if (int rc = ensure(eng, s.scratch, (size_t)blocks * LONG_WARPS * (size_t)s.long_stride)) return rc;
+        CUDA_TRY(cudaMemsetAsync(s.d_queue, 0, sizeof(unsigned int), s.st));
+        bsw_long_kernel<<<s.long_blocks, LONG_WARPS * 32, 0, s.st>>>(
+            s.desc.d, s.llist.d, s.qbase, s.rbase, s.res.d, (int)s.n_llist, eng->kp, s.scratch.d, s.long_stride,
+            s.d_queue, c.d_cells);
         eng->stats.kernel_launches++;
     }
     CUDA_TRY(cudaGetLastError());
     return BSW_OK;
 }
 
-int d2h_chunk(bsw_engine* eng, DevCtx& c, Chunk& ch)
+// results of a chunk leave the device: straight into the caller's records (direct) or D2H
+int output_chunk(bsw_engine* eng, DevCtx& c, Slot& s, SeqPair* pairs)
 {
-    for (int s = 0; s < NSTREAMS; ++s) {
-        CUDA_TRY(cudaEventRecord(c.ev_join[s], c.st[s]));
-        CUDA_TRY(cudaStreamWaitEvent(c.st_d2h, c.ev_join[s], 0));
+    if (s.direct) {
+        // results go into the device copy of the records, which then returns by one DMA (the
+        // input fields come back as they left; per-field writes over PCIe would be 4-byte TLPs)
+        bsw_writeback<<<grid_for(c, s.n, 256), 256, 0, s.st>>>(s.res.d, s.n, reinterpret_cast<SeqPair*>(s.raw_pairs.d));
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(pairs + s.a, s.raw_pairs.d, (size_t)s.n * sizeof(SeqPair), cudaMemcpyDeviceToHost, s.st));
+        eng->stats.kernel_launches++;
+        eng->stats.d2h_bytes += (int64_t)s.n * (int64_t)sizeof(SeqPair);
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(s.res.h, s.res.d, sizeof(int4) * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
+        eng->stats.d2h_bytes += (int64_t)sizeof(int4) * s.n;
     }
-    CUDA_TRY(cudaMemcpyAsync(c.res.h + ch.s0, c.res.d + ch.s0, sizeof(int4) * (size_t)(ch.s1 - ch.s0), cudaMemcpyDeviceToHost, c.st_d2h));
-    CUDA_TRY(cudaEventRecord(ch.ev_done, c.st_d2h));
-    eng->stats.d2h_bytes += (int64_t)(sizeof(int4) * (size_t)(ch.s1 - ch.s0));
+    CUDA_TRY(cudaEventRecord(s.ev_out, s.st));
     return BSW_OK;
 }
 
@@ -359,141 +533,23 @@ inline void write_result(SeqPair& sp, const int4 v)
     sp.gscore = (int16_t)(v.z & 0xffff); sp.max_off = (int16_t)(v.z >> 16);
 }
 
-void scatter_chunk(bsw_engine* eng, DevCtx& c, Chunk& ch, SeqPair* pairs)
+// staged route: second streaming pass, results into the caller's records
+void unpack_chunk(bsw_engine* eng, Slot& s, SeqPair* pairs)
 {
-    const uint32_t* idx = c.idx.data();
-    const int4* r = c.res.h;
-    eng->pool->for_range(ch.s1 - ch.s0, 4096, [&](int64_t b, int64_t e, int) {
-        b += ch.s0; e += ch.s0;
-        for (int64_t s = b; s < e; ++s) {
-            if (s + 8 < e) __builtin_prefetch(&pairs[idx[s + 8]].score, 1, 0);
-            if (!c.hasn[s]) write_result(pairs[idx[s]], r[s]);
-        }
+    if (s.direct) return;
+    const double t0 = now_ms();
+    SeqPair* P = pairs + s.a;
+    const int4* r = s.res.h;
+    eng->pool->for_range(s.n, 8192, [&](int64_t b, int64_t e, int) {
+        for (int64_t k = b; k < e; ++k) write_result(P[k], r[k]);
     });
-    ch.scattered = true;
+    eng->stats.ms_scatter += now_ms() - t0;
 }
 
-// byte-staged pairs: short pairs with N + all long pairs.  Staging (host) and H2D.
-int stage_bytes(bsw_engine* eng, DevCtx& c, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer)
+// after ev_dp: the pack kernel's counters are on the host
+void read_lists(Slot& s)
 {
-    (void)pairs;
-    c.pos_n.clear();
-    c.qmax_bytes_short = 0;
-    for (int64_t s = 0; s < c.n_short; ++s)
-        if (c.hasn[s]) { c.pos_n.push_back((uint32_t)s); c.qmax_bytes_short = std::max<int>(c.qmax_bytes_short, c.len2[s]); }
-    c.n_bytes_short = (int64_t)c.pos_n.size();
-    for (int64_t s = c.n_short; s < c.n; ++s) c.pos_n.push_back((uint32_t)s);
-    const size_t nb = c.pos_n.size();
-    if (nb == 0) return BSW_OK;
-    if (int rc = ensure(eng, c.meta_n, nb)) return rc;
-    if (int rc = ensure(eng, c.res_n, nb)) return rc;
-    uint64_t qo = 0, to = 0;
-    for (size_t k = 0; k < nb; ++k) {
-        const uint32_t s = c.pos_n[k];
-        c.meta_n.h[k] = make_int4((int)qo, (int)to, c.len2[s] | (c.len1[s] << 16), c.h0[s]);
-        qo += ((uint64_t)c.len2[s] + 7) & ~3ull; to += ((uint64_t)c.len1[s] + 7) & ~3ull;   // 4-byte aligned, >= 4 B slack
-    }
-    if (qo > 0x7fffffffull || to > 0x7fffffffull) { eng->err = "too many byte-staged bases in one batch"; return BSW_ERR_PARAM; }
-    c.qb_bytes = qo; c.tb_bytes = to;
-    if (int rc = ensure(eng, c.qb, c.qb_bytes + 16)) return rc;
-    if (int rc = ensure(eng, c.tb, c.tb_bytes + 16)) return rc;
-    eng->pool->for_range((int64_t)nb, 256, [&](int64_t b, int64_t e, int) {
-        for (int64_t k = b; k < e; ++k) {
-            const uint32_t s = c.pos_n[k], i = c.idx[s];
-            memcpy(c.qb.h + c.meta_n.h[k].x, seq_qer + eng->sb.offq[i], (size_t)c.len2[s]);
-            memcpy(c.tb.h + c.meta_n.h[k].y, seq_ref + eng->sb.offr[i], (size_t)c.len1[s]);
-        }
-    });
-    if (c.n_long > 0) {
-        const int qmax = c.len2[c.n - 1];
-        c.long_stride = (qmax + 12) & ~3;
-        int64_t blocks = std::min<int64_t>((c.n_long + LONG_WARPS - 1) / LONG_WARPS, (int64_t)c.sms * 8);
-        const int64_t cap_words = (int64_t)(256ll << 20) / 4;       // <= 256 MB of eh rows
-        blocks = std::max<int64_t>(1, std::min(blocks, cap_words / ((int64_t)c.long_stride * LONG_WARPS)));
-        c.long_blocks = (int)blocks;
-        if (int rc = ensure(eng, c.scratch, (size_t)blocks * LONG_WARPS * c.long_stride, false)) return rc;
-    }
-    cudaStream_t st = c.st_copy;
-    CUDA_TRY(cudaMemcpyAsync(c.meta_n.d, c.meta_n.h, sizeof(int4) * nb, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.qb.d, c.qb.h, c.qb_bytes, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.tb.d, c.tb.h, c.tb_bytes, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaEventRecord(c.ev_a, st));
-    eng->stats.h2d_bytes += (int64_t)(sizeof(int4) * nb + c.qb_bytes + c.tb_bytes);
-    return BSW_OK;
-}
-
-int launch_bytes(bsw_engine* eng, DevCtx& c, bool wait_h2d)
-{
-    if (c.pos_n.empty()) return BSW_OK;
-    cudaStream_t st = c.st[0];
-    if (wait_h2d) CUDA_TRY(cudaStreamWaitEvent(st, c.ev_a, 0));
-    if (c.n_bytes_short > 0) {
-        const int grid = (int)((c.n_bytes_short + SHORT_BLOCK - 1) / SHORT_BLOCK);
-        const int qstride = stride_for(c.qmax_bytes_short);
-        bsw_short_kernel<SHORT_BLOCK, true><<<grid, SHORT_BLOCK, short_smem_bytes(qstride), st>>>(
-            c.meta_n.d, reinterpret_cast<const uint32_t*>(c.qb.d), reinterpret_cast<const uint32_t*>(c.tb.d),
-            c.res_n.d, 0, (int)c.n_bytes_short, qstride, eng->kp, c.d_cells);
-        eng->stats.kernel_launches++;
-    }
-    if (c.n_long > 0) {
-        CUDA_TRY(cudaMemsetAsync(c.d_queue, 0, sizeof(unsigned int), st));
-        bsw_long_kernel<<<c.long_blocks, LONG_WARPS * 32, 0, st>>>(
-            c.meta_n.d + c.n_bytes_short, c.qb.d, c.tb.d, c.res_n.d + c.n_bytes_short, (int)c.n_long, eng->kp,
-            c.scratch.d, c.long_stride, c.d_queue, c.d_cells);
-        eng->stats.kernel_launches++;
-    }
-    CUDA_TRY(cudaGetLastError());
-    return BSW_OK;
-}
-
-int d2h_bytes(bsw_engine* eng, DevCtx& c)
-{
-    if (c.pos_n.empty()) return BSW_OK;
-    CUDA_TRY(cudaEventRecord(c.ev_join[0], c.st[0]));
-    CUDA_TRY(cudaStreamWaitEvent(c.st_d2h, c.ev_join[0], 0));
-    CUDA_TRY(cudaMemcpyAsync(c.res_n.h, c.res_n.d, sizeof(int4) * c.pos_n.size(), cudaMemcpyDeviceToHost, c.st_d2h));
-    eng->stats.d2h_bytes += (int64_t)(sizeof(int4) * c.pos_n.size());
-    return BSW_OK;
-}
-
-void scatter_bytes(bsw_engine* eng, DevCtx& c, SeqPair* pairs)
-{
-    eng->pool->for_range((int64_t)c.pos_n.size(), 4096, [&](int64_t b, int64_t e, int) {
-        for (int64_t k = b; k < e; ++k) write_result(pairs[c.idx[c.pos_n[k]]], c.res_n.h[k]);
-    });
-}
-
-// Splits the sorted batch across the engine's devices (views copied per shard).
-int build_shards(bsw_engine* eng)
-{
-    SortedBatch& sb = eng->sb;
-    const int ndev = (int)eng->devs.size();
-    if (ndev == 1) {
-        DevCtx& c = eng->devs[0];
-        c.n = sb.n;
-        c.idx.swap(sb.idx); c.len2.swap(sb.len2); c.len1.swap(sb.len1); c.h0.swap(sb.h0);
-        return BSW_OK;
-    }
-    std::vector<std::vector<int64_t>> blocks_of;
-    partition_blocks(sb, eng->w, ndev, blocks_of);
-    for (int g = 0; g < ndev; ++g) {
-        DevCtx& c = eng->devs[g];
-        size_t cnt = 0;
-        for (int64_t b : blocks_of[g]) cnt += (size_t)(std::min(sb.n, b * 1024 + 1024) - b * 1024);
-        c.idx.reserve(cnt); c.len2.reserve(cnt); c.len1.reserve(cnt); c.h0.reserve(cnt);
-        size_t pos = 0;
-        for (int64_t b : blocks_of[g]) {
-            const int64_t lo = b * 1024, hi = std::min(sb.n, lo + 1024);
-            const size_t m = (size_t)(hi - lo);
-            memcpy(c.idx.data() + pos, sb.idx.data() + lo, m * sizeof(uint32_t));
-            memcpy(c.len2.data() + pos, sb.len2.data() + lo, m * sizeof(uint16_t));
-            memcpy(c.len1.data() + pos, sb.len1.data() + lo, m * sizeof(uint16_t));
-            memcpy(c.h0.data() + pos, sb.h0.data() + lo, m * sizeof(uint16_t));
-            pos += m;
-        }
-        c.n = (int64_t)cnt;
-    }
-    return BSW_OK;
+    s.n_nlist = s.h_info->n_nlist; s.n_llist = s.h_info->n_llist; s.qmax_n = s.h_info->qmax_n;
 }
 
 int begin_batch(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
@@ -507,23 +563,121 @@ int begin_batch(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, c
     memset(&S, 0, sizeof(S));
     S.pairs = n;
     eng->n = n; eng->w = w; eng->kp.w = w;
-    const double t0 = now_ms();
-    build_sorted_batch(*eng->pool, pairs, n, eng->p.match, eng->sb);
-    if (!eng->sb.domain_ok) {
-        eng->err = "pair outside the domain: need 1<=len1,len2<=32767, h0>=1, h0+len2*match<=32767, offsets>=0 (bandedSWA.h:84, SURVEY 8b)";
-        return BSW_ERR_DOMAIN;
-    }
-    S.cells_nominal = eng->sb.cells_nominal;
-    if (int rc = build_shards(eng)) return rc;
-    S.ms_sort = now_ms() - t0;
     return BSW_OK;
+}
+
+const char* kDomainMsg =
+    "pair outside the domain: need 1<=len1,len2<=32767, h0>=1, h0+len2*match<=32767, offsets>=0 "
+    "(bandedSWA.h:84, SURVEY 8b); result fields of the batch are unspecified";
+
+struct ChunkRef { int dev; int slot; };
+
+// Runs the chunks of the batch through the pipeline.  keep == true: stop before the DP launches
+// and keep every chunk resident in its own slot (bsw_stage).
+int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
+                 int64_t n, int64_t chunk_pairs, bool keep)
+{
+    bsw_stats& S = eng->stats;
+    const int ndev = (int)eng->devs.size();
+    const bool direct = is_pinned(pairs) && is_pinned(seq_ref) && is_pinned(seq_qer);
+    const int64_t nchunks = (n + chunk_pairs - 1) / chunk_pairs;
+    const int64_t per = nchunks ? (n + nchunks - 1) / nchunks : 0;
+    std::vector<ChunkRef> refs((size_t)nchunks);
+    eng->staged_chunks.clear();
+    for (DevCtx& c : eng->devs) {
+        CUDA_TRY(cudaSetDevice(c.dev));
+        if (int rc = set_kernel_attrs(eng, c)) return rc;
+        CUDA_TRY(cudaMemsetAsync(c.d_cells, 0, sizeof(unsigned long long), c.cs[0]));
+        CUDA_TRY(cudaStreamSynchronize(c.cs[0]));
+    }
+    auto slot_of = [&](int64_t k) -> Slot& { return eng->devs[(size_t)refs[(size_t)k].dev].slots[(size_t)refs[(size_t)k].slot]; };
+    auto dev_of = [&](int64_t k) -> DevCtx& { return eng->devs[(size_t)refs[(size_t)k].dev]; };
+
+    // finish: the chunk's DP is enqueued; learn the byte-kernel lists, run them, send results out
+    auto finish = [&](int64_t k) -> int {
+        DevCtx& c = dev_of(k); Slot& s = slot_of(k);
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaEventSynchronize(s.ev_dp));
+        read_lists(s);
+        S.n_short += s.n_sorted - (int)s.n_nlist; S.n_long += (int)s.n_llist;
+        if (int rc = launch_bytes(eng, c, s)) return rc;
+        CUDA_TRY(cudaEventRecord(s.ev_k1, s.st));
+        return output_chunk(eng, c, s, pairs);
+    };
+    auto retire = [&](int64_t k) -> int {
+        DevCtx& c = dev_of(k); Slot& s = slot_of(k);
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaEventSynchronize(s.ev_out));
+        unpack_chunk(eng, s, pairs);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) S.ms_kernel += (double)ms;
+        return BSW_OK;
+    };
+
+    const int lag = ndev;
+    for (int64_t k = 0; k < nchunks + 2 * lag; ++k) {
+        if (k < nchunks) {
+            const int d = (int)(k % ndev);
+            const int sl = keep ? (int)(k / ndev) : (int)((k / ndev) % NSLOTS);
+            refs[(size_t)k] = ChunkRef{d, sl};
+            DevCtx& c = eng->devs[(size_t)d];
+            CUDA_TRY(cudaSetDevice(c.dev));
+            Slot* sp = nullptr;
+            if (int rc = get_slot(eng, c, sl, &sp)) return rc;
+            Slot& s = *sp;
+            s.a = k * per; s.n = (int)std::min<int64_t>(per, n - s.a);
+            s.direct = direct;
+            CUDA_TRY(cudaEventRecord(s.ev_k0, s.st));
+            int rc;
+            if (direct) {
+                if ((rc = direct_begin(eng, c, s, pairs))) return rc;
+                rc = direct_sequences(eng, s, pairs, seq_ref, seq_qer);
+            } else {
+                rc = staged_prepare(eng, s, pairs, seq_ref, seq_qer);
+            }
+            if (rc) { if (rc == BSW_ERR_DOMAIN) eng->err = kDomainMsg; return rc; }
+            S.cells_nominal += (int64_t)s.info.nominal;
+            if ((rc = device_prepare(eng, c, s))) return rc;
+            if (!keep && (rc = launch_dp(eng, c, s))) return rc;
+            CUDA_TRY(cudaEventRecord(s.ev_dp, s.st));
+            if (keep) eng->staged_chunks.emplace_back(d, sl);
+        }
+        if (keep) continue;
+        if (k - lag >= 0 && k - lag < nchunks) if (int rc = finish(k - lag)) return rc;
+        if (k - 2 * lag >= 0 && k - 2 * lag < nchunks) if (int rc = retire(k - 2 * lag)) return rc;
+    }
+    if (keep) {
+        for (int64_t k = 0; k < nchunks; ++k) {
+            DevCtx& c = dev_of(k); Slot& s = slot_of(k);
+            CUDA_TRY(cudaSetDevice(c.dev));
+            CUDA_TRY(cudaEventSynchronize(s.ev_dp));
+            read_lists(s);
+            S.n_short += s.n_sorted - (int)s.n_nlist; S.n_long += (int)s.n_llist;
+        }
+    }
+    return BSW_OK;
+}
+
+int collect_cells(bsw_engine* eng)
+{
+    for (DevCtx& c : eng->devs) {
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaMemcpy(c.h_cells, c.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        eng->stats.cells_effective += (int64_t)*c.h_cells;
+    }
+    return BSW_OK;
+}
+
+void quiesce(bsw_engine* eng)
+{
+    for (DevCtx& c : eng->devs) { cudaSetDevice(c.dev); cudaDeviceSynchronize(); }
 }
 
 } // namespace
 
 extern "C" {
 
-const char* bsw_version(void) { return "bsw_b200 0.2 sm_100a"; }
+const char* bsw_version(void) { return "bsw_b200 0.3 sm_100a"; }
 
 void bsw_default_params(bsw_params* p)
 {
@@ -591,20 +745,12 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
                                       " is not sm_100: this library carries sm_100a code only");
         }
         c.sms = prop.multiProcessorCount;
-        ok = ok && cudaStreamCreateWithFlags(&c.st_copy, cudaStreamNonBlocking) == cudaSuccess;
-        ok = ok && cudaStreamCreateWithFlags(&c.st_d2h, cudaStreamNonBlocking) == cudaSuccess;
         for (int s = 0; ok && s < NSTREAMS; ++s) {
-            ok = cudaStreamCreateWithFlags(&c.st[s], cudaStreamNonBlocking) == cudaSuccess;
+            ok = cudaStreamCreateWithFlags(&c.cs[s], cudaStreamNonBlocking) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&c.ev_join[s], cudaEventDisableTiming) == cudaSuccess;
         }
-        for (int k2 = 0; ok && k2 < MAX_CHUNKS; ++k2) {
-            ok = cudaEventCreateWithFlags(&c.chunks[k2].ev_h2d, cudaEventDisableTiming) == cudaSuccess;
-            ok = ok && cudaEventCreateWithFlags(&c.chunks[k2].ev_done, cudaEventDisableTiming) == cudaSuccess;
-        }
-        ok = ok && cudaEventCreate(&c.ev_a) == cudaSuccess && cudaEventCreate(&c.ev_b) == cudaSuccess;
-        ok = ok && cudaEventCreate(&c.ev_k0) == cudaSuccess && cudaEventCreate(&c.ev_k1) == cudaSuccess;
+        ok = ok && cudaEventCreate(&c.ev_t0) == cudaSuccess && cudaEventCreate(&c.ev_t1) == cudaSuccess;
         ok = ok && cudaMalloc((void**)&c.d_cells, sizeof(unsigned long long)) == cudaSuccess;
-        ok = ok && cudaMalloc((void**)&c.d_queue, sizeof(unsigned int)) == cudaSuccess;
         ok = ok && cudaHostAlloc((void**)&c.h_cells, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
         if (!ok) {
             std::string m = std::string("device setup failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -622,21 +768,14 @@ void bsw_destroy(bsw_engine* eng)
     for (DevCtx& c : eng->devs) {
         cudaSetDevice(c.dev);
         cudaDeviceSynchronize();
-        for (cudaStream_t s : {c.st_copy, c.st_d2h}) if (s) cudaStreamDestroy(s);
+        for (Slot& s : c.slots) slot_destroy(s);
         for (int s = 0; s < NSTREAMS; ++s) {
-            if (c.st[s]) cudaStreamDestroy(c.st[s]);
+            if (c.cs[s]) cudaStreamDestroy(c.cs[s]);
             if (c.ev_join[s]) cudaEventDestroy(c.ev_join[s]);
         }
-        for (Chunk& ch : c.chunks) {
-            if (ch.ev_h2d) cudaEventDestroy(ch.ev_h2d);
-            if (ch.ev_done) cudaEventDestroy(ch.ev_done);
-        }
-        for (cudaEvent_t e : {c.ev_a, c.ev_b, c.ev_k0, c.ev_k1})
-            if (e) cudaEventDestroy(e);
-        release(c.meta); release(c.res); release(c.meta_n); release(c.res_n); release(c.q); release(c.t);
-        release(c.qb); release(c.tb); release(c.scratch);
+        if (c.ev_t0) cudaEventDestroy(c.ev_t0);
+        if (c.ev_t1) cudaEventDestroy(c.ev_t1);
         if (c.d_cells) cudaFree(c.d_cells);
-        if (c.d_queue) cudaFree(c.d_queue);
         if (c.h_cells) cudaFreeHost(c.h_cells);
     }
     delete eng;
@@ -650,7 +789,25 @@ int bsw_get_stats(const bsw_engine* eng, bsw_stats* out)
 }
 
 // ------------------------------------------------------------------------------------------
-// resident form: stage (host -> HBM), run (kernels only, repeatable), fetch (HBM -> SeqPair[])
+// the hot path: host buffers in, results in place
+// ------------------------------------------------------------------------------------------
+int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
+               int64_t n, int32_t w)
+{
+    if (!eng) return BSW_ERR_PARAM;
+    const double t_begin = now_ms();
+    if (int rc = begin_batch(eng, pairs, seq_ref, seq_qer, n, w)) return rc;
+    if (n == 0) return BSW_OK;
+    const int rc = run_pipeline(eng, pairs, seq_ref, seq_qer, n, CHUNK_EXTEND, false);
+    if (rc != BSW_OK) { quiesce(eng); return rc; }
+    if (int rc2 = collect_cells(eng)) return rc2;
+    eng->stats.ms_total = now_ms() - t_begin;
+    return BSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// resident form: stage (host -> HBM, packed + bucketed), run (DP kernels only, repeatable),
+// fetch (results -> SeqPair[])
 // ------------------------------------------------------------------------------------------
 int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
               int64_t n, int32_t w)
@@ -658,34 +815,13 @@ int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, con
     if (!eng) return BSW_ERR_PARAM;
     const double t_begin = now_ms();
     if (int rc = begin_batch(eng, pairs, seq_ref, seq_qer, n, w)) return rc;
-    bsw_stats& S = eng->stats;
-    for (DevCtx& c : eng->devs) {
-        if (int rc = prepare_shard(eng, c, false)) return rc;
-        if (c.n == 0) continue;
-        const double tp = now_ms();
-        CUDA_TRY(cudaEventRecord(c.ev_a, c.st_copy));
-        for (int k = 0; k < c.nchunks; ++k) {
-            pack_chunk(eng, c, c.chunks[k], pairs, seq_ref, seq_qer);
-            if (int rc = h2d_chunk(eng, c, c.chunks[k])) return rc;
-        }
-        CUDA_TRY(cudaEventRecord(c.ev_b, c.st_copy));
-        S.ms_pack += now_ms() - tp;
-    }
-    for (DevCtx& c : eng->devs) {
-        if (c.n == 0) continue;
-        CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaStreamSynchronize(c.st_copy));
-        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_a, c.ev_b));
-        S.ms_h2d = std::max(S.ms_h2d, (double)ms);
-        const double tp = now_ms();
-        if (int rc = stage_bytes(eng, c, pairs, seq_ref, seq_qer)) return rc;
-        CUDA_TRY(cudaStreamSynchronize(c.st_copy));
-        S.ms_pack += now_ms() - tp;
-        S.n_short += (int32_t)c.n_short;
-        S.n_long += (int32_t)c.n_long;
+    eng->staged_chunks.clear();
+    if (n > 0) {
+        const int rc = run_pipeline(eng, const_cast<SeqPair*>(pairs), seq_ref, seq_qer, n, CHUNK_STAGE, true);
+        if (rc != BSW_OK) { quiesce(eng); return rc; }
     }
     eng->staged = true;
-    S.ms_total = now_ms() - t_begin;
+    eng->stats.ms_total = now_ms() - t_begin;
     return BSW_OK;
 }
 
@@ -695,30 +831,33 @@ int bsw_run_staged(bsw_engine* eng)
     if (!eng->staged) { eng->err = "bsw_run_staged before bsw_stage"; return BSW_ERR_STATE; }
     bsw_stats& S = eng->stats;
     S.kernel_launches = 0; S.ms_kernel = 0; S.cells_effective = 0;
+    // device timeline per GPU: ev_t0 on cs[0] -> every chunk's launches -> joined back -> ev_t1
     for (DevCtx& c : eng->devs) {
-        if (c.n == 0) continue;
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaMemsetAsync(c.d_cells, 0, sizeof(unsigned long long), c.st[0]));
-        CUDA_TRY(cudaEventRecord(c.ev_k0, c.st[0]));
-        for (int s = 1; s < NSTREAMS; ++s) CUDA_TRY(cudaStreamWaitEvent(c.st[s], c.ev_k0, 0));
-        for (int k = c.nchunks - 1; k >= 0; --k)
-            if (int rc = launch_chunk(eng, c, c.chunks[k], false)) return rc;
-        for (int s = 1; s < NSTREAMS; ++s) {
-            CUDA_TRY(cudaEventRecord(c.ev_join[s], c.st[s]));
-            CUDA_TRY(cudaStreamWaitEvent(c.st[0], c.ev_join[s], 0));
-        }
-        if (int rc = launch_bytes(eng, c, false)) return rc;
-        CUDA_TRY(cudaEventRecord(c.ev_k1, c.st[0]));
-        CUDA_TRY(cudaMemcpyAsync(c.h_cells, c.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.st[0]));
+        CUDA_TRY(cudaMemsetAsync(c.d_cells, 0, sizeof(unsigned long long), c.cs[0]));
+        CUDA_TRY(cudaStreamSynchronize(c.cs[0]));
+        CUDA_TRY(cudaEventRecord(c.ev_t0, c.cs[0]));
+    }
+    for (auto& ds : eng->staged_chunks) {
+        DevCtx& c = eng->devs[(size_t)ds.first]; Slot& s = c.slots[(size_t)ds.second];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaStreamWaitEvent(s.st, c.ev_t0, 0));
+        if (int rc = launch_dp(eng, c, s)) return rc;
+        if (int rc = launch_bytes(eng, c, s)) return rc;
+        CUDA_TRY(cudaEventRecord(s.ev_k1, s.st));
+        CUDA_TRY(cudaStreamWaitEvent(c.cs[0], s.ev_k1, 0));
     }
     for (DevCtx& c : eng->devs) {
-        if (c.n == 0) continue;
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaStreamSynchronize(c.st[0]));
-        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_k0, c.ev_k1));
+        CUDA_TRY(cudaEventRecord(c.ev_t1, c.cs[0]));
+    }
+    for (DevCtx& c : eng->devs) {
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaEventSynchronize(c.ev_t1));
+        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_t0, c.ev_t1));
         S.ms_kernel = std::max(S.ms_kernel, (double)ms);
-        S.cells_effective += (int64_t)*c.h_cells;
     }
+    if (int rc = collect_cells(eng)) return rc;
     eng->ran = true;
     return BSW_OK;
 }
@@ -730,105 +869,52 @@ int bsw_fetch(bsw_engine* eng, SeqPair* pairs, int64_t n)
     if (n != eng->n || (n > 0 && !pairs)) { eng->err = "bsw_fetch: pair count differs from the staged batch"; return BSW_ERR_PARAM; }
     bsw_stats& S = eng->stats;
     S.d2h_bytes = 0; S.ms_d2h = 0; S.ms_scatter = 0;
-    for (DevCtx& c : eng->devs) {
-        if (c.n == 0) continue;
+    const bool pinned_out = n > 0 && is_pinned(pairs);
+    for (auto& ds : eng->staged_chunks) {
+        DevCtx& c = eng->devs[(size_t)ds.first]; Slot& s = c.slots[(size_t)ds.second];
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaEventRecord(c.ev_a, c.st_d2h));
-        for (int k = 0; k < c.nchunks; ++k) if (int rc = d2h_chunk(eng, c, c.chunks[k])) return rc;
-        if (int rc = d2h_bytes(eng, c)) return rc;
-        CUDA_TRY(cudaEventRecord(c.ev_b, c.st_d2h));
+        s.direct = pinned_out && s.direct;           // the record DMA needs the chunk's device copy
+        if (!s.direct) if (int rc = ensure(eng, s.res, (size_t)s.n, true)) return rc;
+        if (int rc = output_chunk(eng, c, s, pairs)) return rc;
     }
-    for (DevCtx& c : eng->devs) {
-        if (c.n == 0) continue;
+    for (auto& ds : eng->staged_chunks) {
+        DevCtx& c = eng->devs[(size_t)ds.first]; Slot& s = c.slots[(size_t)ds.second];
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaStreamSynchronize(c.st_d2h));
-        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_a, c.ev_b));
-        S.ms_d2h = std::max(S.ms_d2h, (double)ms);
-        const double t0 = now_ms();
-        for (int k = 0; k < c.nchunks; ++k) scatter_chunk(eng, c, c.chunks[k], pairs);
-        scatter_bytes(eng, c, pairs);
-        S.ms_scatter += now_ms() - t0;
+        CUDA_TRY(cudaEventSynchronize(s.ev_out));
+        unpack_chunk(eng, s, pairs);
     }
     return BSW_OK;
 }
 
 // ------------------------------------------------------------------------------------------
-// the hot path: host buffers in, results in place.  Chunk pipeline (see the file header).
+// pinned host memory for callers without a CUDA toolchain
 // ------------------------------------------------------------------------------------------
-int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
-               int64_t n, int32_t w)
+void* bsw_host_alloc(size_t bytes)
 {
-    if (!eng) return BSW_ERR_PARAM;
-    const double t_begin = now_ms();
-    if (int rc = begin_batch(eng, pairs, seq_ref, seq_qer, n, w)) return rc;
-    bsw_stats& S = eng->stats;
-    for (DevCtx& c : eng->devs) {
-        if (int rc = prepare_shard(eng, c, true)) return rc;
-        if (c.n == 0) continue;
-        CUDA_TRY(cudaMemsetAsync(c.d_cells, 0, sizeof(unsigned long long), c.st_copy));
-        CUDA_TRY(cudaEventRecord(c.ev_k0, c.st_copy));
-        for (int s = 0; s < NSTREAMS; ++s) CUDA_TRY(cudaStreamWaitEvent(c.st[s], c.ev_k0, 0));
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
     }
-    // longest chunk first on every device; the devices' pipelines are interleaved chunk by chunk
-    int max_chunks = 0;
-    for (DevCtx& c : eng->devs) max_chunks = std::max(max_chunks, c.nchunks);
-    for (int step = 0; step < max_chunks; ++step) {
-        for (DevCtx& c : eng->devs) {
-            const int k = c.nchunks - 1 - step;
-            if (k < 0) continue;
-            CUDA_TRY(cudaSetDevice(c.dev));
-            double t0 = now_ms();
-            pack_chunk(eng, c, c.chunks[k], pairs, seq_ref, seq_qer);
-            S.ms_pack += now_ms() - t0;
-            if (int rc = h2d_chunk(eng, c, c.chunks[k])) return rc;
-            if (int rc = launch_chunk(eng, c, c.chunks[k], true)) return rc;
-            if (int rc = d2h_chunk(eng, c, c.chunks[k])) return rc;
-            // scatter whatever already came back while the GPU works on this chunk
-            t0 = now_ms();
-            for (int j = c.nchunks - 1; j > k; --j) {
-                Chunk& done = c.chunks[j];
-                if (!done.scattered && cudaEventQuery(done.ev_done) == cudaSuccess) scatter_chunk(eng, c, done, pairs);
-            }
-            S.ms_scatter += now_ms() - t0;
-        }
+    return p;
+}
+
+void bsw_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int bsw_host_register(void* p, size_t bytes)
+{
+    if (!p || !bytes) return BSW_ERR_PARAM;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
+        cudaGetLastError();
+        return BSW_ERR_CUDA;
     }
-    for (DevCtx& c : eng->devs) {
-        if (c.n == 0) continue;
-        CUDA_TRY(cudaSetDevice(c.dev));
-        const double t0 = now_ms();
-        if (int rc = stage_bytes(eng, c, pairs, seq_ref, seq_qer)) return rc;
-        S.ms_pack += now_ms() - t0;
-        if (int rc = launch_bytes(eng, c, true)) return rc;
-        if (int rc = d2h_bytes(eng, c)) return rc;
-        for (int s = 0; s < NSTREAMS; ++s) {
-            CUDA_TRY(cudaEventRecord(c.ev_join[s], c.st[s]));
-            CUDA_TRY(cudaStreamWaitEvent(c.st_d2h, c.ev_join[s], 0));
-        }
-        CUDA_TRY(cudaEventRecord(c.ev_k1, c.st_d2h));
-        CUDA_TRY(cudaMemcpyAsync(c.h_cells, c.d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.st_d2h));
-        S.n_short += (int32_t)c.n_short;
-        S.n_long += (int32_t)c.n_long;
-    }
-    for (DevCtx& c : eng->devs) {
-        if (c.n == 0) continue;
-        CUDA_TRY(cudaSetDevice(c.dev));
-        for (int k = c.nchunks - 1; k >= 0; --k) {
-            Chunk& ch = c.chunks[k];
-            if (ch.scattered) continue;
-            CUDA_TRY(cudaEventSynchronize(ch.ev_done));
-            const double t0 = now_ms();
-            scatter_chunk(eng, c, ch, pairs);
-            S.ms_scatter += now_ms() - t0;
-        }
-        CUDA_TRY(cudaStreamSynchronize(c.st_d2h));
-        const double t0 = now_ms();
-        scatter_bytes(eng, c, pairs);
-        S.ms_scatter += now_ms() - t0;
-        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_k0, c.ev_k1));
-        S.ms_kernel = std::max(S.ms_kernel, (double)ms);      // first H2D .. last kernel, copies overlapped
-        S.cells_effective += (int64_t)*c.h_cells;
-    }
-    S.ms_total = now_ms() - t_begin;
+    return BSW_OK;
+}
+
+int bsw_host_unregister(void* p)
+{
+    if (!p) return BSW_ERR_PARAM;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return BSW_ERR_CUDA; }
     return BSW_OK;
 }
 
@@ -844,10 +930,10 @@ double bsw_measure_int_peak(bsw_engine* eng)
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
-        cudaEventRecord(e0, c.st[0]);
-        bsw_int_peak_kernel<<<blocks, threads, 0, c.st[0]>>>(d_out, iters, 12345 + rep);
-        cudaEventRecord(e1, c.st[0]);
-        if (cudaStreamSynchronize(c.st[0]) != cudaSuccess) { best = 0.0; break; }
+        cudaEventRecord(e0, c.cs[0]);
+        bsw_int_peak_kernel<<<blocks, threads, 0, c.cs[0]>>>(d_out, iters, 12345 + rep);
+        cudaEventRecord(e1, c.cs[0]);
+        if (cudaStreamSynchronize(c.cs[0]) != cudaSuccess) { best = 0.0; break; }
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
         const double ops = (double)threads * blocks * (double)iters * 64.0;
         if (rep > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3));

@@ -121,7 +121,9 @@ __device__ __forceinline__ int4 bsw_pack_result(const PairState& st)
 
 // ---------------------------------------------------------------------------------------
 // Short-pair kernel: one pair per thread.
-//   meta[s] = {query word/byte offset, target word/byte offset, qlen | tlen << 16, h0}
+//   Position p of the processing order handles pair s = perm[first + p] of the chunk:
+//   meta[s] = {query word/byte offset, target word/byte offset, qlen | tlen << 16, h0 | flags},
+//   res[s] receives its packed result (input order).
 //   BYTESEQ = false: sequences are 2-bit packed, 16 bases per 32-bit word, word-aligned.
 //   BYTESEQ = true : one base code per byte (pairs that contain N, code 4).
 //   Shared memory of a block (qstride = cells per thread >= qlen + 8: the pipelined sweep reads one
@@ -141,30 +143,32 @@ __device__ __forceinline__ int4 bsw_pack_result(const PairState& st)
 // ---------------------------------------------------------------------------------------
 template <int BLOCK, bool BYTESEQ>
 __global__ void __launch_bounds__(BLOCK)
-bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qseq,
-                 const uint32_t* __restrict__ tseq, int4* __restrict__ res,
-                 int first, int count, int qstride, const __grid_constant__ KParams P,
-                 unsigned long long* __restrict__ cell_counter)
+bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ perm,
+                 const uint32_t* __restrict__ qseq, const uint32_t* __restrict__ tseq,
+                 int4* __restrict__ res, int first, int count, int qstride,
+                 const __grid_constant__ KParams P, unsigned long long* __restrict__ cell_counter)
 {
     extern __shared__ uint32_t eh_smem[];
     const int tid = threadIdx.x;
     const int local = blockIdx.x * BLOCK + tid;
     long long my_cells = 0;
     int4 md = make_int4(0, 0, 0, 0);
-    const int s = first + local;
+    int s = 0;                        // the pair's index in the chunk (input order)
     bool run = local < count;
     if (run) {
+        s = (int)perm[first + local];
         md = meta[s];
         if (!BYTESEQ && (md.w & BSW_META_NFLAG)) run = false;
     }
     if (run) {
-        const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w;
+        const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w & 0xffff;
         uint32_t* const eh = eh_smem + tid;
         uint8_t* const qpk = reinterpret_cast<uint8_t*>(eh_smem + qstride * BLOCK) + tid;
         const uint32_t eh_sa = (uint32_t)__cvta_generic_to_shared(eh);
         const uint32_t qpk_sa = (uint32_t)__cvta_generic_to_shared(qpk);
-        const uint8_t* qb = reinterpret_cast<const uint8_t*>(qseq) + (BYTESEQ ? (uint32_t)md.x : 0u);
-        const uint8_t* tb = reinterpret_cast<const uint8_t*>(tseq) + (BYTESEQ ? (uint32_t)md.y : 0u);
+        // byte variant: signed byte offsets (sequences are read in place, before or after offset 0)
+        const uint8_t* qb = reinterpret_cast<const uint8_t*>(qseq) + (BYTESEQ ? (ptrdiff_t)md.x : (ptrdiff_t)0);
+        const uint8_t* tb = reinterpret_cast<const uint8_t*>(tseq) + (BYTESEQ ? (ptrdiff_t)md.y : (ptrdiff_t)0);
         const uint32_t* qw = qseq + (BYTESEQ ? 0u : (uint32_t)md.x);
         const uint32_t* tw = tseq + (BYTESEQ ? 0u : (uint32_t)md.y);
 
@@ -327,16 +331,16 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ qse
 //   and each cell takes max(local, F_in - k*e_ins).  The diagonal H hand-off between lanes
 //   and chunks is one __shfl_up_sync.  Rows stay strictly sequential because the window,
 //   the m == 0 exit and z-drop need the complete previous row (SURVEY.md finding 0.6).
-//   Sequences are one base per byte (codes 0-4), 4-byte aligned; eh[] (h | e << 16 per cell)
+//   Sequences are one base per byte (codes 0-4), read in place at any alignment; eh[] (h | e << 16 per cell)
 //   lives in a per-warp global scratch row that stays L1/L2 resident.
 //   Pairs are pulled from an atomic queue, longest first.
 // ---------------------------------------------------------------------------------------
 constexpr int LONG_WARPS = 4;
 
 __global__ void __launch_bounds__(LONG_WARPS * 32)
-bsw_long_kernel(const int4* __restrict__ meta, const uint8_t* __restrict__ qbytes,
-                const uint8_t* __restrict__ tbytes, int4* __restrict__ res,
-                int count, const __grid_constant__ KParams P,
+bsw_long_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ perm,
+                const uint8_t* __restrict__ qbytes, const uint8_t* __restrict__ tbytes,
+                int4* __restrict__ res, int count, const __grid_constant__ KParams P,
                 uint32_t* __restrict__ scratch, int scratch_stride, unsigned int* __restrict__ queue,
                 unsigned long long* __restrict__ cell_counter)
 {
@@ -352,11 +356,11 @@ bsw_long_kernel(const int4* __restrict__ meta, const uint8_t* __restrict__ qbyte
         if (lane == 0) k = atomicAdd(queue, 1u);
         k = __shfl_sync(FULL, k, 0);
         if (k >= (unsigned)count) break;
-        const int s = count - 1 - (int)k;                  // ascending in len2 -> longest first
+        const int s = (int)perm[k];
         const int4 md = meta[s];
-        const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w;
-        const uint8_t* qb = qbytes + (uint32_t)md.x;
-        const uint8_t* tb = tbytes + (uint32_t)md.y;
+        const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w & 0xffff;
+        const uint8_t* qb = qbytes + (ptrdiff_t)md.x;     // signed: sequences are read in place
+        const uint8_t* tb = tbytes + (ptrdiff_t)md.y;
 
         // first row, closed form of bandedSWA.cpp:155-157: eh[j].h = max(h0 - oe_ins - (j-1)*e_ins, 0)
         for (int j = lane; j <= qlen + 4; j += 32) {
@@ -386,7 +390,19 @@ bsw_long_kernel(const int4* __restrict__ meta, const uint8_t* __restrict__ qbyte
                     uint32_t qw = 0;
                     if (j0 <= end) {
                         wd = *reinterpret_cast<const uint4*>(eh + j0);
-                        if (j0 < qlen) qw = __ldg(reinterpret_cast<const uint32_t*>(qb + j0));
+                        if (j0 < qlen) {
+                            // 4 query bases at any alignment (sequences are read in place)
+                            const uint8_t* pq = qb + j0;
+                            if (j0 + 8 <= qlen) {
+                                const uintptr_t a = reinterpret_cast<uintptr_t>(pq);
+                                const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+                                qw = __funnelshift_r(__ldg(aw), __ldg(aw + 1), (unsigned)(a & 3) * 8u);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    if (j0 + c < qlen) qw |= (uint32_t)__ldg(pq + c) << (8 * c);
+                            }
+                        }
                     }
                     const uint32_t wds[4] = {wd.x, wd.y, wd.z, wd.w};
                     int M[4], E[4], g[5];

@@ -76,15 +76,16 @@ typedef struct bsw_stats {
     int64_t pairs;               /* pairs processed by the last call                     */
     int64_t cells_nominal;       /* sum len1*len2 (reference GCUPS convention)           */
     int64_t cells_effective;     /* inner-loop iterations actually executed (SW_cells)   */
-    double  ms_sort;             /* host: length bucketing                               */
-    double  ms_pack;             /* host: 2-bit packing into pinned staging              */
-    double  ms_h2d;              /* device timeline: H2D copies                          */
-    double  ms_kernel;           /* device timeline: sum of DP kernel launches (events)  */
-    double  ms_d2h;              /* device timeline: D2H copies                          */
-    double  ms_scatter;          /* host: results written back into SeqPair[] in order   */
+    double  ms_sort;             /* unused (bucketing runs on the device)                */
+    double  ms_pack;             /* host: streaming pass into pinned staging (pageable buffers only) */
+    double  ms_h2d;              /* unused (copies overlap the kernels)                  */
+    double  ms_kernel;           /* bsw_run_staged: device timeline of the DP launches (events);
+                                    bsw_extend: sum of the chunks' device timelines      */
+    double  ms_d2h;              /* unused                                               */
+    double  ms_scatter;          /* host: results written into SeqPair[] (pageable buffers only) */
     double  ms_total;            /* host wall clock of the whole call                    */
     int64_t h2d_bytes, d2h_bytes;
-    int32_t kernel_launches;     /* DP kernel launches issued by the last call           */
+    int32_t kernel_launches;     /* kernels launched by the last call (prep + DP + write-back) */
     int32_t n_short, n_long;     /* pairs routed to the thread-per-pair / warp-per-pair kernel */
     int32_t reserved[5];
 } bsw_stats;
@@ -105,6 +106,18 @@ void        bsw_default_params(bsw_params* p);       /* bwa defaults: main_bande
  * input order preserved; pads are never written and pair.id is never read. */
 int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref,
                const uint8_t* seq_qer, int64_t n_pairs, int32_t w);
+
+/* Pinned host memory.  bsw_extend takes any host pointers; when all three buffers (pairs,
+ * seq_ref, seq_qer) are page-locked -- allocated here, or registered, or pinned by the caller's
+ * own CUDA / torch allocator -- the engine DMAs them as they are and DMAs the records back with
+ * the six result fields filled in ("direct" route: no host pass over the payload; the input
+ * fields of pairs[] are rewritten with the values they had).  Pageable buffers
+ * go through one streaming host pass into pinned staging instead.  A maintainer's binding swaps
+ * the _mm_malloc calls of main_banded.cpp:244-246 for bsw_host_alloc. */
+void* bsw_host_alloc(size_t bytes);                 /* NULL on failure */
+void  bsw_host_free(void* p);
+int   bsw_host_register(void* p, size_t bytes);     /* page-locks an existing allocation */
+int   bsw_host_unregister(void* p);
 
 /* Split form of the same call, so that a caller (and bench.py) can keep a batch
  * resident in HBM and time the DP kernels alone:

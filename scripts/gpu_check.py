@@ -39,12 +39,19 @@ for name in ["small", "short8", "long16", "large", "sweep"]:
         st = eng.stats()
         best = min(best, st["ms_kernel"])
     t0 = time.time(); eng.fetch(pairs); t_fetch = time.time() - t0
+    eng.extend(pairs, r, q, 100)
     t0 = time.time(); eng.extend(pairs, r, q, 100); t_e2e = time.time() - t0
     st2 = eng.stats()
+    pp, pr, pq = gb.pinned_copy(pairs), gb.pinned_copy(r), gb.pinned_copy(q)
+    eng.extend(pp, pr, pq, 100)
+    t0 = time.time(); eng.extend(pp, pr, pq, 100); t_pin = time.time() - t0
+    st3 = eng.stats()
+    same = all(np.array_equal(pp[f], pairs[f]) for f in gb.RESULT_FIELDS)
     cells = st["cells_effective"]
     rec = dict(n=nt, ms_kernel=best, gcups_eff=cells / best / 1e6, gcups_nom=st["cells_nominal"] / best / 1e6,
                mpairs_s=nt / best / 1e3, roofline_frac=(cells * 10 / (best * 1e-3)) / peak if peak else None,
                launches=st["kernel_launches"], stage_ms=t_stage * 1e3, fetch_ms=t_fetch * 1e3, e2e_ms=t_e2e * 1e3,
+               e2e_pinned_ms=t_pin * 1e3, pinned_equals_pageable=bool(same), pinned_launches=st3["kernel_launches"],
                e2e_stats={k: st2[k] for k in ("ms_sort", "ms_pack", "ms_h2d", "ms_kernel", "ms_d2h", "ms_scatter", "ms_total")})
     out["configs"][name] = rec
     print(name, json.dumps(rec), flush=True)

@@ -64,3 +64,56 @@ def test_multi_engine_same_device(lib):
     e2.extend(b, ref, qer, 100)
     assert np.array_equal(results_matrix(a), results_matrix(b))
     e1.close(); e2.close()
+
+
+def test_direct_route_equals_staged_route(lib, oracle):
+    """Pinned host buffers (bsw_host_alloc) take the engine's direct route -- records and sequences
+    DMA'd as they are, results written into the records from the device; pageable buffers take the
+    staged route.  Same results, and both equal the oracle."""
+    cfg = lib.gen_named_config("large")
+    pairs, ref, qer = lib.gen_pairs(cfg, 0, 300_000)             # > 1 chunk
+    ref[::997] = 4                                               # sprinkle N: byte-kernel path on both routes
+    want = pairs[:30_000].copy()
+    oracle.batch(make_params(), want, ref, qer, 100)
+    with lib.Engine() as eng:
+        a = pairs.copy()
+        eng.extend(a, ref, qer, 100)
+        st_a = eng.stats()
+        pp, pr, pq = lib.pinned_copy(pairs), lib.pinned_copy(ref), lib.pinned_copy(qer)
+        eng.extend(pp, pr, pq, 100)
+        st_p = eng.stats()
+        assert np.array_equal(results_matrix(pp), results_matrix(a))
+        assert np.array_equal(results_matrix(a[:30_000]), results_matrix(want))
+        assert st_a["ms_pack"] > 0 and st_p["ms_pack"] == 0        # no host pass on the direct route
+        assert st_a["cells_effective"] == st_p["cells_effective"]
+        assert (pp["h0"] == pairs["h0"]).all() and (pp["idr"] == pairs["idr"]).all()
+        # permuted records over the same pinned sequences: offsets no longer ascend
+        perm = np.random.default_rng(5).permutation(len(pairs))
+        pb = lib.pinned_copy(pairs[perm])
+        eng.extend(pb, pr, pq, 100)
+        assert np.array_equal(results_matrix(pb), results_matrix(a)[perm])
+
+
+def test_sparse_sequence_buffers_are_read_in_place(lib, oracle):
+    """The reference loader's layout (main_banded.cpp:55-58,244-246: one 2048-byte slot per
+    reference, 256 per query): on the direct route the engine must not DMA the whole slots."""
+    from genomicsbench_b200 import SEQPAIR_DTYPE
+    cfg = lib.gen_named_config("small")
+    pairs, ref, qer = lib.gen_pairs(cfg, 0, 5000)
+    n = len(pairs)
+    sref = lib.pinned_empty(n * 2048, np.uint8); sqer = lib.pinned_empty(n * 256, np.uint8)
+    sref[:] = 0; sqer[:] = 0
+    sp = lib.pinned_copy(pairs)
+    for k in range(n):
+        l1, l2 = int(pairs["len1"][k]), int(pairs["len2"][k])
+        sref[k * 2048: k * 2048 + l1] = ref[pairs["idr"][k]: pairs["idr"][k] + l1]
+        sqer[k * 256: k * 256 + l2] = qer[pairs["idq"][k]: pairs["idq"][k] + l2]
+    sp["idr"] = np.arange(n) * 2048
+    sp["idq"] = np.arange(n) * 256
+    want = pairs.copy()
+    oracle.batch(make_params(), want, ref, qer, 100)
+    with lib.Engine() as eng:
+        eng.extend(sp, sref, sqer, 100)
+        st = eng.stats()
+    assert np.array_equal(results_matrix(sp), results_matrix(want))
+    assert st["h2d_bytes"] < n * 2304 // 2                         # far less than the slots' span
