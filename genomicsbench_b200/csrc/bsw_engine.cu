@@ -34,7 +34,7 @@ using namespace bsw;
 namespace {
 
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
-constexpr int SHORT_MAX_QLEN = 832;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
+constexpr int SHORT_MAX_QLEN = 824;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
 constexpr int NSTREAMS = 4;               // DP compute streams per device
 constexpr int NSLOTS = 3;                 // chunks in flight per device (prepare / compute / drain)
 constexpr int64_t CHUNK_EXTEND = 1 << 18; // pairs per chunk of bsw_extend (overlap vs bucketing quality)
@@ -145,17 +145,20 @@ void release(Buf<T>& b)
     b.d = nullptr; b.h = nullptr; b.cap = b.hcap = 0;
 }
 
-// Shared-memory rows per thread come in steps (one launch per step present in a chunk): fine
-// steps where occupancy is most sensitive to them, coarser ones for long queries.
+// Shared-memory words per thread (S).  S >= qlen + 8 (one prefetched group, bsw_kernels.cuh), S / 4
+// odd (the 128-bit row accesses of a quarter warp then fall into 8 distinct bank groups).  Steps
+// of 8 words where occupancy is most sensitive to them, coarser for long queries (one launch per
+// step present in a chunk).
 inline int stride_for(int qmax)
 {
-    const int need = qmax + 8;                    // + one prefetched group (bsw_kernels.cuh)
+    const int need = qmax + 8;
     if (need > SHORT_MAX_QLEN + 8) return -1;
-    int s;
-    if (need <= 136) s = (need + 7) & ~7;
-    else if (need <= 520) s = (need + 15) & ~15;
-    else s = (need + 31) & ~31;
-    return std::min(s, SHORT_MAX_QLEN + 8);
+    int q;                                        // S / 4
+    if (need <= 136) q = (need + 3) / 4;
+    else if (need <= 520) q = ((need + 15) & ~15) / 4;
+    else q = ((need + 31) & ~31) / 4;
+    if (!(q & 1)) ++q;
+    return 4 * q;
 }
 
 // dynamic shared memory of one short-kernel block: eh words + the 2-bit query byte plane

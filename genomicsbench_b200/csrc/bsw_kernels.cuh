@@ -59,15 +59,18 @@ __device__ __forceinline__ int bsw_mad(int a, int b, int c)
     return r;
 }
 
-// Shared-memory accessors of the short kernel's row sweep.  The two halves of a cell are read as
-// two LDS.U16 (LSU pipe) -- left to the compiler they are fused into LDS.32 + LOP3 + PRMT, two
-// instructions on the ALU pipe that bounds the kernel.  "memory" keeps them ordered against the
-// plain C++ accesses to the same array; among themselves they stay in program order (volatile).
-__device__ __forceinline__ int bsw_lds_u16(uint32_t saddr)
+// Shared-memory accessors of the short kernel's row sweep: one 128-bit load / store moves a whole
+// 4-column group.  "memory" keeps them ordered against the plain C++ accesses to the same array;
+// among themselves they stay in program order (volatile).
+__device__ __forceinline__ uint4 bsw_lds_u128(uint32_t saddr)
 {
-    int v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
     return v;
+}
+__device__ __forceinline__ void bsw_sts_u128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ uint32_t bsw_lds_u8(uint32_t saddr)
 {
@@ -75,9 +78,12 @@ __device__ __forceinline__ uint32_t bsw_lds_u8(uint32_t saddr)
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
     return v;
 }
-__device__ __forceinline__ void bsw_sts_u32(uint32_t saddr, uint32_t v)
+// x >> 16 on the FMA pipe (IMAD.HI.U32 with a register multiplier of 65536; two issue slots there)
+__device__ __forceinline__ uint32_t bsw_hi16_fma(uint32_t x, uint32_t k65536)
 {
-    asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(k65536));
+    return r;
 }
 
 // Running per-pair state shared by both kernels' row epilogues.
@@ -126,20 +132,22 @@ __device__ __forceinline__ int4 bsw_pack_result(const PairState& st)
 //   res[s] receives its packed result (input order).
 //   BYTESEQ = false: sequences are 2-bit packed, 16 bases per 32-bit word, word-aligned.
 //   BYTESEQ = true : one base code per byte (pairs that contain N, code 4).
-//   Shared memory of a block (qstride = cells per thread >= qlen + 8: the pipelined sweep reads one
-//   group past the last full one):
-//     eh [j * BLOCK + tid]            cell j of thread tid: e << 16 | h  (bank == lane for any j)
+//   Shared memory of a block (S = qstride = words per thread, S / 4 odd, S >= qlen + 8: the
+//   pipelined sweep reads one group past the last full one):
+//     eh [tid * S + j]                cell j of thread tid: e << 16 | h.  A 128-bit access moves
+//                                     columns j..j+3; with S / 4 odd the 8 lanes of a quarter warp
+//                                     hit 8 distinct 16-byte bank groups (conflict-free)
 //     qpk[(j >> 2) * BLOCK + tid]     byte holding query bases j..j+3, 2 bits each (2-bit variant)
-//   Row sweep: columns are processed in groups of 4 aligned to j % 4 == 0, so one byte load
-//   brings the four query bases of a group and the match tests are single LOP3s with immediate
-//   masks.  Columns left of `beg` are dead for the rest of the pair (beg never decreases), so
-//   the <= 3 columns between the group boundary and beg are zeroed and swept like live ones:
-//   they produce h = e = f = 0, exactly the state the reference enters column beg with when
-//   beg > 0.  The <= 3 columns right of the last full group run through the scalar tail loop.
-//   Instruction budget per cell (the ALU pipe issues 2 warp-instructions/clk/SM and bounds this
-//   kernel, scripts/int_pipe_probe.cu): ALU = match test, select, M, h, E', F' (+ half of the two
-//   dual-issue ops); FMA pipe = cap, the gap decrement, the cell re-pack and the argmax key;
-//   LSU = 2 x LDS.U16 + STS.32 (+ 1/4 LDS.U8).
+//   Row sweep: columns are processed in groups of 4 aligned to j % 4 == 0: one LDS.128, one LDS.U8
+//   (the group's four query bases; the match tests are single LOP3s with immediate masks) and one
+//   STS.128 per group.  Columns left of `beg` are dead for the rest of the pair (beg never
+//   decreases), so the <= 3 columns between the group boundary and beg are zeroed and swept like
+//   live ones: they produce h = e = f = 0, exactly the state the reference enters column beg
+//   with when beg > 0.  The <= 3 columns right of the last full group run the scalar tail loop.
+//   Instruction budget per cell (scripts/int_pipe_probe.cu: ALU pipe 2 warp-instructions/clk/SM,
+//   FMA pipe 2, IMAD.HI 1): ALU = match test, select, M, h, E', F' (+ the e unpack of two cells in
+//   four, + half of the dual-issue ops); FMA = cap, h unpack, e unpack of the other two cells, the
+//   gap decrement, the cell re-pack and the argmax key.  ~7 ALU + ~6.5 FMA + 0.75 LSU slots.
 // ---------------------------------------------------------------------------------------
 template <int BLOCK, bool BYTESEQ>
 __global__ void __launch_bounds__(BLOCK)
@@ -148,7 +156,7 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
                  int4* __restrict__ res, int first, int count, int qstride,
                  const __grid_constant__ KParams P, unsigned long long* __restrict__ cell_counter)
 {
-    extern __shared__ uint32_t eh_smem[];
+    extern __shared__ __align__(16) uint32_t eh_smem[];
     const int tid = threadIdx.x;
     const int local = blockIdx.x * BLOCK + tid;
     long long my_cells = 0;
@@ -162,7 +170,7 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
     }
     if (run) {
         const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w & 0xffff;
-        uint32_t* const eh = eh_smem + tid;
+        uint32_t* const eh = eh_smem + tid * qstride;
         uint8_t* const qpk = reinterpret_cast<uint8_t*>(eh_smem + qstride * BLOCK) + tid;
         const uint32_t eh_sa = (uint32_t)__cvta_generic_to_shared(eh);
         const uint32_t qpk_sa = (uint32_t)__cvta_generic_to_shared(qpk);
@@ -172,13 +180,19 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
         const uint32_t* qw = qseq + (BYTESEQ ? 0u : (uint32_t)md.x);
         const uint32_t* tw = tseq + (BYTESEQ ? 0u : (uint32_t)md.y);
 
-        // ---- first row (bandedSWA.cpp:155-157); the query goes to its byte plane
+        // ---- first row (bandedSWA.cpp:155-157), four columns per store; the query goes to its byte plane
         {
             int hv = h0;
-            for (int j = 0; j <= qlen; ++j) {
-                if (j == 1) hv = h0 > P.oe_ins ? h0 - P.oe_ins : 0;
-                else if (j >= 2) hv = hv > P.e_ins ? hv - P.e_ins : 0;
-                eh[j * BLOCK] = (uint32_t)hv;
+            for (int j0 = 0; j0 <= qlen; j0 += 4) {
+                uint32_t v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = j0 + c;
+                    if (j == 1) hv = h0 > P.oe_ins ? h0 - P.oe_ins : 0;
+                    else if (j >= 2) hv = hv > P.e_ins ? hv - P.e_ins : 0;
+                    v[c] = j <= qlen ? (uint32_t)hv : 0u;
+                }
+                bsw_sts_u128(eh_sa + 4u * (uint32_t)j0, v[0], v[1], v[2], v[3]);
             }
             if (!BYTESEQ) {
                 const int nw = (qlen + 15) >> 4;
@@ -196,10 +210,16 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
         st.max = h0; st.max_i = -1; st.max_j = -1; st.max_ie = -1; st.gscore = -1; st.max_off = 0;
         int beg = 0, end = qlen;
         uint32_t tword = 0;
-        const int neg_oe_del = -P.oe_del, neg_oe_ins = -P.oe_ins, neg_e_del = -P.e_del, neg_e_ins = -P.e_ins;
-        const int c_match = P.match, c_mis = P.mismatch_neg;
+        // Loop constants.  `zero` is 0 but opaque to the compiler (bit 31 of a loaded word that never
+        // has it set): adding it pins the constants in registers -- otherwise every group iteration
+        // re-reads them from the constant bank and the first dependent instruction stalls on it.
+        const int zero = (int)((uint32_t)md.z >> 31);
+        const int neg_oe_del = zero - P.oe_del, neg_oe_ins = zero - P.oe_ins;
+        const int neg_e_del = zero - P.e_del, neg_e_ins = zero - P.e_ins;
+        const int c_match = zero + P.match, c_mis = zero + P.mismatch_neg;
         // argmax-key addends kept in registers so that the key is one IMAD (h * 65536 + k)
-        const int k1 = P.kone, k2 = 2 * P.kone, k3 = 3 * P.kone;
+        const int k1 = zero + P.kone, k2 = zero + 2 * P.kone, k3 = zero + 3 * P.kone;
+        const uint32_t k65536 = (uint32_t)(zero + 65536 * P.kone);
 
         for (int i = 0; i < tlen; ++i) {
             int ti;
@@ -214,16 +234,19 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
             if (beg == 0) h1 = max(h0 - (P.o_del + P.e_del * (i + 1)), 0);
             int f = 0;
             int mkey = 0;                                    // (row max << 16) | argmax column
-            // DP recurrence of one cell given its diagonal H (Hd), E (e) and match score (sc);
-            // writes the cell back as {h = H(i, j-1), e = E(i+1, j)}  (bandedSWA.cpp:196-210)
-#define BSW_CELL_CORE(STORE, HD, EE, SC, KEYADD)                                                     \
+            // DP recurrence of one cell from its packed word WD = E(i, j) << 16 | H(i-1, j-1) and the
+            // match score SC; NW receives the new word H(i, j-1) | E(i+1, j) << 16
+            // (bandedSWA.cpp:196-210).  EXPR_E unpacks e on the ALU pipe (shift) or the FMA pipe.
+#define BSW_CELL_CORE(NW, WD, EXPR_E, SC, KEYADD)                                                    \
             {                                                                                        \
+                const int e = (int)(EXPR_E);                                                         \
+                const int Hd = bsw_mad(e, -65536, (int)(WD));            /* low half, on the FMA pipe */ \
                 /* M = Hd ? Hd + s : 0, clamped at 0 (a negative M is equivalent to 0 in every use) */ \
-                const int M = __viaddmin_s32_relu((HD), (SC), bsw_mad((HD), 65536, 0));              \
-                const int h = __vimax3_s32(M, (EE), f);                                              \
-                const int en = __viaddmax_s32_relu(M, neg_oe_del, bsw_mad((EE), 1, neg_e_del));      \
+                const int M = __viaddmin_s32_relu(Hd, (SC), bsw_mad((int)(WD), 65536, 0));           \
+                const int h = __vimax3_s32(M, e, f);                                                 \
+                const int en = __viaddmax_s32_relu(M, neg_oe_del, bsw_mad(e, 1, neg_e_del));         \
                 f = __viaddmax_s32_relu(M, neg_oe_ins, f + neg_e_ins);                               \
-                STORE((uint32_t)bsw_mad(en, 65536, h1));                                             \
+                NW = (uint32_t)bsw_mad(en, 65536, h1);                                               \
                 mkey = max(mkey, bsw_mad(h, 65536, (KEYADD)));                                       \
                 h1 = h;                                                                              \
             }
@@ -233,55 +256,40 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
             } else {
                 // zero the dead columns between the group boundary and beg, then sweep full groups
                 j = beg & ~3;
-                if (j + 0 < beg) eh[(j + 0) * BLOCK] = 0u;
-                if (j + 1 < beg) eh[(j + 1) * BLOCK] = 0u;
-                if (j + 2 < beg) eh[(j + 2) * BLOCK] = 0u;
+                if (j + 0 < beg) eh[j + 0] = 0u;
+                if (j + 1 < beg) eh[j + 1] = 0u;
+                if (j + 2 < beg) eh[j + 2] = 0u;
                 const uint32_t trep = (uint32_t)ti * 0x55u;
-                uint32_t sa = eh_sa + (uint32_t)j * (4 * BLOCK);
+                uint32_t sa = eh_sa + 4u * (uint32_t)j;
                 uint32_t qa = qpk_sa + (uint32_t)(j >> 2) * BLOCK;
                 // software pipeline: group g+1 is loaded while group g is computed (the row buffer
-                // is padded, so the load past the last full group stays inside this thread's column)
-                int h_0 = bsw_lds_u16(sa), e_0 = bsw_lds_u16(sa + 2);
-                int h_1 = bsw_lds_u16(sa + 4 * BLOCK), e_1 = bsw_lds_u16(sa + 4 * BLOCK + 2);
-                int h_2 = bsw_lds_u16(sa + 8 * BLOCK), e_2 = bsw_lds_u16(sa + 8 * BLOCK + 2);
-                int h_3 = bsw_lds_u16(sa + 12 * BLOCK), e_3 = bsw_lds_u16(sa + 12 * BLOCK + 2);
+                // is padded, so the load past the last full group stays inside this thread's row)
+                uint4 cur = bsw_lds_u128(sa);
                 uint32_t qv = bsw_lds_u8(qa);
                 for (; j + 4 <= end; j += 4) {
                     const uint32_t x = qv ^ trep;
-                    const uint32_t sn = sa + 16 * BLOCK;
-                    const int nh_0 = bsw_lds_u16(sn), ne_0 = bsw_lds_u16(sn + 2);
-                    const int nh_1 = bsw_lds_u16(sn + 4 * BLOCK), ne_1 = bsw_lds_u16(sn + 4 * BLOCK + 2);
-                    const int nh_2 = bsw_lds_u16(sn + 8 * BLOCK), ne_2 = bsw_lds_u16(sn + 8 * BLOCK + 2);
-                    const int nh_3 = bsw_lds_u16(sn + 12 * BLOCK), ne_3 = bsw_lds_u16(sn + 12 * BLOCK + 2);
+                    const uint4 nxt = bsw_lds_u128(sa + 16);
                     qa += BLOCK;
                     qv = bsw_lds_u8(qa);
+                    uint32_t n0, n1, n2, n3;
                     int mk4;
                     {
                         int mkey = 0;
-#define BSW_ST0(V) bsw_sts_u32(sa, (V))
-#define BSW_ST1(V) bsw_sts_u32(sa + 4 * BLOCK, (V))
-#define BSW_ST2(V) bsw_sts_u32(sa + 8 * BLOCK, (V))
-#define BSW_ST3(V) bsw_sts_u32(sa + 12 * BLOCK, (V))
-                        BSW_CELL_CORE(BSW_ST0, h_0, e_0, (x & 0x03u) ? c_mis : c_match, 0)
-                        BSW_CELL_CORE(BSW_ST1, h_1, e_1, (x & 0x0cu) ? c_mis : c_match, k1)
-                        BSW_CELL_CORE(BSW_ST2, h_2, e_2, (x & 0x30u) ? c_mis : c_match, k2)
-                        BSW_CELL_CORE(BSW_ST3, h_3, e_3, (x & 0xc0u) ? c_mis : c_match, k3)
-#undef BSW_ST0
-#undef BSW_ST1
-#undef BSW_ST2
-#undef BSW_ST3
+                        BSW_CELL_CORE(n0, cur.x, cur.x >> 16,                  (x & 0x03u) ? c_mis : c_match, 0)
+                        BSW_CELL_CORE(n1, cur.y, bsw_hi16_fma(cur.y, k65536),  (x & 0x0cu) ? c_mis : c_match, k1)
+                        BSW_CELL_CORE(n2, cur.z, cur.z >> 16,                  (x & 0x30u) ? c_mis : c_match, k2)
+                        BSW_CELL_CORE(n3, cur.w, bsw_hi16_fma(cur.w, k65536),  (x & 0xc0u) ? c_mis : c_match, k3)
                         mk4 = mkey;
                     }
+                    bsw_sts_u128(sa, n0, n1, n2, n3);
                     mkey = max(mkey, mk4 + j);                // same order: j + k < 65536 never carries
-                    h_0 = nh_0; e_0 = ne_0; h_1 = nh_1; e_1 = ne_1;
-                    h_2 = nh_2; e_2 = ne_2; h_3 = nh_3; e_3 = ne_3;
-                    sa = sn;
+                    cur = nxt;
+                    sa += 16;
                 }
             }
             // scalar tail (2-bit variant: <= 3 columns) / whole window (byte variant)
             for (; j < end; ++j) {
-                uint32_t* p = eh + j * BLOCK;
-                const uint32_t wd = *p;
+                const uint32_t wd = eh[j];
                 int sc;
                 if (BYTESEQ) {
                     const int qj = __ldg(qb + j);
@@ -290,14 +298,14 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
                     const int qj = ((int)qpk[(j >> 2) * BLOCK] >> ((j & 3) * 2)) & 3;
                     sc = qj == ti ? c_match : c_mis;
                 }
-#define BSW_STP(V) *p = (V)
-                BSW_CELL_CORE(BSW_STP, (int)(wd & 0xffffu), (int)(wd >> 16), sc, j)
-#undef BSW_STP
+                uint32_t nw;
+                BSW_CELL_CORE(nw, wd, wd >> 16, sc, j)
+                eh[j] = nw;
             }
 #undef BSW_CELL_CORE
             if (end > beg) my_cells += end - beg;
             // eh[end] = {h1, 0}  (bandedSWA.cpp:213)
-            eh[end * BLOCK] = (uint32_t)h1;
+            eh[end] = (uint32_t)h1;
             const int jfin = end > beg ? end : beg;
             if (jfin == qlen) {                               // bandedSWA.cpp:214-217
                 if (!(st.gscore > h1)) st.max_ie = i;
@@ -308,10 +316,10 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
             // next row's window (bandedSWA.cpp:230-233)
             {
                 int jj = beg;
-                while (jj < end && eh[jj * BLOCK] == 0u) ++jj;
+                while (jj < end && eh[jj] == 0u) ++jj;
                 beg = jj;
                 jj = end;
-                while (jj >= beg && eh[jj * BLOCK] == 0u) --jj;
+                while (jj >= beg && eh[jj] == 0u) --jj;
                 end = min(jj + 2, qlen);
             }
         }

@@ -100,3 +100,17 @@ def strong_shard(n_total: int, rank: int, world: int) -> tuple:
     base, rem = divmod(n_total, world)
     first = rank * base + min(rank, rem)
     return first, base + (1 if rank < rem else 0)
+
+
+def bind_near_gpu(physical_index: int) -> bool:
+    """Pins the calling process to the CPUs NVML reports as local to the GPU (same NUMA node /
+    PCIe root), so that page-locked buffers allocated afterwards are DMA'd without crossing the
+    socket interconnect.  Best effort: returns False when NVML or the call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(physical_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False

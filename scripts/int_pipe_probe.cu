@@ -49,6 +49,21 @@ __global__ void probe(int* out, int iters, int seed)
                     if (k & 1) asm volatile("add.s32 %0, %0, %1;" : "+r"(a[k]) : "r"(b));
                     else a[k] = __viaddmax_s32(a[k], b, c);
                 }
+                if (OP == 16) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(b));                  // IMAD.HI.U32
+                if (OP == 17) {                                                       // IMAD.HI + VIADDMNMX alternating
+                    if (k & 1) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(b));
+                    else a[k] = __viaddmax_s32(a[k], b, c);
+                }
+                if (OP == 18) asm volatile("mad.lo.s32 %0, %0, -65536, %1;" : "+r"(a[k]) : "r"(c));           // IMAD with immediate
+                if (OP == 19) asm volatile("shr.u32 %0, %0, 16;" : "+r"(a[k]));                              // shift right by immediate
+                if (OP == 20) {                                                       // 2 IMAD : 1 IMAD.HI : 3 ALU (the planned cell mix)
+                    if (k == 0 || k == 4) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(b));
+                    else if (k == 1 || k == 5) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+                    else if (k == 2) a[k] = __viaddmax_s32(a[k], b, c);
+                    else if (k == 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b), "r"(c));
+                    else if (k == 6) a[k] = __vimax3_s32(a[k], b, c);
+                    else asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+                }
                 if (OP == 15) {                                                       // 1 IMAD : 3 mixed ALU
                     if ((k & 3) == 0) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
                     else if ((k & 3) == 1) a[k] = __viaddmax_s32(a[k], b, c);
@@ -83,9 +98,30 @@ __global__ void probe_lds(int* out, int iters, int seed)
     out[blockIdx.x * blockDim.x + threadIdx.x] = x;
 }
 
+// 128-bit shared loads/stores, one 4-word group per lane, lane stride 4*odd words (conflict-free)
+__global__ void probe_lds128(int* out, int iters, int seed, int stride_words)
+{
+    extern __shared__ int sm[];
+    int4* p = reinterpret_cast<int4*>(sm + threadIdx.x * stride_words);
+    for (int k = 0; k < 8; ++k) p[k] = make_int4(seed + k, seed, k, 1);
+    int x = 0;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int4 v = p[k];
+            x += v.x + v.w;
+            v.y = x;
+            p[k] = v;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
 static const char* names[] = {"VIADDMNMX", "VIMNMX3", "LOP3", "IMAD", "IADD(VIADD)", "SHF", "VIMNMX", "PRMT",
                               "VIADDMNMX+IMAD", "LOP3+IMAD", "VIADDMNMX+LOP3", "VIADDMNMX.S16x2.RELU",
-                              "ISETP+SEL (2 instr)", "SHL imm", "VIADDMNMX+IADD", "IMAD+VIADDMNMX+LOP3+VIMNMX3"};
+                              "ISETP+SEL (2 instr)", "SHL imm", "VIADDMNMX+IADD", "IMAD+VIADDMNMX+LOP3+VIMNMX3",
+                              "IMAD.HI.U32", "IMAD.HI+VIADDMNMX", "IMAD imm", "SHR imm", "cell mix 2HI:3IMAD:3ALU"};
 
 template <int OP>
 void run(int* d_out, int sms, double clk_ghz)
@@ -124,6 +160,7 @@ int main()
     run<4>(d_out, sms, ghz); run<5>(d_out, sms, ghz); run<6>(d_out, sms, ghz); run<7>(d_out, sms, ghz);
     run<8>(d_out, sms, ghz); run<9>(d_out, sms, ghz); run<10>(d_out, sms, ghz); run<11>(d_out, sms, ghz);
     run<12>(d_out, sms, ghz); run<13>(d_out, sms, ghz); run<14>(d_out, sms, ghz); run<15>(d_out, sms, ghz);
+    run<16>(d_out, sms, ghz); run<17>(d_out, sms, ghz); run<18>(d_out, sms, ghz); run<19>(d_out, sms, ghz); run<20>(d_out, sms, ghz);
     {
         const int threads = 64, blocks = sms * 16, iters = 2048;
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -137,6 +174,20 @@ int main()
         }
         const double pairs = (double)threads / 32 * blocks * (double)iters * 32;
         printf("LDS+IADD+STS dependent triple      %8.3f ms  %6.3f triples/clk/SM\n", best, pairs / (best * 1e-3) / (ghz * 1e9) / sms);
+    }
+    for (int stride : {36, 44, 32, 33}) {
+        const int threads = 64, blocks = sms * 8, iters = 2048;
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(e0);
+            probe_lds128<<<blocks, threads, (threads * stride + 64) * 4>>>(d_out, iters, rep, stride);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep) best = ms < best ? ms : best;
+        }
+        const double pairs = (double)threads / 32 * blocks * (double)iters * 8;
+        printf("LDS.128+STS.128 pair, lane stride %2d words  %8.3f ms  %6.3f pairs/clk/SM\n", stride, best, pairs / (best * 1e-3) / (ghz * 1e9) / sms);
     }
     printf("cuda error: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
