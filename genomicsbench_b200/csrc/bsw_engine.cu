@@ -34,8 +34,8 @@ using namespace bsw;
 namespace {
 
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
-constexpr int SHORT_MAX_QLEN = 824;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
-constexpr int NSTREAMS = 4;               // DP compute streams per device
+constexpr int SHORT_MAX_QLEN = 820;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
+constexpr int NSTREAMS = 16;              // DP compute streams per device (one shared-memory class each, run concurrently)
 constexpr int NSLOTS = 3;                 // chunks in flight per device (prepare / compute / drain)
 constexpr int64_t CHUNK_EXTEND = 1 << 18; // pairs per chunk of bsw_extend (overlap vs bucketing quality)
 constexpr int64_t CHUNK_STAGE = 1 << 20;  // pairs per chunk of bsw_stage (resident: best bucketing)
@@ -145,14 +145,14 @@ void release(Buf<T>& b)
     b.d = nullptr; b.h = nullptr; b.cap = b.hcap = 0;
 }
 
-// Shared-memory words per thread (S).  S >= qlen + 8 (one prefetched group, bsw_kernels.cuh), S / 4
+// Shared-memory words per thread (S).  S >= qlen + 12 (prefetched groups, bsw_kernels.cuh), S / 4
 // odd (the 128-bit row accesses of a quarter warp then fall into 8 distinct bank groups).  Steps
 // of 8 words where occupancy is most sensitive to them, coarser for long queries (one launch per
 // step present in a chunk).
 inline int stride_for(int qmax)
 {
-    const int need = qmax + 8;
-    if (need > SHORT_MAX_QLEN + 8) return -1;
+    const int need = qmax + 12;
+    if (need > SHORT_MAX_QLEN + 12) return -1;
     int q;                                        // S / 4
     if (need <= 136) q = (need + 3) / 4;
     else if (need <= 520) q = ((need + 15) & ~15) / 4;

@@ -132,8 +132,8 @@ __device__ __forceinline__ int4 bsw_pack_result(const PairState& st)
 //   res[s] receives its packed result (input order).
 //   BYTESEQ = false: sequences are 2-bit packed, 16 bases per 32-bit word, word-aligned.
 //   BYTESEQ = true : one base code per byte (pairs that contain N, code 4).
-//   Shared memory of a block (S = qstride = words per thread, S / 4 odd, S >= qlen + 8: the
-//   pipelined sweep reads one group past the last full one):
+//   Shared memory of a block (S = qstride = words per thread, S / 4 odd, S >= qlen + 12: the
+//   pipelined sweep reads up to two groups past the last full one):
 //     eh [tid * S + j]                cell j of thread tid: e << 16 | h.  A 128-bit access moves
 //                                     columns j..j+3; with S / 4 odd the 8 lanes of a quarter warp
 //                                     hit 8 distinct 16-byte bank groups (conflict-free)
@@ -266,26 +266,42 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
                 // is padded, so the load past the last full group stays inside this thread's row)
                 uint4 cur = bsw_lds_u128(sa);
                 uint32_t qv = bsw_lds_u8(qa);
-                for (; j + 4 <= end; j += 4) {
-                    const uint32_t x = qv ^ trep;
-                    const uint4 nxt = bsw_lds_u128(sa + 16);
-                    qa += BLOCK;
-                    qv = bsw_lds_u8(qa);
-                    uint32_t n0, n1, n2, n3;
-                    int mk4;
-                    {
-                        int mkey = 0;
-                        BSW_CELL_CORE(n0, cur.x, cur.x >> 16,                  (x & 0x03u) ? c_mis : c_match, 0)
-                        BSW_CELL_CORE(n1, cur.y, bsw_hi16_fma(cur.y, k65536),  (x & 0x0cu) ? c_mis : c_match, k1)
-                        BSW_CELL_CORE(n2, cur.z, cur.z >> 16,                  (x & 0x30u) ? c_mis : c_match, k2)
-                        BSW_CELL_CORE(n3, cur.w, bsw_hi16_fma(cur.w, k65536),  (x & 0xc0u) ? c_mis : c_match, k3)
-                        mk4 = mkey;
-                    }
-                    bsw_sts_u128(sa, n0, n1, n2, n3);
-                    mkey = max(mkey, mk4 + j);                // same order: j + k < 65536 never carries
-                    cur = nxt;
-                    sa += 16;
+                // one 4-column group: X = query byte ^ target pattern, CUR = the group's four words
+#define BSW_GROUP(X, CUR, JBASE)                                                                     \
+                {                                                                                    \
+                    uint32_t n0, n1, n2, n3;                                                         \
+                    int mk4;                                                                         \
+                    {                                                                                \
+                        int mkey = 0;                                                                \
+                        BSW_CELL_CORE(n0, CUR.x, CUR.x >> 16,                 ((X) & 0x03u) ? c_mis : c_match, 0)  \
+                        BSW_CELL_CORE(n1, CUR.y, bsw_hi16_fma(CUR.y, k65536), ((X) & 0x0cu) ? c_mis : c_match, k1) \
+                        BSW_CELL_CORE(n2, CUR.z, CUR.z >> 16,                 ((X) & 0x30u) ? c_mis : c_match, k2) \
+                        BSW_CELL_CORE(n3, CUR.w, bsw_hi16_fma(CUR.w, k65536), ((X) & 0xc0u) ? c_mis : c_match, k3) \
+                        mk4 = mkey;                                                                  \
+                    }                                                                                \
+                    bsw_sts_u128(sa, n0, n1, n2, n3);                                                \
+                    mkey = max(mkey, mk4 + (JBASE));          /* same order: j + k < 65536 never carries */ \
+                    sa += 16;                                                                        \
                 }
+                // two groups per iteration while they last (more independent work per warp: these
+                // kernels run at 1-3 warps per scheduler because of the shared-memory footprint)
+                for (; j + 8 <= end; j += 8) {
+                    const uint32_t x0 = qv ^ trep;
+                    const uint4 cur2 = bsw_lds_u128(sa + 16);
+                    const uint32_t x1 = bsw_lds_u8(qa + BLOCK) ^ trep;
+                    const uint4 nxt = bsw_lds_u128(sa + 32);
+                    qa += 2 * BLOCK;
+                    qv = bsw_lds_u8(qa);
+                    BSW_GROUP(x0, cur, j)
+                    BSW_GROUP(x1, cur2, j + 4)
+                    cur = nxt;
+                }
+                if (j + 4 <= end) {
+                    const uint32_t x = qv ^ trep;
+                    BSW_GROUP(x, cur, j)
+                    j += 4;
+                }
+#undef BSW_GROUP
             }
             // scalar tail (2-bit variant: <= 3 columns) / whole window (byte variant)
             for (; j < end; ++j) {

@@ -65,7 +65,7 @@ typedef struct bsw_params {
     int32_t devices[16];                  /* CUDA ordinals when n_devices > 0        */
     int32_t host_threads;                 /* packer threads per engine, 0 => auto    */
     int32_t long_min_qlen;                /* queries of at least this length use the warp-per-pair
-                                             kernel; 0 => default (825, the short kernel's shared-
+                                             kernel; 0 => default (821, the short kernel's shared-
                                              memory limit + 1); 1 routes every pair to it          */
     int32_t reserved[7];
 } bsw_params;
