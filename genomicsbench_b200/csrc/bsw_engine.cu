@@ -36,8 +36,9 @@ namespace {
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
 constexpr int SHORT_MAX_QLEN = 820;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
 constexpr int NSTREAMS = 16;              // DP compute streams per device (one shared-memory class each, run concurrently)
-constexpr int NSLOTS = 3;                 // chunks in flight per device (prepare / compute / drain)
-constexpr int64_t CHUNK_EXTEND = 1 << 18; // pairs per chunk of bsw_extend (overlap vs bucketing quality)
+constexpr int NSLOTS = 4;                 // chunks in flight per device (records ahead / prepare / compute / drain)
+constexpr int64_t CHUNK_EXTEND = 1 << 18; // largest chunk of bsw_extend (overlap vs bucketing quality)
+constexpr int64_t CHUNK_MIN = 1 << 15;    // the last chunks of a batch shrink towards this (short pipeline drain)
 constexpr int64_t CHUNK_STAGE = 1 << 20;  // pairs per chunk of bsw_stage (resident: best bucketing)
 constexpr int BUCKET_BITS = 18;           // bins of the counting sort (1 MB table)
 constexpr long long OFF_BIAS = 1ll << 30; // bias of ChunkInfo::min_* / max_* (bsw_prep.cuh)
@@ -583,8 +584,18 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
     bsw_stats& S = eng->stats;
     const int ndev = (int)eng->devs.size();
     const bool direct = is_pinned(pairs) && is_pinned(seq_ref) && is_pinned(seq_qer);
-    const int64_t nchunks = (n + chunk_pairs - 1) / chunk_pairs;
-    const int64_t per = nchunks ? (n + nchunks - 1) / nchunks : 0;
+    // chunk boundaries: full-size chunks, then a geometric ramp-down so that the work left after
+    // the last H2D (its DP and its D2H) is small
+    std::vector<int64_t> cut{0};
+    for (int64_t rem = n; rem > 0;) {
+        int64_t sz;
+        if (keep || rem > 2 * chunk_pairs) sz = std::min(rem, chunk_pairs);
+        else if (rem > 2 * CHUNK_MIN) sz = std::min(rem, ((rem + 1) / 2 + 4095) & ~(int64_t)4095);
+        else sz = rem;
+        cut.push_back(cut.back() + sz);
+        rem -= sz;
+    }
+    const int64_t nchunks = (int64_t)cut.size() - 1;
     std::vector<ChunkRef> refs((size_t)nchunks);
     eng->staged_chunks.clear();
     for (DevCtx& c : eng->devs) {
@@ -596,6 +607,22 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
     auto slot_of = [&](int64_t k) -> Slot& { return eng->devs[(size_t)refs[(size_t)k].dev].slots[(size_t)refs[(size_t)k].slot]; };
     auto dev_of = [&](int64_t k) -> DevCtx& { return eng->devs[(size_t)refs[(size_t)k].dev]; };
 
+    // open: bind chunk k to its device and slot; on the direct route start its records DMA + scan
+    auto open = [&](int64_t k) -> int {
+        const int d = (int)(k % ndev);
+        const int sl = keep ? (int)(k / ndev) : (int)((k / ndev) % NSLOTS);
+        refs[(size_t)k] = ChunkRef{d, sl};
+        DevCtx& c = eng->devs[(size_t)d];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        Slot* sp = nullptr;
+        if (int rc = get_slot(eng, c, sl, &sp)) return rc;
+        Slot& s = *sp;
+        s.a = cut[(size_t)k]; s.n = (int)(cut[(size_t)k + 1] - cut[(size_t)k]);
+        s.direct = direct;
+        CUDA_TRY(cudaEventRecord(s.ev_k0, s.st));
+        if (direct) return direct_begin(eng, c, s, pairs);
+        return BSW_OK;
+    };
     // finish: the chunk's DP is enqueued; learn the byte-kernel lists, run them, send results out
     auto finish = [&](int64_t k) -> int {
         DevCtx& c = dev_of(k); Slot& s = slot_of(k);
@@ -617,33 +644,23 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
         return BSW_OK;
     };
 
+    // Per iteration k: records of chunk k + ndev go out (direct route) so the copy engine never
+    // waits for the host; chunk k gets its sequences, prep kernels and DP launches; chunk
+    // k - ndev drains (byte kernels, results out); chunk k - 2 ndev retires.
     const int lag = ndev;
+    for (int64_t k = 0; k < std::min<int64_t>(lag, nchunks); ++k) if (int rc = open(k)) return rc;
     for (int64_t k = 0; k < nchunks + 2 * lag; ++k) {
+        if (k + lag < nchunks) if (int rc = open(k + lag)) return rc;
         if (k < nchunks) {
-            const int d = (int)(k % ndev);
-            const int sl = keep ? (int)(k / ndev) : (int)((k / ndev) % NSLOTS);
-            refs[(size_t)k] = ChunkRef{d, sl};
-            DevCtx& c = eng->devs[(size_t)d];
+            DevCtx& c = dev_of(k); Slot& s = slot_of(k);
             CUDA_TRY(cudaSetDevice(c.dev));
-            Slot* sp = nullptr;
-            if (int rc = get_slot(eng, c, sl, &sp)) return rc;
-            Slot& s = *sp;
-            s.a = k * per; s.n = (int)std::min<int64_t>(per, n - s.a);
-            s.direct = direct;
-            CUDA_TRY(cudaEventRecord(s.ev_k0, s.st));
-            int rc;
-            if (direct) {
-                if ((rc = direct_begin(eng, c, s, pairs))) return rc;
-                rc = direct_sequences(eng, s, pairs, seq_ref, seq_qer);
-            } else {
-                rc = staged_prepare(eng, s, pairs, seq_ref, seq_qer);
-            }
+            int rc = direct ? direct_sequences(eng, s, pairs, seq_ref, seq_qer) : staged_prepare(eng, s, pairs, seq_ref, seq_qer);
             if (rc) { if (rc == BSW_ERR_DOMAIN) eng->err = kDomainMsg; return rc; }
             S.cells_nominal += (int64_t)s.info.nominal;
             if ((rc = device_prepare(eng, c, s))) return rc;
             if (!keep && (rc = launch_dp(eng, c, s))) return rc;
             CUDA_TRY(cudaEventRecord(s.ev_dp, s.st));
-            if (keep) eng->staged_chunks.emplace_back(d, sl);
+            if (keep) eng->staged_chunks.emplace_back(refs[(size_t)k].dev, refs[(size_t)k].slot);
         }
         if (keep) continue;
         if (k - lag >= 0 && k - lag < nchunks) if (int rc = finish(k - lag)) return rc;

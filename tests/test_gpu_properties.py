@@ -117,3 +117,30 @@ def test_sparse_sequence_buffers_are_read_in_place(lib, oracle):
         st = eng.stats()
     assert np.array_equal(results_matrix(sp), results_matrix(want))
     assert st["h2d_bytes"] < n * 2304 // 2                         # far less than the slots' span
+
+
+@pytest.mark.parametrize("devices", [[0, 0], [0, 1], [0, 1, 0]])
+def test_engine_deals_chunks_over_its_devices(lib, devices):
+    """One engine driving several devices (bsw_params.devices): chunks are dealt round-robin, every
+    chunk is bucketed and computed on its own device, results land in input order.  [0, 0] runs
+    the multi-device plumbing on a single GPU; [0, 1] needs two."""
+    import torch
+    if max(devices) >= torch.cuda.device_count():
+        pytest.skip("needs more GPUs")
+    cfg = lib.gen_named_config("large")
+    pairs, ref, qer = lib.gen_pairs(cfg, 0, 700_000)                 # several chunks per device
+    with lib.Engine() as one:
+        a = pairs.copy()
+        one.extend(a, ref, qer, 100)
+        cells = one.stats()["cells_effective"]
+    with lib.Engine(devices=devices) as eng:
+        b = pairs.copy()
+        eng.extend(b, ref, qer, 100)                                 # staged route
+        assert np.array_equal(results_matrix(b), results_matrix(a))
+        assert eng.stats()["cells_effective"] == cells
+        pp, pr, pq = lib.pinned_copy(pairs), lib.pinned_copy(ref), lib.pinned_copy(qer)
+        eng.extend(pp, pr, pq, 100)                                  # direct route
+        assert np.array_equal(results_matrix(pp), results_matrix(a))
+        c = pairs.copy()
+        eng.stage(c, ref, qer, 100); eng.run_staged(); eng.fetch(c)
+        assert np.array_equal(results_matrix(c), results_matrix(a))
