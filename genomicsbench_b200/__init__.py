@@ -86,6 +86,21 @@ class Engine:
         _check_arrays(pairs, seq_ref, seq_qer)
         self._rc(self._lib.bsw_extend(self._h, ptr(pairs), ptr(seq_ref), ptr(seq_qer), len(pairs), w))
 
+    def extend_retry(self, pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray, w: int,
+                     max_try: int = 2, prev_score: Optional[np.ndarray] = None) -> np.ndarray:
+        """Band-doubling retry of the aligner (tools/bwa/bwamem.c:630,723-753,770-800; MAX_BAND_TRY = 2).
+        Returns the band each pair's last try ran with."""
+        _check_arrays(pairs, seq_ref, seq_qer)
+        band = np.zeros(len(pairs), dtype=np.int32)
+        prev = None
+        if prev_score is not None:
+            prev = np.ascontiguousarray(prev_score, dtype=np.int32)
+            if len(prev) != len(pairs):
+                raise ValueError("prev_score must have one entry per pair")
+        self._rc(self._lib.bsw_extend_retry(self._h, ptr(pairs), ptr(seq_ref), ptr(seq_qer), len(pairs), w,
+                                            max_try, ptr(prev) if prev is not None else None, ptr(band)))
+        return band
+
     def stage(self, pairs, seq_ref, seq_qer, w: int) -> None:
         _check_arrays(pairs, seq_ref, seq_qer)
         self._rc(self._lib.bsw_stage(self._h, ptr(pairs), ptr(seq_ref), ptr(seq_qer), len(pairs), w))

@@ -76,6 +76,7 @@ ABI = [
     ("bsw_last_error", C.c_char_p, [_P]),
     ("bsw_default_params", None, [C.POINTER(BswParams)]),
     ("bsw_extend", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32]),
+    ("bsw_extend_retry", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     ("bsw_host_alloc", _P, [C.c_size_t]),
     ("bsw_host_free", None, [_P]),
     ("bsw_host_register", C.c_int, [_P, C.c_size_t]),

@@ -8,7 +8,7 @@
 //   host buffers pinned (bsw_host_alloc / bsw_host_register, "direct" route):
 //     DMA of the raw SeqPair records -> bsw_scan_pairs (validate, 16-byte descriptors, summary)
 //     -> DMA of the byte range the chunk's sequences span (or zero-copy reads when that range is
-//     sparse) -> bsw_pack_pairs (2 bits/base) -> bsw_bucket_* (counting sort by len2|h0|len1)
+//     sparse) -> bsw_bucket_* (counting sort by len2|h0|len1) -> bsw_pack_pairs (2 bits/base, processing order)
 //     -> bsw_short_kernel per shared-memory class -> bsw_writeback into the device copy of the
 //     records -> DMA of the records back.  The host touches no payload byte.
 //   pageable host buffers ("staged" route):
@@ -34,7 +34,7 @@ using namespace bsw;
 namespace {
 
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
-constexpr int SHORT_MAX_QLEN = 820;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
+constexpr int SHORT_MAX_QLEN = 824;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
 constexpr int NSTREAMS = 16;              // DP compute streams per device (one shared-memory class each, run concurrently)
 constexpr int NSLOTS = 4;                 // chunks in flight per device (records ahead / prepare / compute / drain)
 constexpr int64_t CHUNK_EXTEND = 1 << 18; // largest chunk of bsw_extend (overlap vs bucketing quality)
@@ -146,14 +146,14 @@ void release(Buf<T>& b)
     b.d = nullptr; b.h = nullptr; b.cap = b.hcap = 0;
 }
 
-// Shared-memory words per thread (S).  S >= qlen + 12 (prefetched groups, bsw_kernels.cuh), S / 4
+// Shared-memory words per thread (S).  S >= qlen + 8 (prefetched group, bsw_kernels.cuh), S / 4
 // odd (the 128-bit row accesses of a quarter warp then fall into 8 distinct bank groups).  Steps
 // of 8 words where occupancy is most sensitive to them, coarser for long queries (one launch per
 // step present in a chunk).
 inline int stride_for(int qmax)
 {
-    const int need = qmax + 12;
-    if (need > SHORT_MAX_QLEN + 12) return -1;
+    const int need = qmax + 8;
+    if (need > SHORT_MAX_QLEN + 8) return -1;
     int q;                                        // S / 4
     if (need <= 136) q = (need + 3) / 4;
     else if (need <= 520) q = ((need + 15) & ~15) / 4;
@@ -400,7 +400,7 @@ int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t
 }
 
 // ------------------------------------------------------------------------------------------
-// stage C (both routes): pack, bucket, launch plan
+// stage C (both routes): bucket, pack in processing order, launch plan
 // ------------------------------------------------------------------------------------------
 int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
 {
@@ -417,16 +417,13 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
     if (int rc = ensure(eng, s.rank, (size_t)n)) return rc;
     if (int rc = ensure(eng, s.nlist, (size_t)n)) return rc;
     if (int rc = ensure(eng, s.llist, (size_t)n)) return rc;
-    bsw_pack_pairs<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, s.qbase, s.rbase, eng->short_max, s.meta.d,
-                                                          s.qpk.d, s.tpk.d, s.nlist.d, s.llist.d, s.d_info);
-    eng->stats.kernel_launches++;
     s.plan.clear();
-    if (I.n_short > 0) {
+    {
         BucketKey K;
-        K.mn2 = I.mn[0]; K.mnh = I.mn[1]; K.mn1 = I.mn[2];
-        const int b_l2 = bits_for((uint32_t)(I.mx[0] - I.mn[0]));
-        K.b_h0 = bits_for((uint32_t)(I.mx[1] - I.mn[1]));
-        K.b_l1 = bits_for((uint32_t)(I.mx[2] - I.mn[2]));
+        K.mn2 = I.n_short ? I.mn[0] : 0; K.mnh = I.n_short ? I.mn[1] : 0; K.mn1 = I.n_short ? I.mn[2] : 0;
+        const int b_l2 = I.n_short ? bits_for((uint32_t)(I.mx[0] - I.mn[0])) : 0;
+        K.b_h0 = I.n_short ? bits_for((uint32_t)(I.mx[1] - I.mn[1])) : 0;
+        K.b_l1 = I.n_short ? bits_for((uint32_t)(I.mx[2] - I.mn[2])) : 0;
         const int total = b_l2 + K.b_h0 + K.b_l1;
         K.drop = std::max(0, total - BUCKET_BITS);          // only ever eats h0 / len1 bits: b_l2 <= 10
         K.short_max = eng->short_max;
@@ -435,21 +432,27 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
         if (int rc = ensure(eng, s.bins, (size_t)nbins + 1024)) return rc;   // bins, then the tile totals
         uint32_t* totals = s.bins.d + nbins;
         CUDA_TRY(cudaMemsetAsync(s.bins.d, 0, sizeof(uint32_t) * (size_t)nbins, s.st));
-        bsw_bucket_count<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, K, s.bins.d, s.rank.d);
-        bsw_bucket_scan_tiles<<<ntiles, 256, 0, s.st>>>(s.bins.d, nbins, totals);
-        bsw_bucket_scan_totals<<<1, 1024, 0, s.st>>>(totals, ntiles);
-        bsw_bucket_scatter<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d);
-        eng->stats.kernel_launches += 4;
-        // launch plan: the processing order ascends in len2, so the shared-memory classes are
-        // prefix ranges of it, read off the len2 histogram
-        int pos = 0;
-        for (int l = I.mn[0]; l <= std::min(I.mx[0], eng->short_max); ++l) {
-            const int cnt = (int)I.hist[l];
-            if (!cnt) continue;
-            const int qs = stride_for(l);
-            if (!s.plan.empty() && s.plan.back().qstride == qs) s.plan.back().count += cnt;
-            else s.plan.push_back(Launch{pos, cnt, qs});
-            pos += cnt;
+        bsw_bucket_count<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, K, s.bins.d, s.rank.d, s.llist.d, s.d_info);
+        eng->stats.kernel_launches++;
+        if (I.n_short > 0) {
+            bsw_bucket_scan_tiles<<<ntiles, 256, 0, s.st>>>(s.bins.d, nbins, totals);
+            bsw_bucket_scan_totals<<<1, 1024, 0, s.st>>>(totals, ntiles);
+            bsw_bucket_scatter<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d);
+            // 2-bit packing in processing order
+            bsw_pack_pairs<<<grid_for(c, I.n_short, 256), 256, 0, s.st>>>(s.desc.d, s.perm.d, I.n_short, s.qbase, s.rbase,
+                                                                          s.meta.d, s.qpk.d, s.tpk.d, s.nlist.d, s.d_info);
+            eng->stats.kernel_launches += 4;
+            // launch plan: the processing order ascends in len2, so the shared-memory classes are
+            // prefix ranges of it, read off the len2 histogram
+            int pos = 0;
+            for (int l = I.mn[0]; l <= std::min(I.mx[0], eng->short_max); ++l) {
+                const int cnt = (int)I.hist[l];
+                if (!cnt) continue;
+                const int qs = stride_for(l);
+                if (!s.plan.empty() && s.plan.back().qstride == qs) s.plan.back().count += cnt;
+                else s.plan.push_back(Launch{pos, cnt, qs});
+                pos += cnt;
+            }
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -822,6 +825,54 @@ int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const ui
     if (rc != BSW_OK) { quiesce(eng); return rc; }
     if (int rc2 = collect_cells(eng)) return rc2;
     eng->stats.ms_total = now_ms() - t_begin;
+    return BSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// band-doubling retry (tools/bwa/bwamem.c:723-753, :770-800), batched: the pairs that neither
+// repeated their score nor stayed within 3/4 of the band are gathered and re-run with w << t
+// ------------------------------------------------------------------------------------------
+int bsw_extend_retry(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
+                     int64_t n, int32_t w, int32_t max_try, const int32_t* prev_score, int32_t* band_used)
+{
+    if (!eng) return BSW_ERR_PARAM;
+    if (max_try < 1 || max_try > 8 || w < 0 || ((int64_t)w << (max_try - 1)) > 0x3fffffff) {
+        eng->err = "bsw_extend_retry: max_try must be in 1..8 and w << (max_try - 1) must fit";
+        return BSW_ERR_PARAM;
+    }
+    if (int rc = bsw_extend(eng, pairs, seq_ref, seq_qer, n, w)) return rc;
+    bsw_stats total = eng->stats;
+    std::vector<int64_t> active, next;
+    std::vector<int32_t> prev;
+    std::vector<SeqPair> sub;
+    for (int64_t i = 0; i < n; ++i) {
+        if (band_used) band_used[i] = w;
+        const int32_t p0 = prev_score ? prev_score[i] : -1;
+        if (!(pairs[i].score == p0 || pairs[i].max_off < (w >> 1) + (w >> 2))) { active.push_back(i); prev.push_back(pairs[i].score); }
+    }
+    for (int t = 1; t < max_try && !active.empty(); ++t) {
+        const int32_t wt = w << t;
+        sub.resize(active.size());
+        for (size_t k = 0; k < active.size(); ++k) sub[k] = pairs[active[k]];
+        if (int rc = bsw_extend(eng, sub.data(), seq_ref, seq_qer, (int64_t)sub.size(), wt)) return rc;
+        total.cells_effective += eng->stats.cells_effective; total.kernel_launches += eng->stats.kernel_launches;
+        total.h2d_bytes += eng->stats.h2d_bytes; total.d2h_bytes += eng->stats.d2h_bytes;
+        total.ms_kernel += eng->stats.ms_kernel; total.ms_pack += eng->stats.ms_pack; total.ms_scatter += eng->stats.ms_scatter;
+        next.clear();
+        std::vector<int32_t> nprev;
+        for (size_t k = 0; k < active.size(); ++k) {
+            const int64_t i = active[k];
+            SeqPair& d = pairs[i]; const SeqPair& r = sub[k];
+            d.score = r.score; d.tle = r.tle; d.gtle = r.gtle; d.qle = r.qle; d.gscore = r.gscore; d.max_off = r.max_off;
+            if (band_used) band_used[i] = wt;
+            if (!(r.score == prev[k] || r.max_off < (wt >> 1) + (wt >> 2))) { next.push_back(i); nprev.push_back(r.score); }
+        }
+        active.swap(next); prev.swap(nprev);
+    }
+    total.ms_total = 0;
+    total.pairs = n;
+    eng->stats = total;
+    eng->n = n;
     return BSW_OK;
 }
 

@@ -127,13 +127,14 @@ __device__ __forceinline__ int4 bsw_pack_result(const PairState& st)
 
 // ---------------------------------------------------------------------------------------
 // Short-pair kernel: one pair per thread.
-//   Position p of the processing order handles pair s = perm[first + p] of the chunk:
-//   meta[s] = {query word/byte offset, target word/byte offset, qlen | tlen << 16, h0 | flags},
-//   res[s] receives its packed result (input order).
+//   Position p of the processing order handles pair s = perm[first + p] of the chunk; res[s]
+//   receives its packed result (input order).  Descriptor {query word/byte offset, target
+//   word/byte offset, qlen | tlen << 16, h0 | flags}: meta[first + p] for the 2-bit variant (packed
+//   in processing order: neighbouring threads read neighbouring words), meta[s] for the byte variant.
 //   BYTESEQ = false: sequences are 2-bit packed, 16 bases per 32-bit word, word-aligned.
 //   BYTESEQ = true : one base code per byte (pairs that contain N, code 4).
-//   Shared memory of a block (S = qstride = words per thread, S / 4 odd, S >= qlen + 12: the
-//   pipelined sweep reads up to two groups past the last full one):
+//   Shared memory of a block (S = qstride = words per thread, S / 4 odd, S >= qlen + 8: the
+//   pipelined sweep reads at most one group past the window, i.e. up to column qlen + 3):
 //     eh [tid * S + j]                cell j of thread tid: e << 16 | h.  A 128-bit access moves
 //                                     columns j..j+3; with S / 4 odd the 8 lanes of a quarter warp
 //                                     hit 8 distinct 16-byte bank groups (conflict-free)
@@ -165,7 +166,7 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
     bool run = local < count;
     if (run) {
         s = (int)perm[first + local];
-        md = meta[s];
+        md = BYTESEQ ? meta[s] : meta[first + local];
         if (!BYTESEQ && (md.w & BSW_META_NFLAG)) run = false;
     }
     if (run) {

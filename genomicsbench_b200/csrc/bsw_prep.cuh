@@ -6,9 +6,10 @@
 // nothing at all when the caller's buffers are pinned), and these kernels
 //   bsw_scan_pairs   read the caller's 72-byte SeqPair records, validate the domain, emit the
 //                    16-byte descriptor per pair and the chunk summary the host plans with
-//   bsw_pack_pairs   2-bit pack query / reference bytes (16 bases per word), flag pairs with N,
-//                    list the pairs that need the byte-reading kernels
-//   bsw_bucket_*     counting sort of the chunk by (len2, h0, len1) -> processing order perm[]
+//   bsw_bucket_*     counting sort of the chunk by (len2, h0, len1) -> processing order perm[];
+//                    lists the pairs too long for the short kernel
+//   bsw_pack_pairs   2-bit pack query / reference bytes (16 bases per word) in processing order,
+//                    flag and list the pairs with N
 //   bsw_writeback    unpack the 16-byte results into the caller's SeqPair records (input order)
 #pragma once
 #include <cstdint>
@@ -137,33 +138,36 @@ __device__ __forceinline__ uint32_t bsw_pack16(const uint8_t* src, int nb, int r
     return out;
 }
 
-// One warp packs 32 consecutive pairs of the chunk: the word counts are scanned across the warp,
-// one atomicAdd per sequence kind reserves the output range, then the lanes sweep the
-// concatenated word list (lane -> word, pair found by binary search), so loads stay coalesced
-// for short and long sequences alike.  meta[i] gets word offsets; desc[i] keeps byte offsets.
+// One warp packs the pairs at 32 consecutive positions of the processing order (perm[]), so that
+// the DP kernel later reads descriptors and sequences of neighbouring threads from neighbouring
+// addresses.  The word counts are scanned across the warp, one atomicAdd per sequence kind
+// reserves the output range, then the lanes sweep the concatenated word list (lane -> word, pair
+// found by binary search), so loads stay coalesced for short and long sequences alike.
+// meta[s] (processing order) gets word offsets; desc[i] (input order) keeps byte offsets.
 __global__ void __launch_bounds__(256)
-bsw_pack_pairs(const int4* __restrict__ desc, int n, const uint8_t* __restrict__ qraw,
-               const uint8_t* __restrict__ rraw, int short_max, int4* __restrict__ meta,
+bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm, int n_sorted,
+               const uint8_t* __restrict__ qraw, const uint8_t* __restrict__ rraw, int4* __restrict__ meta,
                uint32_t* __restrict__ qpk, uint32_t* __restrict__ tpk,
-               uint32_t* __restrict__ nlist, uint32_t* __restrict__ llist, ChunkInfo* __restrict__ info)
+               uint32_t* __restrict__ nlist, ChunkInfo* __restrict__ info)
 {
     __shared__ uint32_t s_pre[8][2][33];
     __shared__ uint32_t s_bad[8][32];
+    __shared__ int4 s_desc[8][32];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
-    for (int base = (blockIdx.x * (blockDim.x >> 5) + wib) * 32; base < n; base += nwarps * 32) {
-        const int i = base + lane;
+    for (int base = (blockIdx.x * (blockDim.x >> 5) + wib) * 32; base < n_sorted; base += nwarps * 32) {
+        const int s = base + lane;
         int4 d = make_int4(0, 0, 0, 0);
-        int len2 = 0, len1 = 0;
-        bool is_short = false;
-        if (i < n) {
-            d = desc[i];
+        int len2 = 0, len1 = 0, pi = 0;
+        if (s < n_sorted) {
+            pi = (int)perm[s];
+            d = desc[pi];
             len2 = d.z & 0xffff; len1 = (d.z >> 16) & 0xffff;
-            is_short = len2 <= short_max;
         }
-        const uint32_t nq = is_short ? (uint32_t)(len2 + 15) >> 4 : 0u;
-        const uint32_t nt = is_short ? (uint32_t)(len1 + 15) >> 4 : 0u;
+        s_desc[wib][lane] = d;
+        const uint32_t nq = (uint32_t)(len2 + 15) >> 4;
+        const uint32_t nt = (uint32_t)(len1 + 15) >> 4;
         uint32_t pq = nq, pt = nt;                  // inclusive warp scans
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -187,7 +191,7 @@ bsw_pack_pairs(const int4* __restrict__ desc, int n, const uint8_t* __restrict__
 #pragma unroll
                 for (int step = 16; step > 0; step >>= 1)
                     if (pre[lo + step] <= wv) lo += step;
-                const int4 dd = desc[base + lo];
+                const int4 dd = s_desc[wib][lo];
                 const int len = kind ? (dd.z >> 16) & 0xffff : dd.z & 0xffff;
                 const uint32_t wi = wv - pre[lo];
                 const uint8_t* src = (kind ? rraw + dd.y : qraw + dd.x) + 16 * (int)wi;
@@ -199,11 +203,10 @@ bsw_pack_pairs(const int4* __restrict__ desc, int n, const uint8_t* __restrict__
             }
         }
         __syncwarp();
-        if (i < n) {
+        if (s < n_sorted) {
             const bool has_n = s_bad[wib][lane] != 0;
-            meta[i] = make_int4((int)(bq + pq - nq), (int)(bt + pt - nt), d.z, d.w | (has_n ? BSW_META_NFLAG : 0));
-            if (!is_short) llist[atomicAdd(&info->n_llist, 1u)] = (uint32_t)i;
-            else if (has_n) { nlist[atomicAdd(&info->n_nlist, 1u)] = (uint32_t)i; atomicMax(&info->qmax_n, len2); }
+            meta[s] = make_int4((int)(bq + pq - nq), (int)(bt + pt - nt), d.z, d.w | (has_n ? BSW_META_NFLAG : 0));
+            if (has_n) { nlist[atomicAdd(&info->n_nlist, 1u)] = (uint32_t)pi; atomicMax(&info->qmax_n, len2); }
         }
         __syncwarp();
     }
@@ -224,14 +227,16 @@ __device__ __forceinline__ uint32_t bsw_bucket_of(const BucketKey& K, const int4
     return key >> K.drop;
 }
 
-// rank[i] = arrival order of pair i inside its bin; bins[] accumulates the bin sizes
+// rank[i] = arrival order of pair i inside its bin; bins[] accumulates the bin sizes; pairs whose
+// query is too long for the short kernel are listed for the warp-per-pair kernel instead
 __global__ void __launch_bounds__(256)
 bsw_bucket_count(const int4* __restrict__ desc, int n, const __grid_constant__ BucketKey K,
-                 uint32_t* __restrict__ bins, uint32_t* __restrict__ rank)
+                 uint32_t* __restrict__ bins, uint32_t* __restrict__ rank,
+                 uint32_t* __restrict__ llist, ChunkInfo* __restrict__ info)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int4 d = desc[i];
-        if ((d.z & 0xffff) > K.short_max) continue;
+        if ((d.z & 0xffff) > K.short_max) { llist[atomicAdd(&info->n_llist, 1u)] = (uint32_t)i; continue; }
         rank[i] = atomicAdd(&bins[bsw_bucket_of(K, d)], 1u);
     }
 }

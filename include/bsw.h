@@ -65,7 +65,7 @@ typedef struct bsw_params {
     int32_t devices[16];                  /* CUDA ordinals when n_devices > 0        */
     int32_t host_threads;                 /* packer threads per engine, 0 => auto    */
     int32_t long_min_qlen;                /* queries of at least this length use the warp-per-pair
-                                             kernel; 0 => default (821, the short kernel's shared-
+                                             kernel; 0 => default (825, the short kernel's shared-
                                              memory limit + 1); 1 routes every pair to it          */
     int32_t reserved[7];
 } bsw_params;
@@ -106,6 +106,20 @@ void        bsw_default_params(bsw_params* p);       /* bwa defaults: main_bande
  * input order preserved; pads are never written and pair.id is never read. */
 int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref,
                const uint8_t* seq_qer, int64_t n_pairs, int32_t w);
+
+/* ---- (f.1) band-doubling retry of the aligner ------------------------------
+ * replaces: the MAX_BAND_TRY loops around ksw_extend2 in mem_chain2aln,
+ * tools/bwa/bwamem.c:630,723-753 (left extension) and :770-800 (right extension):
+ *     for (t = 0; t < max_try; ++t) { prev = score; w_t = w << t; extend with w_t;
+ *                                     if (score == prev || max_off < (w_t>>1) + (w_t>>2)) break; }
+ * batched: try t re-runs only the pairs that did not break at try t-1.  prev_score[i] is the
+ * score before the first try (bwamem.c uses -1 for left extensions, :707, and the seed / left
+ * score h0 for right extensions, :767); NULL means -1 for every pair.  band_used[i] (optional)
+ * receives the band of the last try pair i ran (aw[] at bwamem.c:725,772).  The six result
+ * fields hold the outcome of that last try. */
+int bsw_extend_retry(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref,
+                     const uint8_t* seq_qer, int64_t n_pairs, int32_t w, int32_t max_try,
+                     const int32_t* prev_score, int32_t* band_used);
 
 /* Pinned host memory.  bsw_extend takes any host pointers; when all three buffers (pairs,
  * seq_ref, seq_qer) are page-locked -- allocated here, or registered, or pinned by the caller's

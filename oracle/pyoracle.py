@@ -67,6 +67,29 @@ class Oracle:
         return int(self.lib.bsw_oracle_batch(C.byref(params), pairs.ctypes.data, seq_ref.ctypes.data,
                                              seq_qer.ctypes.data, len(pairs), w, nthreads))
 
+    def band_retry(self, params: OracleParams, pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray,
+                   w: int, max_try: int = 2, prev_score=None) -> np.ndarray:
+        """Restates the MAX_BAND_TRY loops of mem_chain2aln (tools/bwa/bwamem.c:630,723-753,770-800):
+        for t in range(max_try): prev = score; w_t = w << t; extend; break if score == prev or
+        max_off < (w_t >> 1) + (w_t >> 2).  Results in place; returns the band of each pair's last try."""
+        n = len(pairs)
+        prev = np.full(n, -1, dtype=np.int64) if prev_score is None else np.asarray(prev_score, dtype=np.int64).copy()
+        band = np.zeros(n, dtype=np.int32)
+        active = np.arange(n)
+        for t in range(max_try):
+            if len(active) == 0:
+                break
+            wt = w << t
+            sub = pairs[active].copy()
+            self.batch(params, sub, seq_ref, seq_qer, wt)
+            for f in ("score", "qle", "tle", "gtle", "gscore", "max_off"):
+                pairs[f][active] = sub[f]
+            band[active] = wt
+            stop = (sub["score"] == prev[active]) | (sub["max_off"] < (wt >> 1) + (wt >> 2))
+            prev[active] = sub["score"]
+            active = active[~stop]
+        return band
+
     def pair(self, params: OracleParams, query: np.ndarray, target: np.ndarray, w: int, h0: int):
         out = np.zeros(6, dtype=np.int32)
         cells = self.lib.bsw_oracle_pair(C.byref(params), query.ctypes.data, len(query), target.ctypes.data,
@@ -129,3 +152,60 @@ class Reference:
     def scalar(self, params, pairs, seq_ref, seq_qer, w) -> float:
         return float(self.lib.ref_scalar(C.byref(params), pairs.ctypes.data, seq_ref.ctypes.data,
                                          seq_qer.ctypes.data, len(pairs), w))
+
+
+class KswReference:
+    """The canonical ksw_extend2 of the reference tree (tools/bwa/ksw.c:380-479), compiled unmodified
+    into oracle/_ref/libkswref.so; used to pin the band-retry restatement with the loop exactly as
+    mem_chain2aln writes it (tools/bwa/bwamem.c:723-753)."""
+
+    def __init__(self):
+        if not KSW_SO.exists():
+            raise FileNotFoundError(f"{KSW_SO} absent (built only where /root/reference is mounted)")
+        self.lib = C.CDLL(str(KSW_SO))
+        I, PI = C.c_int, C.POINTER(C.c_int)
+        self.lib.ksw_extend2.restype = I
+        self.lib.ksw_extend2.argtypes = [I, C.c_void_p, I, C.c_void_p, I, C.c_void_p, I, I, I, I, I, I, I, I,
+                                         PI, PI, PI, PI, PI]
+
+    @staticmethod
+    def available() -> bool:
+        return KSW_SO.exists()
+
+    @staticmethod
+    def scmat(match: int, mismatch: int, ambig: int) -> np.ndarray:
+        """bwa_fill_scmat (benchmarks/bsw/main_banded.cpp:73-81)."""
+        m = np.zeros(25, dtype=np.int8)
+        k = 0
+        for i in range(4):
+            for j in range(4):
+                m[k] = match if i == j else -mismatch
+                k += 1
+            m[k] = ambig
+            k += 1
+        m[20:25] = ambig
+        return m
+
+    def band_retry(self, params: OracleParams, pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray,
+                   w: int, max_try: int = 2, prev_score=None) -> np.ndarray:
+        mat = self.scmat(params.match, params.mismatch, params.ambig)
+        band = np.zeros(len(pairs), dtype=np.int32)
+        out = [C.c_int(0) for _ in range(5)]
+        for i in range(len(pairs)):
+            q = np.ascontiguousarray(seq_qer[pairs["idq"][i]: pairs["idq"][i] + pairs["len2"][i]])
+            t = np.ascontiguousarray(seq_ref[pairs["idr"][i]: pairs["idr"][i] + pairs["len1"][i]])
+            score = -1 if prev_score is None else int(prev_score[i])
+            for tr in range(max_try):                                   # bwamem.c:723 / :770
+                prev = score                                            # :724 / :771
+                aw = w << tr                                            # :725 / :772
+                score = self.lib.ksw_extend2(len(q), q.ctypes.data, len(t), t.ctypes.data, 5, mat.ctypes.data,
+                                             params.o_del, params.e_del, params.o_ins, params.e_ins, aw,
+                                             params.end_bonus, params.zdrop, int(pairs["h0"][i]),
+                                             *[C.byref(x) for x in out])  # :746 / :793
+                band[i] = aw
+                if score == prev or out[4].value < (aw >> 1) + (aw >> 2):   # :753 / :800
+                    break
+            pairs["score"][i] = score
+            for f, x in zip(("qle", "tle", "gtle", "gscore", "max_off"), out):
+                pairs[f][i] = x.value
+        return band

@@ -129,7 +129,7 @@ def test_edge_cases(lib, oracle):
         assert eng.stats()["pairs"] == 0
         rng = np.random.default_rng(7)
         lens = [(1, 1), (1, 50), (50, 1), (2, 3), (127, 128), (128, 127), (129, 129), (300, 17), (17, 300),
-                (820, 820), (5, 820), (33, 31), (64, 64), (65, 63)]
+                (824, 824), (5, 824), (33, 31), (64, 64), (65, 63)]
         n = len(lens)
         pairs = np.zeros(n, dtype=SEQPAIR_DTYPE)
         ref = rng.integers(0, 4, size=sum(a for a, _ in lens) + 8, dtype=np.uint8)
