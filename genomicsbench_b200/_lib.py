@@ -30,6 +30,7 @@ RESULT_FIELDS = ("score", "qle", "tle", "gtle", "gscore", "max_off")
 BSW_OK = 0
 BSW_ERR_PARAM, BSW_ERR_DOMAIN, BSW_ERR_CUDA, BSW_ERR_NOMEM, BSW_ERR_STATE, BSW_ERR_IO = -1, -2, -3, -4, -5, -6
 BSW_ZDROP_VECTOR, BSW_ZDROP_SCALAR = 0, 1
+BSW_SHORT_PACKED16, BSW_SHORT_WIDE32 = 0, 1
 
 
 class BswParams(C.Structure):
@@ -38,7 +39,7 @@ class BswParams(C.Structure):
         ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32),
         ("ambig", C.c_int32), ("zdrop_mode", C.c_int32), ("n_devices", C.c_int32),
         ("devices", C.c_int32 * 16), ("host_threads", C.c_int32), ("long_min_qlen", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("short_variant", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

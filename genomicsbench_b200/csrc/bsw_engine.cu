@@ -21,6 +21,7 @@
 // the pack kernel and run by the byte-reading kernels before the chunk's results leave.
 #include "bsw_common.h"
 #include "bsw_kernels.cuh"
+#include "bsw_kernel16.cuh"
 #include "bsw_prep.cuh"
 #include <cstdio>
 #include <cstring>
@@ -100,6 +101,7 @@ struct bsw_engine {
     std::string err;
     bsw_stats stats;
     int short_max = SHORT_MAX_QLEN;       // longest query the short kernel takes
+    bool use16 = true;                    // short pairs run the packed 16-bit kernel (bsw_kernel16.cuh)
     // staged batch (bsw_stage / bsw_run_staged / bsw_fetch)
     bool staged = false, ran = false;
     int64_t n = 0;
@@ -150,12 +152,12 @@ void release(Buf<T>& b)
 // odd (the 128-bit row accesses of a quarter warp then fall into 8 distinct bank groups).  Steps
 // of 8 words where occupancy is most sensitive to them, coarser for long queries (one launch per
 // step present in a chunk).
-inline int stride_for(int qmax)
+inline int stride_for(int qmax, bool fine = false)
 {
     const int need = qmax + 8;
     if (need > SHORT_MAX_QLEN + 8) return -1;
     int q;                                        // S / 4
-    if (need <= 136) q = (need + 3) / 4;
+    if (need <= 136 || (fine && need <= 520)) q = (need + 3) / 4;
     else if (need <= 520) q = ((need + 15) & ~15) / 4;
     else q = ((need + 31) & ~31) / 4;
     if (!(q & 1)) ++q;
@@ -183,6 +185,10 @@ int set_kernel_attrs(bsw_engine* eng, DevCtx& c)
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
     CUDA_TRY(cudaFuncSetAttribute(bsw_short_kernel<SHORT_BLOCK, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<SHORT_BLOCK, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<SHORT_BLOCK, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
     c.attr_set = true;
     return BSW_OK;
 }
@@ -203,6 +209,7 @@ int validate_params(const bsw_params* p, std::string& why)
     if (p->end_bonus < 0 || p->end_bonus > 16000) return bad("end_bonus out of range");
     if (p->n_devices < 0 || p->n_devices > 16) return bad("n_devices must be in 0..16");
     if (p->long_min_qlen < 0) return bad("long_min_qlen must be >= 0");
+    if (p->short_variant != BSW_SHORT_PACKED16 && p->short_variant != BSW_SHORT_WIDE32) return bad("short_variant");
     return BSW_OK;
 }
 
@@ -440,7 +447,8 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
             bsw_bucket_scatter<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d);
             // 2-bit packing in processing order
             bsw_pack_pairs<<<grid_for(c, I.n_short, 256), 256, 0, s.st>>>(s.desc.d, s.perm.d, I.n_short, s.qbase, s.rbase,
-                                                                          s.meta.d, s.qpk.d, s.tpk.d, s.nlist.d, s.d_info);
+                                                                          s.meta.d, s.qpk.d, s.tpk.d, s.nlist.d, s.d_info,
+                                                                          eng->use16 ? eng->p.match : 0);
             eng->stats.kernel_launches += 4;
             // launch plan: the processing order ascends in len2, so the shared-memory classes are
             // prefix ranges of it, read off the len2 histogram
@@ -448,7 +456,7 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
             for (int l = I.mn[0]; l <= std::min(I.mx[0], eng->short_max); ++l) {
                 const int cnt = (int)I.hist[l];
                 if (!cnt) continue;
-                const int qs = stride_for(l);
+                const int qs = stride_for(l, eng->use16);
                 if (!s.plan.empty() && s.plan.back().qstride == qs) s.plan.back().count += cnt;
                 else s.plan.push_back(Launch{pos, cnt, qs});
                 pos += cnt;
@@ -474,8 +482,15 @@ int launch_dp(bsw_engine* eng, DevCtx& c, Slot& s)
         const Launch& L = s.plan[(size_t)k];
         cudaStream_t st = c.cs[li % NSTREAMS];
         const int grid = (L.count + SHORT_BLOCK - 1) / SHORT_BLOCK;
-        bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, short_smem_bytes(L.qstride), st>>>(
-            s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
+        if (!eng->use16)
+            bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, short_smem_bytes(L.qstride), st>>>(
+                s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
+        else if (eng->kp.oe_del == eng->kp.oe_ins)
+            bsw_short16_kernel<SHORT_BLOCK, true><<<grid, SHORT_BLOCK, k16::smem_bytes(SHORT_BLOCK, L.qstride), st>>>(
+                s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
+        else
+            bsw_short16_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, k16::smem_bytes(SHORT_BLOCK, L.qstride), st>>>(
+                s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
         eng->stats.kernel_launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -747,6 +762,7 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
     k.mx = std::max(std::max(k.match, k.mismatch_neg), k.ambig);
     k.w = 0; k.kone = 1;
     eng->pool.reset(new ThreadPool(auto_threads(params->host_threads)));
+    eng->use16 = params->short_variant == BSW_SHORT_PACKED16;
     eng->short_max = params->long_min_qlen > 0 ? std::min(params->long_min_qlen - 1, SHORT_MAX_QLEN) : SHORT_MAX_QLEN;
     memset(&eng->stats, 0, sizeof(eng->stats));
 

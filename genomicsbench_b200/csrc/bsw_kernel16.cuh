@@ -1,0 +1,500 @@
+// bsw_kernel16.cuh -- the packed short-pair kernel: two DP columns per DPX instruction.
+//
+// Same per-pair semantics as bsw_short_kernel (bsw_kernels.cuh; SURVEY.md Appendix A ==
+// benchmarks/bsw/bandedSWA.cpp:128-249 with the z-drop rule of :323-336), same thread-per-pair
+// row sweep over the adaptive window, but the row lives in shared memory as two 16-bit planes
+// and the recurrence runs on the .S16x2 forms of the DPX instructions (VIADDMNMX.S16x2,
+// VIMNMX.S16x2, VIMNMX3.S16x2 -- same issue rate as the 32-bit forms, two cells each):
+//
+//   group g of a thread's row (16 bytes, one LDS.128 / STS.128) = columns 4g .. 4g+3:
+//     word 0 = hs[4g+1] << 16 | hs[4g]      word 1 = hs[4g+3] << 16 | hs[4g+2]
+//     word 2 = es[4g+1] << 16 | es[4g]      word 3 = es[4g+3] << 16 | es[4g+2]
+//   hs[j] = eh[j].h = H(i-1, j-1), es[j] = eh[j].e = E(i, j)  (bandedSWA.cpp:196-213)
+//
+//   per pair word (columns c, c+1), everything elementwise in the two halves:
+//     M  = max(min(Hd + S, Hd * (1 + match)), 0)   M = Hd ? Hd + s : 0, clamped (the cap is 0 iff Hd is)
+//     U  = max(M - oe_del, 0)          E' = max(E - e_del, U)
+//     A  = max(M - oe_ins, 0)          (= U when oe_ins == oe_del: template SAMEGAP)
+//     ME = max(M, E)
+//   the only sequential part is F; it runs in the HIGH halves, one VIADDMNMX per column:
+//     F(c+1) = max(F(c) - e_ins, A(c))   F(c+2) = max(F(c+1) - e_ins, A(c+1))
+//   and one PRMT gathers (F(c+1) | F(c)) for  H = max(ME, F).  One more PRMT per word shifts the
+//   new H values by one column (eh[j].h receives H(i, j-1)).
+//   The match scores S of a column pair come from a 16-entry table (one copy per lane, bank =
+//   lane) indexed by the pair's 4 bits of  query ^ target;  the index arithmetic runs on the
+//   FMA pipe (IMAD.SHL + IMAD.HI), so a score costs no ALU-pipe instruction.
+//   Row maximum: per 8-column block one key  max(H) << 16 | last column of the block; the exact
+//   column (the LAST one holding the maximum, bandedSWA.cpp:202-203) is resolved after the row
+//   from the h plane, and only when the row epilogue needs it.
+//
+// Domain of this kernel: (h0 + len2 * match) * (1 + match) <= 32767 (every intermediate fits 16
+// signed bits and the cap trick holds); the pack kernel routes everything else, and the pairs
+// that contain N, to the 32-bit byte kernel.
+//
+// The row sweep is __host__ __device__: tests/k16_emu.cu runs it on the CPU with emulated DPX
+// instructions and an emulated shared-memory window, so the arithmetic is checked against the
+// oracle without a GPU as well.
+#pragma once
+#include <cstring>
+#include "bsw_kernels.cuh"
+
+namespace bsw {
+namespace k16 {
+
+constexpr int TAB_WORDS = 16 * 32;            // 16 pair patterns x 32 lane copies
+constexpr int TAB_BYTES = TAB_WORDS * 4;
+
+// host emulation state (tests/emu; unused by the product)
+inline thread_local uint8_t* emu_smem = nullptr;
+inline thread_local long long emu_overflows = 0;
+#if !defined(__CUDA_ARCH__)
+inline int16_t emu_wrap(int v)
+{
+    if (v < -32768 || v > 32767) ++emu_overflows;
+    return (int16_t)v;
+}
+#endif
+
+// ---- shared-memory accessors (addresses are 32-bit shared-window addresses) ------------------
+BSW_HD uint4 lds128(uint32_t a)
+{
+    uint4 v;
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+#else
+    memcpy(&v, emu_smem + a, 16);
+#endif
+    return v;
+}
+BSW_HD void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+#else
+    const uint32_t v[4] = {x, y, z, w};
+    memcpy(emu_smem + a, v, 16);
+#endif
+}
+BSW_HD uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+#else
+    memcpy(&v, emu_smem + a, 4);
+#endif
+    return v;
+}
+BSW_HD uint32_t lds16(uint32_t a)
+{
+    uint32_t v;
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+#else
+    uint16_t h;
+    memcpy(&h, emu_smem + a, 2);
+    v = h;
+#endif
+    return v;
+}
+BSW_HD void sts16(uint32_t a, uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(x) : "memory");
+#else
+    const uint16_t h = (uint16_t)x;
+    memcpy(emu_smem + a, &h, 2);
+#endif
+}
+BSW_HD uint32_t ldg32(const uint32_t* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// ---- DPX .S16x2 instructions and the FMA-pipe helpers -----------------------------------------
+#if !defined(__CUDA_ARCH__)
+#define K16_EMU2(EXPR)                                                                            \
+    uint32_t r_ = 0;                                                                              \
+    for (int s_ = 0; s_ < 32; s_ += 16) {                                                         \
+        const int x = (int16_t)(a >> s_), y = (int16_t)(b >> s_), z = (int16_t)(c >> s_);        \
+        (void)x; (void)y; (void)z;                                                                \
+        r_ |= (uint32_t)(uint16_t)(EXPR) << s_;                                                   \
+    }                                                                                             \
+    return r_;
+#endif
+BSW_HD uint32_t addmin_relu(uint32_t a, uint32_t b, uint32_t c)     // max(min(a + b, c), 0)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmin_s16x2_relu(a, b, c);
+#else
+    K16_EMU2(std::max<int>(std::min<int>(emu_wrap(x + y), z), 0))
+#endif
+}
+BSW_HD uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c)     // max(a + b, c, 0)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s16x2_relu(a, b, c);
+#else
+    K16_EMU2(std::max<int>(std::max<int>(emu_wrap(x + y), z), 0))
+#endif
+}
+BSW_HD uint32_t addmax(uint32_t a, uint32_t b, uint32_t c)          // max(a + b, c)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s16x2(a, b, c);
+#else
+    K16_EMU2(std::max<int>(emu_wrap(x + y), z))
+#endif
+}
+BSW_HD uint32_t max2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vmaxs2(a, b);
+#else
+    const uint32_t c = 0;
+    K16_EMU2(std::max<int>(x, y))
+#endif
+}
+BSW_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __vimax3_s16x2(a, b, c);
+#else
+    K16_EMU2(std::max<int>(std::max<int>(x, y), z))
+#endif
+}
+BSW_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t ab = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r |= (uint32_t)((ab >> (8 * ((sel >> (4 * k)) & 7))) & 0xff) << (8 * k);
+    return r;
+#endif
+}
+BSW_HD int imax3(int a, int b, int c)
+{
+#if defined(__CUDA_ARCH__)
+    return __vimax3_s32(a, b, c);
+#else
+    return std::max(std::max(a, b), c);
+#endif
+}
+// a * b + c on the FMA pipe (IMAD)
+BSW_HD uint32_t mad_u(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return a * b + c;
+#endif
+}
+// hi32(a * b) + c on the FMA pipe (IMAD.HI.U32)
+BSW_HD uint32_t madhi_u(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32) + c;
+#endif
+}
+
+BSW_HD uint32_t pack2(int hi, int lo) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu); }
+
+// score-table word of pattern idx = x1 << 2 | x0 (x = query ^ target of the two columns, 0 = match)
+BSW_HD uint32_t table_word(const KParams& P, int idx)
+{
+    return pack2((idx >> 2) ? P.mismatch_neg : P.match, (idx & 3) ? P.mismatch_neg : P.match);
+}
+
+// true when the packed kernel may run the pair (see the header comment)
+BSW_HD bool eligible(int match, int qlen, int h0)
+{
+    return (long long)(h0 + (long long)qlen * match) * (1 + match) <= 32767;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row sweep of one pair.
+//   md        {query word offset (unused here), target word offset (unused), qlen | tlen << 16, h0}
+//   qw, tw    2-bit packed query / target, 16 bases per word
+//   eh_sa     this thread's row (S words, groups of 16 bytes as described above)
+//   qp_sa     this thread's slot of the query plane: halfword k (columns 8k .. 8k+7, 2 bits per
+//             base) at qp_sa + k * qp_stride
+//   tab_sa    score table + 4 * lane
+// ------------------------------------------------------------------------------------------------
+template <bool SAMEGAP>
+BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restrict__ qw,
+                       const uint32_t* __restrict__ tw, const uint32_t eh_sa, const uint32_t qp_sa,
+                       const uint32_t qp_stride, const uint32_t tab_sa, PairState& st, long long& my_cells)
+{
+    const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w & 0xffff;
+
+    // ---- first row (bandedSWA.cpp:155-157) and the query plane
+    {
+        int hv = h0;
+        for (int j0 = 0; j0 <= qlen; j0 += 4) {
+            uint32_t v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = j0 + c;
+                if (j == 1) hv = h0 > P.oe_ins ? h0 - P.oe_ins : 0;
+                else if (j >= 2) hv = hv > P.e_ins ? hv - P.e_ins : 0;
+                v[c] = j <= qlen ? (uint32_t)hv : 0u;
+            }
+            sts128(eh_sa + 4u * (uint32_t)j0, v[0] | (v[1] << 16), v[2] | (v[3] << 16), 0u, 0u);
+        }
+        const int nw = (qlen + 15) >> 4;
+        uint32_t qa = qp_sa;
+        for (int k = 0; k < nw; ++k) {
+            const uint32_t v = ldg32(qw + k);
+            sts16(qa, v & 0xffffu);
+            sts16(qa + qp_stride, v >> 16);
+            qa += 2 * qp_stride;
+        }
+    }
+    const int w = bsw_clamp_band(P, qlen);
+
+    st.max = h0; st.max_i = -1; st.max_j = -1; st.max_ie = -1; st.gscore = -1; st.max_off = 0;
+    int beg = 0, end = qlen;
+    uint32_t tword = 0;
+    // loop constants, pinned in registers through an opaque zero (see bsw_short_kernel)
+    const uint32_t zero = (uint32_t)md.z >> 31;
+    const uint32_t noe_del2 = zero + pack2(-P.oe_del, -P.oe_del);
+    const uint32_t noe_ins2 = zero + pack2(-P.oe_ins, -P.oe_ins);
+    const uint32_t ne_del2 = zero + pack2(-P.e_del, -P.e_del);
+    const uint32_t negg_hi = zero + pack2(-P.e_ins, 0);
+    const uint32_t capmul = zero + (uint32_t)(1 + P.match);
+    const uint32_t k65536 = zero + 65536u * (uint32_t)P.kone;
+    const uint32_t k16c = zero + 16u * (uint32_t)P.kone;
+    const uint32_t k128 = zero + 128u * (uint32_t)P.kone;
+    (void)noe_ins2;
+
+    // address of column j's h half (its e half is 8 bytes further)
+#define K16_HADDR(J) (eh_sa + (((uint32_t)(J) >> 2) << 4) + (((uint32_t)(J) & 3u) << 1))
+    // score word of pair K (columns 2K, 2K+1 of the block) from the block's x halfword: the pair's
+    // nibble is isolated by a left shift + IMAD.HI (x 16 = >> 28), scaled to the table stride by an IMAD
+#define K16_SCORE(X, K) lds32(mad_u(madhi_u((X) << (28 - 4 * (K)), k16c, 0u), k128, tab_sa))
+    // one pair word: HW / EW loaded halves, SW scores; HN = new H of the two columns, EN = new E
+#define K16_WORD(HW, EW, SW, HN, EN)                                                              \
+    {                                                                                             \
+        const uint32_t cap_ = mad_u((HW), capmul, 0u);                                            \
+        const uint32_t M_ = addmin_relu((HW), (SW), cap_);                                        \
+        const uint32_t U_ = addmax_relu(M_, noe_del2, zero);                                        \
+        EN = addmax((EW), ne_del2, U_);                                                           \
+        const uint32_t A_ = SAMEGAP ? U_ : addmax_relu(M_, noe_ins2, zero);                         \
+        const uint32_t ME_ = max2(M_, (EW));                                                      \
+        const uint32_t f1_ = addmax(fc, negg_hi, mad_u(A_, k65536, 0u));                          \
+        const uint32_t Fc_ = prmt(fc, f1_, 0x7632);                                               \
+        fc = addmax(f1_, negg_hi, A_);                                                            \
+        HN = max2(ME_, Fc_);                                                                      \
+    }
+    // one 4-column group: CUR = its four words, SA / SB = scores of its two pairs, ADDR = its address
+#define K16_GROUP(CUR, SA, SB, ADDR, HN0, HN1)                                                    \
+    {                                                                                             \
+        uint32_t en0_, en1_;                                                                      \
+        K16_WORD((CUR).x, (CUR).z, (SA), HN0, en0_)                                               \
+        K16_WORD((CUR).y, (CUR).w, (SB), HN1, en1_)                                               \
+        sts128((ADDR), prmt(carry, HN0, 0x5432), prmt(HN0, HN1, 0x5432), en0_, en1_);             \
+        carry = HN1;                                                                              \
+    }
+    // row-maximum key of a block whose packed maximum is G and whose last column is CODE
+#define K16_KEY(G, CODE)                                                                          \
+    mkey = imax3(mkey, (int)(((G) & 0xffff0000u) | (uint32_t)(CODE)), (int)mad_u((G), k65536, (uint32_t)(CODE)));
+
+    for (int i = 0; i < tlen; ++i) {
+        if ((i & 15) == 0) tword = ldg32(tw + (i >> 4));
+        const int ti = (int)((tword >> ((i & 15) * 2)) & 3u);
+        beg = beg > i - w ? beg : i - w;
+        end = end < i + w + 1 ? end : i + w + 1;
+        end = end < qlen ? end : qlen;
+        int h1 = 0;
+        if (beg == 0) { h1 = h0 - (P.o_del + P.e_del * (i + 1)); h1 = h1 > 0 ? h1 : 0; }
+        int f = 0;
+        int mkey = 0;                     // (row max << 16) | column code
+        int jt = beg;                     // first column of the scalar tail
+        int j = beg & ~3;
+        if (j + 4 <= end) {
+            const uint32_t trep = (uint32_t)ti * 0x5555u;
+            uint32_t fc = 0;                                  // high half: F entering the next column
+            uint32_t carry = (uint32_t)h1 << 16;              // high half: H(i, j - 1)
+            uint32_t sa = eh_sa + 4u * (uint32_t)j;
+            uint32_t qa = qp_sa + ((uint32_t)j >> 3) * qp_stride;
+            uint4 g0 = lds128(sa);
+            if (j < beg) {
+                // the <= 3 columns between the group boundary and beg are dead for good (beg never
+                // decreases): swept as zeros they produce zeros, the state the reference enters beg with
+                const int d = beg - j;
+                const uint32_t m0 = d >= 2 ? 0u : 0xffff0000u;
+                const uint32_t m1 = d == 3 ? 0xffff0000u : 0xffffffffu;
+                g0.x &= m0; g0.z &= m0; g0.y &= m1; g0.w &= m1;
+            }
+            uint32_t hn0, hn1, hn2, hn3;
+            if (j & 4) {
+                // leading half block: pairs 2, 3 of its query halfword
+                const uint32_t x = lds16(qa) ^ trep;
+                const uint32_t s2 = K16_SCORE(x, 2), s3 = K16_SCORE(x, 3);
+                K16_GROUP(g0, s2, s3, sa, hn0, hn1)
+                const uint32_t g = max2(hn0, hn1);
+                K16_KEY(g, j + 3)
+                j += 4; sa += 16; qa += qp_stride;
+                g0 = lds128(sa);
+            }
+            uint32_t cs0 = 0, cs1 = 0;
+            bool fresh = true;
+            if (j + 8 <= end) {
+                // full blocks of 8 columns, software-pipelined: block b+1 is loaded while b computes
+                uint4 c0 = g0, c1 = lds128(sa + 16);
+                const uint32_t x = lds16(qa) ^ trep;
+                uint32_t s0 = K16_SCORE(x, 0), s1 = K16_SCORE(x, 1), s2 = K16_SCORE(x, 2), s3 = K16_SCORE(x, 3);
+                uint32_t xn = lds16(qa + qp_stride) ^ trep;
+                int code = j + 7;
+                do {
+                    const uint4 n0 = lds128(sa + 32), n1 = lds128(sa + 48);
+                    const uint32_t t0 = K16_SCORE(xn, 0), t1 = K16_SCORE(xn, 1), t2 = K16_SCORE(xn, 2), t3 = K16_SCORE(xn, 3);
+                    const uint32_t xn2 = lds16(qa + 2 * qp_stride) ^ trep;
+                    K16_GROUP(c0, s0, s1, sa, hn0, hn1)
+                    K16_GROUP(c1, s2, s3, sa + 16, hn2, hn3)
+                    const uint32_t g = max2(max3(hn0, hn1, hn2), hn3);
+                    K16_KEY(g, code)
+                    j += 8; sa += 32; qa += qp_stride; code += 8;
+                    c0 = n0; c1 = n1; s0 = t0; s1 = t1; s2 = t2; s3 = t3; xn = xn2;
+                } while (j + 8 <= end);
+                g0 = c0; cs0 = s0; cs1 = s1; fresh = false;
+            }
+            if (j + 4 <= end) {
+                // trailing half block: pairs 0, 1 of its query halfword
+                if (fresh) {
+                    const uint32_t x = lds16(qa) ^ trep;
+                    cs0 = K16_SCORE(x, 0); cs1 = K16_SCORE(x, 1);
+                }
+                K16_GROUP(g0, cs0, cs1, sa, hn0, hn1)
+                const uint32_t g = max2(hn0, hn1);
+                K16_KEY(g, j + 3)
+                j += 4;
+            }
+            jt = j;
+            h1 = (int)(carry >> 16);
+            f = (int)(fc >> 16);
+        } else {
+            j = beg;
+        }
+        // scalar tail: the <= 3 columns right of the last full group (or a window narrower than a group)
+        for (; j < end; ++j) {
+            const uint32_t ha = K16_HADDR(j);
+            const int hd = (int)lds16(ha), e = (int)lds16(ha + 8);
+            const int qj = (int)((lds16(qp_sa + ((uint32_t)j >> 3) * qp_stride) >> ((j & 7) * 2)) & 3u);
+            const int sc = qj == ti ? P.match : P.mismatch_neg;
+            int M = hd ? hd + sc : 0;
+            M = M > 0 ? M : 0;                               // a negative M is equivalent to 0 in every use
+            int h = M > e ? M : e;
+            h = h > f ? h : f;
+            sts16(ha, (uint32_t)h1);
+            h1 = h;
+            int t = M - P.oe_del; t = t > 0 ? t : 0;
+            int en = e - P.e_del; en = en > t ? en : t;
+            sts16(ha + 8, (uint32_t)en);
+            t = M - P.oe_ins; t = t > 0 ? t : 0;
+            f -= P.e_ins; f = f > t ? f : t;
+            const int key = (h << 16) | j;
+            mkey = mkey > key ? mkey : key;
+        }
+        if (end > beg) my_cells += end - beg;
+        // eh[end] = {h1, 0}  (bandedSWA.cpp:213)
+        {
+            const uint32_t ha = K16_HADDR(end);
+            sts16(ha, (uint32_t)h1);
+            sts16(ha + 8, 0u);
+        }
+        const int jfin = end > beg ? end : beg;
+        if (jfin == qlen) {                                   // bandedSWA.cpp:214-217
+            if (!(st.gscore > h1)) st.max_ie = i;
+            st.gscore = st.gscore > h1 ? st.gscore : h1;
+        }
+        const int m = mkey >> 16;
+        int mj = mkey & 0xffff;
+        if (mj < jt && (m > st.max || st.max - m > P.zdrop)) {
+            // the key names a block: the last column of it whose H equals m is the reference's mj
+            // (H(i, c) sits in hs[c + 1]); the epilogue reads mj only under the condition above
+            const int lo = mj - 7 > 0 ? mj - 7 : 0;
+            while (mj > lo && (int)lds16(K16_HADDR(mj + 1)) != m) --mj;
+        }
+        if (bsw_row_update(P, st, i, m, mj)) break;
+        // next row's window (bandedSWA.cpp:230-233)
+        {
+            int jj = beg;
+            while (jj < end) {
+                const uint32_t ha = K16_HADDR(jj);
+                if (lds16(ha) | lds16(ha + 8)) break;
+                ++jj;
+            }
+            beg = jj;
+            jj = end;
+            while (jj >= beg) {
+                const uint32_t ha = K16_HADDR(jj);
+                if (lds16(ha) | lds16(ha + 8)) break;
+                --jj;
+            }
+            end = jj + 2 < qlen ? jj + 2 : qlen;
+        }
+    }
+#undef K16_HADDR
+#undef K16_SCORE
+#undef K16_WORD
+#undef K16_GROUP
+#undef K16_KEY
+}
+
+// shared memory of one block: score table + rows + query plane
+BSW_HD size_t smem_bytes(int block, int qstride)
+{
+    return (size_t)TAB_BYTES + (size_t)qstride * block * 4 + (size_t)((qstride >> 3) + 2) * block * 2;
+}
+
+} // namespace k16
+
+// ------------------------------------------------------------------------------------------------
+// Kernel: one pair per thread; same arguments as bsw_short_kernel<BLOCK, false>.
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+template <int BLOCK, bool SAMEGAP>
+__global__ void __launch_bounds__(BLOCK)
+bsw_short16_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ perm,
+                   const uint32_t* __restrict__ qseq, const uint32_t* __restrict__ tseq,
+                   int4* __restrict__ res, int first, int count, int qstride,
+                   const __grid_constant__ KParams P, unsigned long long* __restrict__ cell_counter)
+{
+    extern __shared__ __align__(16) uint32_t k16_smem[];
+    const int tid = threadIdx.x;
+    for (int k = tid; k < k16::TAB_WORDS; k += BLOCK) k16_smem[k] = k16::table_word(P, k >> 5);
+    __syncthreads();
+    const int local = blockIdx.x * BLOCK + tid;
+    long long my_cells = 0;
+    if (local < count) {
+        const int4 md = meta[first + local];
+        if (!(md.w & BSW_META_NFLAG)) {
+            const uint32_t smem_sa = (uint32_t)__cvta_generic_to_shared(k16_smem);
+            const uint32_t eh_sa = smem_sa + k16::TAB_BYTES + (uint32_t)(tid * qstride) * 4u;
+            const uint32_t qp_sa = smem_sa + k16::TAB_BYTES + (uint32_t)(BLOCK * qstride) * 4u + (uint32_t)tid * 2u;
+            const uint32_t tab_sa = smem_sa + (uint32_t)(tid & 31) * 4u;
+            PairState st;
+            k16::pair_sweep<SAMEGAP>(P, md, qseq + (uint32_t)md.x, tseq + (uint32_t)md.y, eh_sa, qp_sa, BLOCK * 2u,
+                                     tab_sa, st, my_cells);
+            res[perm[first + local]] = bsw_pack_result(st);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) my_cells += __shfl_down_sync(0xffffffffu, my_cells, off);
+    if ((tid & 31) == 0 && my_cells) atomicAdd(cell_counter, (unsigned long long)my_cells);
+}
+#endif
+
+} // namespace bsw

@@ -15,6 +15,9 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// functions shared with the host-side emulation of the row sweeps (tests/k16_emu.cu)
+#define BSW_HD __host__ __device__ __forceinline__
+
 namespace bsw {
 
 struct KParams {
@@ -38,7 +41,7 @@ struct KParams {
 #define BSW_META_NFLAG (1 << 30)
 
 // band clamp of bandedSWA.cpp:160-168, same double arithmetic
-__device__ __forceinline__ int bsw_clamp_band(const KParams& P, int qlen)
+BSW_HD int bsw_clamp_band(const KParams& P, int qlen)
 {
     int w = P.w;
     int max_ins = (int)((double)(qlen * P.mx + P.end_bonus - P.o_ins) / P.e_ins + 1.);
@@ -93,7 +96,7 @@ struct PairState {
 
 // Row epilogue: global max / max_off / z-drop (bandedSWA.cpp:218-228, :323-336).
 // Returns true when the row loop must stop.
-__device__ __forceinline__ bool bsw_row_update(const KParams& P, PairState& st, int i, int m, int mj)
+BSW_HD bool bsw_row_update(const KParams& P, PairState& st, int i, int m, int mj)
 {
     if (m == 0) return true;
     if (m > st.max) {
@@ -114,7 +117,7 @@ __device__ __forceinline__ bool bsw_row_update(const KParams& P, PairState& st, 
     return false;
 }
 
-__device__ __forceinline__ int4 bsw_pack_result(const PairState& st)
+BSW_HD int4 bsw_pack_result(const PairState& st)
 {
     // 8 x int16: score, qle, tle, gtle, gscore, max_off, 0, 0
     int4 r;

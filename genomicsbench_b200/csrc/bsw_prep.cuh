@@ -9,13 +9,14 @@
 //   bsw_bucket_*     counting sort of the chunk by (len2, h0, len1) -> processing order perm[];
 //                    lists the pairs too long for the short kernel
 //   bsw_pack_pairs   2-bit pack query / reference bytes (16 bases per word) in processing order,
-//                    flag and list the pairs with N
+//                    flag and list the pairs with N (and those outside the packed kernel's domain)
 //   bsw_writeback    unpack the 16-byte results into the caller's SeqPair records (input order)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/bsw.h"
 #include "bsw_kernels.cuh"
+#include "bsw_kernel16.cuh"
 
 namespace bsw {
 
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256)
 bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm, int n_sorted,
                const uint8_t* __restrict__ qraw, const uint8_t* __restrict__ rraw, int4* __restrict__ meta,
                uint32_t* __restrict__ qpk, uint32_t* __restrict__ tpk,
-               uint32_t* __restrict__ nlist, ChunkInfo* __restrict__ info)
+               uint32_t* __restrict__ nlist, ChunkInfo* __restrict__ info, int packed16_match)
 {
     __shared__ uint32_t s_pre[8][2][33];
     __shared__ uint32_t s_bad[8][32];
@@ -204,7 +205,10 @@ bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm,
         }
         __syncwarp();
         if (s < n_sorted) {
-            const bool has_n = s_bad[wib][lane] != 0;
+            // pairs for the 32-bit byte kernel: those that contain N and, when the packed 16-bit kernel
+            // runs the rest (packed16_match = its match score), those outside its score domain
+            const bool has_n = s_bad[wib][lane] != 0 ||
+                               (packed16_match > 0 && !k16::eligible(packed16_match, len2, d.w & 0xffff));
             meta[s] = make_int4((int)(bq + pq - nq), (int)(bt + pt - nt), d.z, d.w | (has_n ? BSW_META_NFLAG : 0));
             if (has_n) { nlist[atomicAdd(&info->n_nlist, 1u)] = (uint32_t)pi; atomicMax(&info->qmax_n, len2); }
         }

@@ -52,6 +52,11 @@ enum {
  * scalarBandedSWAWrapper uses SCALAR. */
 enum { BSW_ZDROP_VECTOR = 0, BSW_ZDROP_SCALAR = 1 };
 
+/* Thread-per-pair kernel of the short pairs.  PACKED16: two DP columns per DPX .S16x2
+ * instruction (pairs with N or with (h0 + len2*match)*(1+match) > 32767 still take the 32-bit
+ * kernel); WIDE32: the 32-bit kernel for every short pair (A/B measurements). */
+enum { BSW_SHORT_PACKED16 = 0, BSW_SHORT_WIDE32 = 1 };
+
 /* ---- a2: constructor arguments of BandedPairWiseSW (bandedSWA.cpp:51-100) -- */
 typedef struct bsw_params {
     int32_t o_del, e_del, o_ins, e_ins;   /* gap open / extend, > 0 extend           */
@@ -67,7 +72,8 @@ typedef struct bsw_params {
     int32_t long_min_qlen;                /* queries of at least this length use the warp-per-pair
                                              kernel; 0 => default (825, the short kernel's shared-
                                              memory limit + 1); 1 routes every pair to it          */
-    int32_t reserved[7];
+    int32_t short_variant;                /* BSW_SHORT_PACKED16 (default) | BSW_SHORT_WIDE32               */
+    int32_t reserved[6];
 } bsw_params;
 
 /* Per-call statistics (replaces the rdtsc counters behind getTicks(),

@@ -1,5 +1,5 @@
 """Quick GPU sanity run: parity of every named config (sampled) against the oracle, the measured
-integer peak, and kernel-only timing.  Usage: python scripts/gpu_check.py [n_parity] [n_timing]"""
+integer peak, and kernel-only timing.  Usage: python scripts/gpu_check.py [n_parity] [n_timing] [short_variant]"""
 import sys, time, json
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -9,12 +9,13 @@ from oracle.pyoracle import Oracle, make_params
 
 n_par = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 n_tim = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
+variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # 0 = packed 16-bit short kernel, 1 = 32-bit
 orc = Oracle()
 P = make_params()
-eng = gb.Engine()
+eng = gb.Engine(short_variant=variant)
 peak = eng.measure_int_peak()
 print("int peak lane-ops/s: %.4g" % peak, flush=True)
-out = {"int_peak": peak, "configs": {}}
+out = {"int_peak": peak, "short_variant": variant, "configs": {}}
 for name in ["small", "short8", "long16", "large", "sweep"]:
     cfg = gb.gen_named_config(name)
     pairs, r, q = gb.gen_pairs(cfg, 0, min(n_par, cfg.n_pairs))
@@ -56,4 +57,4 @@ for name in ["small", "short8", "long16", "large", "sweep"]:
     out["configs"][name] = rec
     print(name, json.dumps(rec), flush=True)
 Path("gpurun_out").mkdir(exist_ok=True)
-Path("gpurun_out/gpu_check.json").write_text(json.dumps(out, indent=1))
+Path(f"gpurun_out/gpu_check_v{variant}.json").write_text(json.dumps(out, indent=1))

@@ -27,6 +27,32 @@ def test_cuda_matches_reference_golden(lib, case):
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_wide32_kernel_matches_reference_golden(lib, case):
+    """Every golden case again with the 32-bit thread-per-pair kernel for all short pairs
+    (short_variant = BSW_SHORT_WIDE32; the default is the packed 16-bit kernel)."""
+    pairs, ref, qer, w, params, expect, _ = load_golden(case)
+    with lib.Engine(**engine_kwargs(params, short_variant=1)) as eng:
+        eng.extend(pairs, ref, qer, w)
+    assert np.array_equal(results_matrix(pairs), expect)
+
+
+def test_packed16_domain_routing(lib, oracle):
+    """Pairs whose scores leave the packed kernel's 16-bit domain ((h0 + len2*match)*(1+match) > 32767)
+    must take the 32-bit kernel inside the same batch: high h0 next to ordinary pairs."""
+    import genomicsbench_b200 as gb
+    cfg = gb.gen_named_config("large")
+    pairs, ref, qer = gb.gen_pairs(cfg, 4242, 6000)
+    rng = np.random.default_rng(7)
+    hi = rng.random(len(pairs)) < 0.3
+    pairs["h0"][hi] = rng.integers(16000, 32000, hi.sum())        # (h0 + len2) * 2 > 32767, still h0 + len2 <= 32767
+    want = pairs.copy()
+    oracle.batch(make_params(), want, ref, qer, 100)
+    with lib.Engine() as eng:
+        eng.extend(pairs, ref, qer, 100)
+    assert np.array_equal(results_matrix(pairs), results_matrix(want))
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_long_kernel_matches_reference_golden(lib, case):
     """Every golden case again with all pairs routed to the warp-per-pair kernel."""
     pairs, ref, qer, w, params, expect, _ = load_golden(case)
