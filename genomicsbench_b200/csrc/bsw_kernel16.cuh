@@ -209,6 +209,18 @@ BSW_HD uint32_t madhi_u(uint32_t a, uint32_t b, uint32_t c)
 #endif
 }
 
+// index of the highest set bit (x != 0)
+BSW_HD int hibit(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)x);
+#else
+    int r = 0;
+    while (x >>= 1) ++r;
+    return r;
+#endif
+}
+
 BSW_HD uint32_t pack2(int hi, int lo) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu); }
 
 // score-table word of pattern idx = x1 << 2 | x0 (x = query ^ target of the two columns, 0 = match)
@@ -352,23 +364,34 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
             uint32_t cs0 = 0, cs1 = 0;
             bool fresh = true;
             if (j + 8 <= end) {
-                // full blocks of 8 columns, software-pipelined: block b+1 is loaded while b computes
-                uint4 c0 = g0, c1 = lds128(sa + 16);
+                // full blocks of 8 columns, software-pipelined and unrolled twice: while one block
+                // computes from one register set, the next block's row words, query halfword and score
+                // words are loaded into the other set (the shared-memory accesses are volatile, so
+                // ptxas keeps the loads ahead of the block's stores instead of sinking them to their use)
+                uint4 c0 = g0, c1 = lds128(sa + 16), n0, n1;
                 const uint32_t x = lds16(qa) ^ trep;
                 uint32_t s0 = K16_SCORE(x, 0), s1 = K16_SCORE(x, 1), s2 = K16_SCORE(x, 2), s3 = K16_SCORE(x, 3);
-                uint32_t xn = lds16(qa + qp_stride) ^ trep;
+                uint32_t t0, t1, t2, t3;
+                uint32_t xa = lds16(qa + qp_stride) ^ trep, xb;
                 int code = j + 7;
-                do {
-                    const uint4 n0 = lds128(sa + 32), n1 = lds128(sa + 48);
-                    const uint32_t t0 = K16_SCORE(xn, 0), t1 = K16_SCORE(xn, 1), t2 = K16_SCORE(xn, 2), t3 = K16_SCORE(xn, 3);
-                    const uint32_t xn2 = lds16(qa + 2 * qp_stride) ^ trep;
-                    K16_GROUP(c0, s0, s1, sa, hn0, hn1)
-                    K16_GROUP(c1, s2, s3, sa + 16, hn2, hn3)
-                    const uint32_t g = max2(max3(hn0, hn1, hn2), hn3);
-                    K16_KEY(g, code)
-                    j += 8; sa += 32; qa += qp_stride; code += 8;
-                    c0 = n0; c1 = n1; s0 = t0; s1 = t1; s2 = t2; s3 = t3; xn = xn2;
-                } while (j + 8 <= end);
+#define K16_BLOCK(C0, C1, S0, S1, S2, S3, XN, N0, N1, T0, T1, T2, T3, XN2)                              \
+                {                                                                                     \
+                    N0 = lds128(sa + 32); N1 = lds128(sa + 48);                                       \
+                    T0 = K16_SCORE(XN, 0); T1 = K16_SCORE(XN, 1); T2 = K16_SCORE(XN, 2); T3 = K16_SCORE(XN, 3); \
+                    XN2 = lds16(qa + 2 * qp_stride) ^ trep;                                           \
+                    K16_GROUP(C0, S0, S1, sa, hn0, hn1)                                               \
+                    K16_GROUP(C1, S2, S3, sa + 16, hn2, hn3)                                          \
+                    const uint32_t g_ = max2(max3(hn0, hn1, hn2), hn3);                               \
+                    K16_KEY(g_, code)                                                                 \
+                    j += 8; sa += 32; qa += qp_stride; code += 8;                                     \
+                }
+                for (;;) {
+                    K16_BLOCK(c0, c1, s0, s1, s2, s3, xa, n0, n1, t0, t1, t2, t3, xb)
+                    if (j + 8 > end) { c0 = n0; s0 = t0; s1 = t1; break; }
+                    K16_BLOCK(n0, n1, t0, t1, t2, t3, xb, c0, c1, s0, s1, s2, s3, xa)
+                    if (j + 8 > end) break;
+                }
+#undef K16_BLOCK
                 g0 = c0; cs0 = s0; cs1 = s1; fresh = false;
             }
             if (j + 4 <= end) {
@@ -423,10 +446,21 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
         const int m = mkey >> 16;
         int mj = mkey & 0xffff;
         if (mj < jt && (m > st.max || st.max - m > P.zdrop)) {
-            // the key names a block: the last column of it whose H equals m is the reference's mj
-            // (H(i, c) sits in hs[c + 1]); the epilogue reads mj only under the condition above
-            const int lo = mj - 7 > 0 ? mj - 7 : 0;
-            while (mj > lo && (int)lds16(K16_HADDR(mj + 1)) != m) --mj;
+            // the key names a block (its last column, mj + 1 a multiple of 4): the reference's mj is
+            // the last column of [mj - 7, mj] whose H equals m (bandedSWA.cpp:202-203).  H(i, c) sits
+            // in hs[c + 1]; the eight halves are flagged in parallel (1 where hs >= m: inside this
+            // row's sweep no H exceeds m, and whatever lies left of the sweep is lower than the
+            // block's own maximum column, so a stale hit there never wins) and the highest flag taken.
+            // The epilogue reads mj only under the condition above.
+            const uint32_t ga = eh_sa + (((uint32_t)(mj + 1) >> 2) << 4);
+            const uint32_t a0 = lds32(ga - 32), a1 = lds32(ga - 28), b0 = lds32(ga - 16), b1 = lds32(ga - 12), c0 = lds32(ga);
+            const uint32_t dm = pack2(1 - m, 1 - m), one2 = 0x00010001u;
+            const uint32_t fa0 = addmin_relu(a0, dm, one2), fa1 = addmin_relu(a1, dm, one2);
+            const uint32_t fb0 = addmin_relu(b0, dm, one2), fb1 = addmin_relu(b1, dm, one2), fc0 = addmin_relu(c0, dm, one2);
+            // bit k of the mask = column mj - 7 + k
+            const uint32_t xw = mad_u(fc0, 128u, mad_u(fb1, 32u, mad_u(fb0, 8u, fa1 * 2u)));
+            const uint32_t mask = (xw & 0xaau) | ((xw >> 15) & 0x54u) | (fa0 >> 16);
+            mj = mj - 7 + hibit(mask);
         }
         if (bsw_row_update(P, st, i, m, mj)) break;
         // next row's window (bandedSWA.cpp:230-233)
