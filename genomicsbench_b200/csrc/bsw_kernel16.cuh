@@ -221,6 +221,46 @@ BSW_HD int hibit(uint32_t x)
 #endif
 }
 
+// a << s with s in 0..63: 0 from 32 on (PTX shl clamps the amount; C++ << does not)
+BSW_HD uint32_t shl_sat(uint32_t a, int s)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(s));
+    return r;
+#else
+    return s >= 32 ? 0u : a << s;
+#endif
+}
+BSW_HD int imax0(int a) { return a > 0 ? a : 0; }
+// per-halfword unsigned minimum
+BSW_HD uint32_t minu2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vminu2(a, b);
+#else
+    const uint32_t lo = std::min(a & 0xffffu, b & 0xffffu), hi = std::min(a >> 16, b >> 16);
+    return lo | (hi << 16);
+#endif
+}
+// bits of b where the mask is set, bits of a elsewhere (one LOP3)
+BSW_HD uint32_t bitsel(uint32_t a, uint32_t b, uint32_t keep_b_mask_inv)
+{
+    // keep_b_mask_inv = 1 bits: keep a (the old content); 0 bits: take b (the new content)
+    return (a & keep_b_mask_inv) | (b & ~keep_b_mask_inv);
+}
+// index of the lowest set bit (x != 0)
+BSW_HD int lobit(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    int r = 0;
+    while (!(x & 1u)) { x >>= 1; ++r; }
+    return r;
+#endif
+}
+
 BSW_HD uint32_t pack2(int hi, int lo) { return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu); }
 
 // score-table word of pattern idx = x1 << 2 | x0 (x = query ^ target of the two columns, 0 = match)
@@ -243,6 +283,23 @@ BSW_HD bool eligible(int match, int qlen, int h0)
 //   qp_sa     this thread's slot of the query plane: halfword k (columns 8k .. 8k+7, 2 bits per
 //             base) at qp_sa + k * qp_stride
 //   tab_sa    score table + 4 * lane
+//
+// A row's window [beg, end) is swept in aligned blocks of 8 columns, from the block holding column
+// beg to the block holding column end (which receives eh[end] = {H(i, end-1), 0},
+// bandedSWA.cpp:213).
+//   Left of beg: the columns between the block boundary and beg are dead for good (beg never
+//   decreases) and hold zeros -- a column leaves the window either because its (h | e) is zero
+//   (bandedSWA.cpp:230) or because the band cuts it (:175), and then the row prologue zeroes it.
+//   Swept as zeros they produce zeros, the state the reference enters beg with when beg > 0, so
+//   the first block needs no mask.
+//   Right of end: the last block runs the same recurrence under three halfword masks:
+//     in    columns >= end enter as h = e = 0 (their results are discarded)
+//     key   the row maximum only looks at columns < end (F leaks into the discarded ones)
+//     store columns <= end are written, columns > end keep their old content (the reference leaves
+//           them untouched, and later rows may read them: SURVEY.md Appendix B, stale eh[])
+// The first and the last block also produce, from the values they store, an 8-bit map of the
+// columns whose (h | e) is non-zero; the next row's window (bandedSWA.cpp:230-233) is read off
+// these two maps and only falls back to scanning shared memory when a map is empty.
 // ------------------------------------------------------------------------------------------------
 template <bool SAMEGAP>
 BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restrict__ qw,
@@ -251,10 +308,11 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
 {
     const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w & 0xffff;
 
-    // ---- first row (bandedSWA.cpp:155-157) and the query plane
+    // ---- first row (bandedSWA.cpp:155-157) and the query plane; the row is initialised up to the
+    // end of the block that holds column qlen
     {
         int hv = h0;
-        for (int j0 = 0; j0 <= qlen; j0 += 4) {
+        for (int j0 = 0; j0 <= (qlen | 7); j0 += 4) {
             uint32_t v[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -301,16 +359,16 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
     {                                                                                             \
         const uint32_t cap_ = mad_u((HW), capmul, 0u);                                            \
         const uint32_t M_ = addmin_relu((HW), (SW), cap_);                                        \
-        const uint32_t U_ = addmax_relu(M_, noe_del2, zero);                                        \
+        const uint32_t U_ = addmax_relu(M_, noe_del2, zero);                                      \
         EN = addmax((EW), ne_del2, U_);                                                           \
-        const uint32_t A_ = SAMEGAP ? U_ : addmax_relu(M_, noe_ins2, zero);                         \
+        const uint32_t A_ = SAMEGAP ? U_ : addmax_relu(M_, noe_ins2, zero);                       \
         const uint32_t ME_ = max2(M_, (EW));                                                      \
         const uint32_t f1_ = addmax(fc, negg_hi, mad_u(A_, k65536, 0u));                          \
         const uint32_t Fc_ = prmt(fc, f1_, 0x7632);                                               \
         fc = addmax(f1_, negg_hi, A_);                                                            \
         HN = max2(ME_, Fc_);                                                                      \
     }
-    // one 4-column group: CUR = its four words, SA / SB = scores of its two pairs, ADDR = its address
+    // one interior 4-column group: CUR = its four words, SA / SB = scores of its two pairs
 #define K16_GROUP(CUR, SA, SB, ADDR, HN0, HN1)                                                    \
     {                                                                                             \
         uint32_t en0_, en1_;                                                                      \
@@ -322,118 +380,133 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
     // row-maximum key of a block whose packed maximum is G and whose last column is CODE
 #define K16_KEY(G, CODE)                                                                          \
     mkey = imax3(mkey, (int)(((G) & 0xffff0000u) | (uint32_t)(CODE)), (int)mad_u((G), k65536, (uint32_t)(CODE)));
+    // the block at sa computes from (c0, c1, s0..s3) while the next block's row words, score words
+    // and the query halfword after that are loaded into (n0, n1, t0..t3, xb); xa = the next block's
+    // query halfword ^ target.  (The shared-memory accesses are volatile, so ptxas keeps the loads
+    // ahead of the block's stores instead of sinking them to their use.)
+#define K16_PREFETCH(XA, N0, N1, T0, T1, T2, T3, XB)                                              \
+    N0 = lds128(sa + 32); N1 = lds128(sa + 48);                                                   \
+    T0 = K16_SCORE(XA, 0); T1 = K16_SCORE(XA, 1); T2 = K16_SCORE(XA, 2); T3 = K16_SCORE(XA, 3);   \
+    XB = lds16(qa + 2 * qp_stride) ^ trep;
+#define K16_BLOCK(C0, C1, S0, S1, S2, S3, XA, N0, N1, T0, T1, T2, T3, XB)                         \
+    {                                                                                             \
+        uint32_t hn0, hn1, hn2, hn3;                                                              \
+        K16_PREFETCH(XA, N0, N1, T0, T1, T2, T3, XB)                                              \
+        K16_GROUP(C0, S0, S1, sa, hn0, hn1)                                                       \
+        K16_GROUP(C1, S2, S3, sa + 16, hn2, hn3)                                                  \
+        const uint32_t g_ = max2(max3(hn0, hn1, hn2), hn3);                                       \
+        K16_KEY(g_, code)                                                                         \
+        sa += 32; qa += qp_stride; code += 8;                                                     \
+    }
+    // 8-bit map of the non-zero halfwords of four words (bit c = column c of the block)
+#define K16_ZMAP(Z0, Z1, Z2, Z3, ZMAP)                                                            \
+    {                                                                                             \
+        const uint32_t f0_ = minu2((Z0), 0x00010001u), f1_ = minu2((Z1), 0x00010001u);            \
+        const uint32_t f2_ = minu2((Z2), 0x00010001u), f3_ = minu2((Z3), 0x00010001u);            \
+        const uint32_t zb_ = mad_u(f3_, 64u, mad_u(f2_, 16u, mad_u(f1_, 4u, f0_)));               \
+        ZMAP = (zb_ | (zb_ >> 15)) & 0xffu;                                                       \
+    }
+    // first block of a window that spans several blocks: the bare recurrence + the non-zero map
+#define K16_FIRST(ZMAP)                                                                           \
+    {                                                                                             \
+        uint4 n0, n1;                                                                             \
+        uint32_t t0, t1, t2, t3, xb;                                                              \
+        K16_PREFETCH(xa, n0, n1, t0, t1, t2, t3, xb)                                              \
+        uint32_t hn0, hn1, hn2, hn3, en0, en1, en2, en3;                                          \
+        K16_WORD(c0.x, c0.z, s0, hn0, en0)                                                        \
+        K16_WORD(c0.y, c0.w, s1, hn1, en1)                                                        \
+        const uint32_t hw0 = prmt(carry, hn0, 0x5432), hw1 = prmt(hn0, hn1, 0x5432);              \
+        sts128(sa, hw0, hw1, en0, en1);                                                           \
+        K16_WORD(c1.x, c1.z, s2, hn2, en2)                                                        \
+        K16_WORD(c1.y, c1.w, s3, hn3, en3)                                                        \
+        const uint32_t hw2 = prmt(hn1, hn2, 0x5432), hw3 = prmt(hn2, hn3, 0x5432);                \
+        sts128(sa + 16, hw2, hw3, en2, en3);                                                      \
+        carry = hn3;                                                                              \
+        const uint32_t g_ = max2(max3(hn0, hn1, hn2), hn3);                                       \
+        K16_KEY(g_, code)                                                                         \
+        K16_ZMAP(hw0 | en0, hw1 | en1, hw2 | en2, hw3 | en3, ZMAP)                                \
+        sa += 32; qa += qp_stride; code += 8;                                                     \
+        c0 = n0; c1 = n1; s0 = t0; s1 = t1; s2 = t2; s3 = t3; xa = xb;                            \
+    }
+    // halfword mask of word K of a block: the columns >= D16 / 16 (D16 = 16 x a column count in 0..8)
+#define K16_GE(D16, K) shl_sat(0xffffffffu, imax0((D16) - 32 * (K)))
+    // last block: LIVE16 = 16 x (columns of the block left of end, 0..7).  ZMAP receives the non-zero
+    // map of the stored columns (<= end), HEND the h half stored at column end (H(i, end - 1)).
+#define K16_EDGE(LIVE16, ZMAP, HEND)                                                              \
+    {                                                                                             \
+        const int l16_ = (LIVE16);                                                                \
+        const uint32_t rk0 = K16_GE(l16_, 0), rk1 = K16_GE(l16_, 1), rk2 = K16_GE(l16_, 2), rk3 = K16_GE(l16_, 3);   \
+        const uint32_t sk0 = K16_GE(l16_ + 16, 0), sk1 = K16_GE(l16_ + 16, 1), sk2 = K16_GE(l16_ + 16, 2), sk3 = K16_GE(l16_ + 16, 3); \
+        uint32_t hn0, hn1, hn2, hn3, en0, en1, en2, en3;                                          \
+        K16_WORD(c0.x & ~rk0, c0.z & ~rk0, s0, hn0, en0)                                          \
+        K16_WORD(c0.y & ~rk1, c0.w & ~rk1, s1, hn1, en1)                                          \
+        K16_WORD(c1.x & ~rk2, c1.z & ~rk2, s2, hn2, en2)                                          \
+        K16_WORD(c1.y & ~rk3, c1.w & ~rk3, s3, hn3, en3)                                          \
+        const uint32_t hw0 = prmt(carry, hn0, 0x5432), hw1 = prmt(hn0, hn1, 0x5432);              \
+        const uint32_t hw2 = prmt(hn1, hn2, 0x5432), hw3 = prmt(hn2, hn3, 0x5432);                \
+        sts128(sa, bitsel(c0.x, hw0, sk0), bitsel(c0.y, hw1, sk1), bitsel(c0.z, en0, sk0), bitsel(c0.w, en1, sk1));       \
+        sts128(sa + 16, bitsel(c1.x, hw2, sk2), bitsel(c1.y, hw3, sk3), bitsel(c1.z, en2, sk2), bitsel(c1.w, en3, sk3));  \
+        const uint32_t g_ = max2(max3(hn0 & ~rk0, hn1 & ~rk1, hn2 & ~rk2), hn3 & ~rk3);          \
+        K16_KEY(g_, code)                                                                         \
+        K16_ZMAP((hw0 | en0) & ~sk0, (hw1 | en1) & ~sk1, (hw2 | en2) & ~sk2, (hw3 | en3) & ~sk3, ZMAP)  \
+        {                                                                                         \
+            const uint32_t ws_ = (l16_ & 64) ? ((l16_ & 32) ? hw3 : hw2) : ((l16_ & 32) ? hw1 : hw0);   \
+            HEND = (int)((l16_ & 16) ? ws_ >> 16 : ws_ & 0xffffu);                                \
+        }                                                                                         \
+    }
 
     for (int i = 0; i < tlen; ++i) {
         if ((i & 15) == 0) tword = ldg32(tw + (i >> 4));
         const int ti = (int)((tword >> ((i & 15) * 2)) & 3u);
-        beg = beg > i - w ? beg : i - w;
+        if (beg < i - w) {
+            // the band cuts column beg (at most one column per row: beg >= i - 1 - w): dead for good,
+            // zeroed so that the first block can sweep it unmasked
+            const uint32_t ha = K16_HADDR(beg);
+            sts16(ha, 0u);
+            sts16(ha + 8, 0u);
+            beg = i - w;
+        }
         end = end < i + w + 1 ? end : i + w + 1;
         end = end < qlen ? end : qlen;
         int h1 = 0;
         if (beg == 0) { h1 = h0 - (P.o_del + P.e_del * (i + 1)); h1 = h1 > 0 ? h1 : 0; }
-        int f = 0;
-        int mkey = 0;                     // (row max << 16) | column code
-        int jt = beg;                     // first column of the scalar tail
-        int j = beg & ~3;
-        if (j + 4 <= end) {
+        int mkey = 0;                     // (row max << 16) | last column of the block that holds it
+        uint32_t zf = 0, zl = 0;          // non-zero maps of the first / last block
+        const int fb = beg & ~7, lb = end & ~7;
+        if (end > beg) {
             const uint32_t trep = (uint32_t)ti * 0x5555u;
             uint32_t fc = 0;                                  // high half: F entering the next column
             uint32_t carry = (uint32_t)h1 << 16;              // high half: H(i, j - 1)
-            uint32_t sa = eh_sa + 4u * (uint32_t)j;
-            uint32_t qa = qp_sa + ((uint32_t)j >> 3) * qp_stride;
-            uint4 g0 = lds128(sa);
-            if (j < beg) {
-                // the <= 3 columns between the group boundary and beg are dead for good (beg never
-                // decreases): swept as zeros they produce zeros, the state the reference enters beg with
-                const int d = beg - j;
-                const uint32_t m0 = d >= 2 ? 0u : 0xffff0000u;
-                const uint32_t m1 = d == 3 ? 0xffff0000u : 0xffffffffu;
-                g0.x &= m0; g0.z &= m0; g0.y &= m1; g0.w &= m1;
-            }
-            uint32_t hn0, hn1, hn2, hn3;
-            if (j & 4) {
-                // leading half block: pairs 2, 3 of its query halfword
+            uint32_t sa = eh_sa + 4u * (uint32_t)fb;
+            uint32_t qa = qp_sa + ((uint32_t)fb >> 3) * qp_stride;
+            int code = fb + 7;
+            uint4 c0 = lds128(sa), c1 = lds128(sa + 16);
+            uint32_t s0, s1, s2, s3, xa;
+            {
                 const uint32_t x = lds16(qa) ^ trep;
-                const uint32_t s2 = K16_SCORE(x, 2), s3 = K16_SCORE(x, 3);
-                K16_GROUP(g0, s2, s3, sa, hn0, hn1)
-                const uint32_t g = max2(hn0, hn1);
-                K16_KEY(g, j + 3)
-                j += 4; sa += 16; qa += qp_stride;
-                g0 = lds128(sa);
+                s0 = K16_SCORE(x, 0); s1 = K16_SCORE(x, 1); s2 = K16_SCORE(x, 2); s3 = K16_SCORE(x, 3);
+                xa = lds16(qa + qp_stride) ^ trep;
             }
-            uint32_t cs0 = 0, cs1 = 0;
-            bool fresh = true;
-            if (j + 8 <= end) {
-                // full blocks of 8 columns, software-pipelined and unrolled twice: while one block
-                // computes from one register set, the next block's row words, query halfword and score
-                // words are loaded into the other set (the shared-memory accesses are volatile, so
-                // ptxas keeps the loads ahead of the block's stores instead of sinking them to their use)
-                uint4 c0 = g0, c1 = lds128(sa + 16), n0, n1;
-                const uint32_t x = lds16(qa) ^ trep;
-                uint32_t s0 = K16_SCORE(x, 0), s1 = K16_SCORE(x, 1), s2 = K16_SCORE(x, 2), s3 = K16_SCORE(x, 3);
-                uint32_t t0, t1, t2, t3;
-                uint32_t xa = lds16(qa + qp_stride) ^ trep, xb;
-                int code = j + 7;
-#define K16_BLOCK(C0, C1, S0, S1, S2, S3, XN, N0, N1, T0, T1, T2, T3, XN2)                              \
-                {                                                                                     \
-                    N0 = lds128(sa + 32); N1 = lds128(sa + 48);                                       \
-                    T0 = K16_SCORE(XN, 0); T1 = K16_SCORE(XN, 1); T2 = K16_SCORE(XN, 2); T3 = K16_SCORE(XN, 3); \
-                    XN2 = lds16(qa + 2 * qp_stride) ^ trep;                                           \
-                    K16_GROUP(C0, S0, S1, sa, hn0, hn1)                                               \
-                    K16_GROUP(C1, S2, S3, sa + 16, hn2, hn3)                                          \
-                    const uint32_t g_ = max2(max3(hn0, hn1, hn2), hn3);                               \
-                    K16_KEY(g_, code)                                                                 \
-                    j += 8; sa += 32; qa += qp_stride; code += 8;                                     \
+            if (lb > fb) {
+                K16_FIRST(zf)
+                // interior blocks, unrolled twice over two register sets
+                int nmid = ((lb - fb) >> 3) - 1;
+                if (nmid > 0) {
+                    uint4 n0, n1;
+                    uint32_t t0, t1, t2, t3, xb;
+                    for (;;) {
+                        K16_BLOCK(c0, c1, s0, s1, s2, s3, xa, n0, n1, t0, t1, t2, t3, xb)
+                        if (--nmid == 0) { c0 = n0; c1 = n1; s0 = t0; s1 = t1; s2 = t2; s3 = t3; break; }
+                        K16_BLOCK(n0, n1, t0, t1, t2, t3, xb, c0, c1, s0, s1, s2, s3, xa)
+                        if (--nmid == 0) break;
+                    }
                 }
-                for (;;) {
-                    K16_BLOCK(c0, c1, s0, s1, s2, s3, xa, n0, n1, t0, t1, t2, t3, xb)
-                    if (j + 8 > end) { c0 = n0; s0 = t0; s1 = t1; break; }
-                    K16_BLOCK(n0, n1, t0, t1, t2, t3, xb, c0, c1, s0, s1, s2, s3, xa)
-                    if (j + 8 > end) break;
-                }
-#undef K16_BLOCK
-                g0 = c0; cs0 = s0; cs1 = s1; fresh = false;
             }
-            if (j + 4 <= end) {
-                // trailing half block: pairs 0, 1 of its query halfword
-                if (fresh) {
-                    const uint32_t x = lds16(qa) ^ trep;
-                    cs0 = K16_SCORE(x, 0); cs1 = K16_SCORE(x, 1);
-                }
-                K16_GROUP(g0, cs0, cs1, sa, hn0, hn1)
-                const uint32_t g = max2(hn0, hn1);
-                K16_KEY(g, j + 3)
-                j += 4;
-            }
-            jt = j;
-            h1 = (int)(carry >> 16);
-            f = (int)(fc >> 16);
+            K16_EDGE(16 * (end - lb), zl, h1)
+            if (lb == fb) zf = zl;
+            my_cells += end - beg;
         } else {
-            j = beg;
-        }
-        // scalar tail: the <= 3 columns right of the last full group (or a window narrower than a group)
-        for (; j < end; ++j) {
-            const uint32_t ha = K16_HADDR(j);
-            const int hd = (int)lds16(ha), e = (int)lds16(ha + 8);
-            const int qj = (int)((lds16(qp_sa + ((uint32_t)j >> 3) * qp_stride) >> ((j & 7) * 2)) & 3u);
-            const int sc = qj == ti ? P.match : P.mismatch_neg;
-            int M = hd ? hd + sc : 0;
-            M = M > 0 ? M : 0;                               // a negative M is equivalent to 0 in every use
-            int h = M > e ? M : e;
-            h = h > f ? h : f;
-            sts16(ha, (uint32_t)h1);
-            h1 = h;
-            int t = M - P.oe_del; t = t > 0 ? t : 0;
-            int en = e - P.e_del; en = en > t ? en : t;
-            sts16(ha + 8, (uint32_t)en);
-            t = M - P.oe_ins; t = t > 0 ? t : 0;
-            f -= P.e_ins; f = f > t ? f : t;
-            const int key = (h << 16) | j;
-            mkey = mkey > key ? mkey : key;
-        }
-        if (end > beg) my_cells += end - beg;
-        // eh[end] = {h1, 0}  (bandedSWA.cpp:213)
-        {
+            // empty window: eh[end] = {h1, 0}  (bandedSWA.cpp:213)
             const uint32_t ha = K16_HADDR(end);
             sts16(ha, (uint32_t)h1);
             sts16(ha + 8, 0u);
@@ -445,13 +518,12 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
         }
         const int m = mkey >> 16;
         int mj = mkey & 0xffff;
-        if (mj < jt && (m > st.max || st.max - m > P.zdrop)) {
-            // the key names a block (its last column, mj + 1 a multiple of 4): the reference's mj is
+        if (m > st.max || st.max - m > P.zdrop) {
+            // the key names a block (its last column, mj + 1 a multiple of 8): the reference's mj is
             // the last column of [mj - 7, mj] whose H equals m (bandedSWA.cpp:202-203).  H(i, c) sits
             // in hs[c + 1]; the eight halves are flagged in parallel (1 where hs >= m: inside this
-            // row's sweep no H exceeds m, and whatever lies left of the sweep is lower than the
-            // block's own maximum column, so a stale hit there never wins) and the highest flag taken.
-            // The epilogue reads mj only under the condition above.
+            // row's sweep no H exceeds m; columns left of beg hold zeros, columns from end on are
+            // masked out) and the highest flag taken.  The epilogue reads mj only under the condition above.
             const uint32_t ga = eh_sa + (((uint32_t)(mj + 1) >> 2) << 4);
             const uint32_t a0 = lds32(ga - 32), a1 = lds32(ga - 28), b0 = lds32(ga - 16), b1 = lds32(ga - 12), c0 = lds32(ga);
             const uint32_t dm = pack2(1 - m, 1 - m), one2 = 0x00010001u;
@@ -459,33 +531,54 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
             const uint32_t fb0 = addmin_relu(b0, dm, one2), fb1 = addmin_relu(b1, dm, one2), fc0 = addmin_relu(c0, dm, one2);
             // bit k of the mask = column mj - 7 + k
             const uint32_t xw = mad_u(fc0, 128u, mad_u(fb1, 32u, mad_u(fb0, 8u, fa1 * 2u)));
-            const uint32_t mask = (xw & 0xaau) | ((xw >> 15) & 0x54u) | (fa0 >> 16);
+            uint32_t mask = (xw & 0xaau) | ((xw >> 15) & 0x54u) | (fa0 >> 16);
+            if (mj >= end) mask &= (1u << (end - (mj - 7))) - 1u;
             mj = mj - 7 + hibit(mask);
         }
         if (bsw_row_update(P, st, i, m, mj)) break;
-        // next row's window (bandedSWA.cpp:230-233)
-        {
-            int jj = beg;
-            while (jj < end) {
-                const uint32_t ha = K16_HADDR(jj);
-                if (lds16(ha) | lds16(ha + 8)) break;
-                ++jj;
+        // next row's window (bandedSWA.cpp:230-233): first non-zero column of [beg, end), then the
+        // last non-zero column of [beg', end]
+        if (end > beg) {
+            uint32_t zb = zf;
+            if (lb == fb) zb &= ~(1u << (end - fb));
+            int jj;
+            if (zb) jj = fb + lobit(zb);
+            else {
+                jj = fb + 8;
+                while (jj < end) {
+                    const uint32_t ha = K16_HADDR(jj);
+                    if (lds16(ha) | lds16(ha + 8)) break;
+                    ++jj;
+                }
+                jj = jj < end ? jj : end;
             }
             beg = jj;
-            jj = end;
-            while (jj >= beg) {
-                const uint32_t ha = K16_HADDR(jj);
-                if (lds16(ha) | lds16(ha + 8)) break;
-                --jj;
+            const uint32_t ze = beg > lb ? zl & (0xffu << (beg - lb)) : zl;
+            if (ze) jj = lb + hibit(ze);
+            else {
+                jj = lb - 1;
+                while (jj >= beg) {
+                    const uint32_t ha = K16_HADDR(jj);
+                    if (lds16(ha) | lds16(ha + 8)) break;
+                    --jj;
+                }
+                jj = jj >= beg - 1 ? jj : beg - 1;
             }
             end = jj + 2 < qlen ? jj + 2 : qlen;
         }
+        // (an empty window has m == 0 and stopped the pair above)
     }
 #undef K16_HADDR
 #undef K16_SCORE
 #undef K16_WORD
 #undef K16_GROUP
 #undef K16_KEY
+#undef K16_PREFETCH
+#undef K16_BLOCK
+#undef K16_GE
+#undef K16_ZMAP
+#undef K16_FIRST
+#undef K16_EDGE
 }
 
 // shared memory of one block: score table + rows + query plane
