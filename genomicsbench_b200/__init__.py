@@ -8,7 +8,12 @@ Host-side mirror of the reference operator interface (benchmarks/bsw/bandedSWA.h
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
+
+# One hardware queue per stream of the engine's pipeline (bsw_create sets the same default, but the
+# variable only counts before the process's first CUDA call -- e.g. torch's, in bench.py).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 

@@ -50,7 +50,7 @@ class BswStats(C.Structure):
         ("ms_kernel", C.c_double), ("ms_d2h", C.c_double), ("ms_scatter", C.c_double),
         ("ms_total", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("kernel_launches", C.c_int32), ("n_short", C.c_int32), ("n_long", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("partitioned", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
     def as_dict(self) -> dict:

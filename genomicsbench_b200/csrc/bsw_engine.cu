@@ -29,6 +29,8 @@
 #include <memory>
 #include <deque>
 #include <climits>
+#include <type_traits>
+#include <cuda.h>                         // types only: the driver entry points are fetched through the runtime
 
 using namespace bsw;
 
@@ -37,15 +39,55 @@ namespace {
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
 constexpr int SHORT_MAX_QLEN = 824;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
 constexpr int NSTREAMS = 16;              // DP compute streams per device (one shared-memory class each, run concurrently)
-constexpr int NSLOTS = 4;                 // chunks in flight per device (records ahead / prepare / compute / drain)
+constexpr int NSLOTS = 6;                 // chunks in flight per device (records ahead / prepare / compute / drain, + slack before a slot is reused)
 constexpr int64_t CHUNK_EXTEND = 1 << 18; // largest chunk of bsw_extend (overlap vs bucketing quality)
 constexpr int64_t CHUNK_MIN = 1 << 15;    // the last chunks of a batch shrink towards this (short pipeline drain)
 constexpr int64_t CHUNK_STAGE = 1 << 20;  // pairs per chunk of bsw_stage (resident: best bucketing)
 constexpr int BUCKET_BITS = 18;           // bins of the counting sort (1 MB table)
 constexpr long long OFF_BIAS = 1ll << 30; // bias of ChunkInfo::min_* / max_* (bsw_prep.cuh)
+constexpr size_t BINS_WORDS = ((size_t)1 << BUCKET_BITS) + SCAN_MAX_TILES + 8;   // bin table + tile totals + ticket
+constexpr int64_t CHUNK_PCIE = 3 << 15;   // chunk of a PCIe-bound batch (98 304 pairs): DP keeps pace with the arrivals
 
 std::string g_create_error;
 std::mutex g_err_mutex;
+// BSW_TIMELINE=1: bsw_extend prints, per chunk, when each pipeline stage finished on the device and
+// when the host reached its enqueue / wait points (diagnostic; the events then carry timestamps)
+const bool g_timeline = getenv("BSW_TIMELINE") != nullptr;
+
+// CUDA green contexts (driver API, CUDA >= 12.4), fetched with cudaGetDriverEntryPoint so that the
+// library does not link libcuda (it must load, and export its symbols, on a box without a driver).
+// They split a device's SMs into a small SERVICE partition for the chunk streams (copies, scan,
+// bucket, pack, write-back) and a DP partition for the extension kernels: a DP launch fills every
+// SM it may use to the register / shared-memory limit with blocks that live as long as the launch,
+// and no stream priority evicts running blocks -- on shared SMs the next chunk's 10-microsecond
+// prep kernels waited ~0.5 ms behind it and the copy engine idled (scripts/greenctx_probe.cu,
+// BSW_TIMELINE).  Used for PCIe-bound batches only; compute-bound ones keep all SMs for the DP.
+struct GreenApi {
+    decltype(&cuDeviceGetDevResource) get_res = nullptr;
+    decltype(&cuDevSmResourceSplitByCount) split = nullptr;
+    decltype(&cuDevResourceGenerateDesc) gen_desc = nullptr;
+    decltype(&cuGreenCtxCreate) create = nullptr;
+    decltype(&cuGreenCtxStreamCreate) stream_create = nullptr;
+    decltype(&cuGreenCtxDestroy) destroy = nullptr;
+    bool ok = false;
+    GreenApi()
+    {
+        auto get = [](const char* name, auto& fn) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+                cudaGetLastError();
+                return false;
+            }
+            fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(p);
+            return true;
+        };
+        ok = get("cuDeviceGetDevResource", get_res) && get("cuDevSmResourceSplitByCount", split) &&
+             get("cuDevResourceGenerateDesc", gen_desc) && get("cuGreenCtxCreate", create) &&
+             get("cuGreenCtxStreamCreate", stream_create) && get("cuGreenCtxDestroy", destroy);
+    }
+};
+const GreenApi& green_api() { static GreenApi g; return g; }
 
 struct Launch {
     int first, count;     // range in the chunk's processing order
@@ -64,9 +106,19 @@ struct Slot {
     Buf<uint32_t> perm, rank, bins, nlist, llist, qpk, tpk, scratch;
     Buf<uint8_t> qraw, rraw;              // sequence bytes (device; pinned twin = staging of the staged route)
     ChunkInfo* d_info = nullptr; ChunkInfo* h_info = nullptr;
+    ChunkInfo* h_info_dev = nullptr;      // device-side address of h_info (mapped page-locked memory)
+    // speculative sequence copies of the direct route (direct_begin): absolute byte range per side
+    bool spec[2] = {false, false};        // [0] query, [1] reference
+    long long spec_lo[2] = {0, 0}, spec_hi[2] = {0, 0};
     unsigned int* d_queue = nullptr;
-    cudaStream_t st{};
-    cudaEvent_t ev_info{}, ev_dp{}, ev_out{}, ev_fork{}, ev_k0{}, ev_k1{};
+    cudaStream_t st{};                    // the stream the chunk in this slot runs on: st_plain or st_svc
+    cudaStream_t st_plain{}, st_svc{};    // whole device (high priority) / service partition
+    cudaEvent_t ev_rec{}, ev_seqd{};      // direct route: records / speculative sequence copy arrived (recorded on the H2D stream)
+    bool bins_zeroed = false;             // the bin table was cleared at open()
+    bool fork_recorded = false;           // ev_fork already marks the end of the prep kernels
+    cudaEvent_t ev_tl[5] = {};            // BSW_TIMELINE: after zero / count / scan / scatter / pack
+    cudaEvent_t ev_info{}, ev_dp{}, ev_out{}, ev_fork{}, ev_k0{}, ev_k1{}, ev_seq{}, ev_lists{};
+    double host_t[6] = {};                // timeline: host clock at open / info / launched / dp seen / out enqueued / retired
     // chunk state
     int64_t a = 0; int n = 0;             // pairs [a, a + n) of the batch
     bool direct = false;
@@ -82,7 +134,11 @@ struct Slot {
 struct DevCtx {
     int dev = 0;
     int sms = 148;
-    cudaStream_t cs[NSTREAMS] = {};
+    cudaStream_t cs[NSTREAMS] = {};       // DP streams over the whole device (low priority)
+    cudaStream_t cs_part[NSTREAMS] = {};  // DP streams of the DP partition
+    cudaStream_t h2d{};                   // every host-to-device copy of the direct route, in chunk order (see direct_begin)
+    CUgreenCtx g_svc = nullptr, g_dp = nullptr;
+    int svc_sms = 0, dp_sms = 0;          // 0: no partitions on this device
     cudaEvent_t ev_join[NSTREAMS] = {};
     cudaEvent_t ev_t0{}, ev_t1{};         // device timeline of bsw_run_staged
     std::deque<Slot> slots;
@@ -193,6 +249,40 @@ int set_kernel_attrs(bsw_engine* eng, DevCtx& c)
     return BSW_OK;
 }
 
+// Splits the device into a service partition and a DP partition (see GreenApi).  Best effort: on
+// any failure the device simply runs unpartitioned.  BSW_SERVICE_SMS overrides the service size
+// (0 disables the split).
+void setup_partitions(DevCtx& c)
+{
+    const GreenApi& G = green_api();
+    int want = 32;
+    if (const char* e = getenv("BSW_SERVICE_SMS")) want = atoi(e);
+    if (!G.ok || want <= 0 || want * 2 > c.sms) return;
+    cudaFree(0);                                            // the primary context must exist
+    CUdevResource all{}, svc{}, rest{};
+    if (G.get_res((CUdevice)c.dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return;
+    unsigned nb = 1;
+    if (G.split(&svc, &nb, &all, &rest, 0, (unsigned)want) != CUDA_SUCCESS || nb != 1 || rest.sm.smCount == 0) return;
+    CUdevResourceDesc d_svc{}, d_rest{};
+    if (G.gen_desc(&d_svc, &svc, 1) != CUDA_SUCCESS || G.gen_desc(&d_rest, &rest, 1) != CUDA_SUCCESS) return;
+    CUgreenCtx g_svc = nullptr, g_dp = nullptr;
+    if (G.create(&g_svc, d_svc, (CUdevice)c.dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+    if (G.create(&g_dp, d_rest, (CUdevice)c.dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { G.destroy(g_svc); return; }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (int k = 0; k < NSTREAMS; ++k) {
+        CUstream cu = nullptr;
+        if (G.stream_create(&cu, g_dp, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS) {
+            for (int j = 0; j < k; ++j) { cudaStreamDestroy(c.cs_part[j]); c.cs_part[j] = nullptr; }
+            G.destroy(g_svc); G.destroy(g_dp);
+            return;
+        }
+        c.cs_part[k] = (cudaStream_t)cu;
+    }
+    c.g_svc = g_svc; c.g_dp = g_dp;
+    c.svc_sms = (int)svc.sm.smCount; c.dp_sms = (int)rest.sm.smCount;
+}
+
 int validate_params(const bsw_params* p, std::string& why)
 {
     auto bad = [&](const char* m) { why = m; return BSW_ERR_PARAM; };
@@ -228,24 +318,42 @@ bool is_pinned(const void* p)
     return at.type == cudaMemoryTypeHost;
 }
 
-int slot_create(bsw_engine* eng, Slot& s)
+int slot_create(bsw_engine* eng, DevCtx& c, Slot& s)
 {
-    CUDA_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&s.ev_info, &s.ev_dp, &s.ev_out, &s.ev_fork})
-        CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    // The chunk streams (copies, prep kernels, write-back) outrank the DP streams: a DP launch
+    // queues thousands of blocks, and at equal priority the small kernels of the NEXT chunks would
+    // wait behind that backlog, starving the copy engine of work (seen in the BSW_TIMELINE trace).
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&s.st_plain, cudaStreamNonBlocking, prio_hi));
+    if (c.svc_sms > 0) {
+        CUstream cu = nullptr;
+        if (green_api().stream_create(&cu, c.g_svc, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) {
+            eng->err = "cuGreenCtxStreamCreate failed";
+            return BSW_ERR_CUDA;
+        }
+        s.st_svc = (cudaStream_t)cu;
+    }
+    s.st = s.st_plain;
+    for (cudaEvent_t* e : {&s.ev_info, &s.ev_dp, &s.ev_out, &s.ev_fork, &s.ev_seq, &s.ev_lists, &s.ev_rec, &s.ev_seqd})
+        CUDA_TRY(cudaEventCreateWithFlags(e, g_timeline ? cudaEventDefault : cudaEventDisableTiming));
+    if (g_timeline) for (cudaEvent_t& e : s.ev_tl) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaEventCreate(&s.ev_k0));
     CUDA_TRY(cudaEventCreate(&s.ev_k1));
     CUDA_TRY(cudaMalloc((void**)&s.d_info, sizeof(ChunkInfo)));
-    CUDA_TRY(cudaHostAlloc((void**)&s.h_info, sizeof(ChunkInfo), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&s.h_info, sizeof(ChunkInfo), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&s.h_info_dev, s.h_info, 0));
     CUDA_TRY(cudaMalloc((void**)&s.d_queue, sizeof(unsigned int)));
     return BSW_OK;
 }
 
 void slot_destroy(Slot& s)
 {
-    if (s.st) cudaStreamDestroy(s.st);
-    for (cudaEvent_t e : {s.ev_info, s.ev_dp, s.ev_out, s.ev_fork, s.ev_k0, s.ev_k1})
+    if (s.st_plain) cudaStreamDestroy(s.st_plain);
+    if (s.st_svc) cudaStreamDestroy(s.st_svc);
+    for (cudaEvent_t e : {s.ev_info, s.ev_dp, s.ev_out, s.ev_fork, s.ev_k0, s.ev_k1, s.ev_seq, s.ev_lists, s.ev_rec, s.ev_seqd})
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s.ev_tl) if (e) cudaEventDestroy(e);
     release(s.raw_pairs); release(s.desc); release(s.meta); release(s.res); release(s.perm); release(s.rank);
     release(s.bins); release(s.nlist); release(s.llist); release(s.qpk); release(s.tpk); release(s.scratch);
     release(s.qraw); release(s.rraw);
@@ -258,7 +366,7 @@ int get_slot(bsw_engine* eng, DevCtx& c, int k, Slot** out)
 {
     while ((int)c.slots.size() <= k) {
         c.slots.emplace_back();
-        if (int rc = slot_create(eng, c.slots.back())) return rc;
+        if (int rc = slot_create(eng, c, c.slots.back())) return rc;
     }
     *out = &c.slots[(size_t)k];
     return BSW_OK;
@@ -266,33 +374,71 @@ int get_slot(bsw_engine* eng, DevCtx& c, int k, Slot** out)
 
 inline int grid_for(const DevCtx& c, int n, int per_block)
 {
-    return std::max(1, std::min((n + per_block - 1) / per_block, c.sms * 8));
+    return std::max(1, std::min((n + per_block - 1) / per_block, c.sms * 32));
 }
 
 // ------------------------------------------------------------------------------------------
 // stage A, direct route: records DMA + scan; the summary comes back through ev_info
 // ------------------------------------------------------------------------------------------
-int direct_begin(bsw_engine* eng, DevCtx& c, Slot& s, const SeqPair* pairs)
+int direct_begin(bsw_engine* eng, DevCtx& c, Slot& s, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer)
 {
     const size_t bytes = (size_t)s.n * sizeof(SeqPair);
     if (int rc = ensure(eng, s.raw_pairs, bytes)) return rc;
     if (int rc = ensure(eng, s.desc, (size_t)s.n)) return rc;
-    init_info(*s.h_info);
-    CUDA_TRY(cudaMemcpyAsync(s.d_info, s.h_info, sizeof(ChunkInfo), cudaMemcpyHostToDevice, s.st));
-    CUDA_TRY(cudaMemcpyAsync(s.raw_pairs.d, pairs + s.a, bytes, cudaMemcpyHostToDevice, s.st));
+    // Host-to-device copies of all chunks go through ONE stream, in chunk order: copies issued on
+    // several streams share the link, so with the next chunks' copies already queued every chunk
+    // would arrive late; in FIFO order chunk k is complete before chunk k + 1 takes bandwidth.
+    if (int rc = ensure(eng, s.bins, BINS_WORDS)) return rc;
+    bsw_info_init<<<1, PREP_BLOCK, 0, s.st>>>(s.d_info);
+    bsw_zero_words<<<64, PREP_BLOCK, 0, s.st>>>(reinterpret_cast<uint4*>(s.bins.d), (int)(BINS_WORDS / 4));
+    s.bins_zeroed = true;
+    CUDA_TRY(cudaMemcpyAsync(s.raw_pairs.d, pairs + s.a, bytes, cudaMemcpyHostToDevice, c.h2d));
+    CUDA_TRY(cudaEventRecord(s.ev_rec, c.h2d));
+    CUDA_TRY(cudaStreamWaitEvent(s.st, s.ev_rec, 0));
     const long long base0_r = pairs[s.a].idr, base0_q = pairs[s.a].idq;     // one record read by the host
-    bsw_scan_pairs<<<grid_for(c, s.n, 256), 256, 0, s.st>>>(
+    bsw_scan_pairs<<<grid_for(c, s.n, 8 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(
         reinterpret_cast<const SeqPair*>(s.raw_pairs.d), s.n, base0_r, base0_q, eng->p.match, eng->short_max,
         s.desc.d, s.d_info);
+    bsw_info_publish<<<1, PREP_BLOCK, 0, s.st>>>(s.d_info, s.h_info_dev);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(s.h_info, s.d_info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, s.st));
     CUDA_TRY(cudaEventRecord(s.ev_info, s.st));
     eng->stats.h2d_bytes += (int64_t)bytes;
-    eng->stats.kernel_launches++;
+    eng->stats.kernel_launches += 4;
+
+    // Speculative sequence copy.  The byte range the chunk's sequences span is only known after the
+    // scan, and waiting for it would leave the copy engine idle for a host round trip per chunk.
+    // Batches are normally laid out in record order (the reference loader, main_banded.cpp:131-185,
+    // appends sequence after sequence), so the range from the first record's offset to the last
+    // record's end is copied right away; direct_sequences() checks the scanned range against it and
+    // copies again in the rare case the guess does not cover it.
+    const SeqPair& f = pairs[s.a];
+    const SeqPair& l = pairs[s.a + s.n - 1];
+    double est_q = 0, est_r = 0;                                            // bases per pair, sampled
+    const int step = std::max(1, s.n / 61);
+    int ns = 0;
+    for (int i = 0; i < s.n; i += step, ++ns) { est_q += pairs[s.a + i].len2; est_r += pairs[s.a + i].len1; }
+    est_q = est_q / ns * s.n; est_r = est_r / ns * s.n;
+    struct Side { const uint8_t* host; long long lo, hi; double est; Buf<uint8_t>* buf; };
+    Side sides[2] = {{seq_qer, std::min(f.idq, l.idq), std::max(f.idq + f.len2, l.idq + l.len2), est_q, &s.qraw},
+                     {seq_ref, std::min(f.idr, l.idr), std::max(f.idr + f.len1, l.idr + l.len1), est_r, &s.rraw}};
+    for (int k = 0; k < 2; ++k) {
+        Side& sd = sides[k];
+        s.spec[k] = false;
+        if (sd.lo < 0 || sd.hi <= sd.lo || f.len1 < 1 || f.len2 < 1 || l.len1 < 1 || l.len2 < 1) continue;
+        const long long lo_al = sd.lo & ~15ll;                              // keep the source's 16-byte phase
+        const double span = (double)(sd.hi - lo_al);
+        if (span > 2.0 * sd.est + (double)(1 << 20) || span > 3.0e9) continue;   // sparse (or not in record order): wait for the scan
+        if (int rc = ensure(eng, *sd.buf, (size_t)(sd.hi - lo_al) + 64)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(sd.buf->d, sd.host + lo_al, (size_t)(sd.hi - lo_al), cudaMemcpyHostToDevice, c.h2d));
+        s.spec[k] = true; s.spec_lo[k] = lo_al; s.spec_hi[k] = sd.hi;
+        eng->stats.h2d_bytes += sd.hi - lo_al;
+    }
+    CUDA_TRY(cudaEventRecord(s.ev_seqd, c.h2d));
     return BSW_OK;
 }
 
-// stage B, direct route: sequences to the device (DMA of the spanned range, or mapped reads)
+// stage B, direct route: sequences on the device -- the speculative copy when it covers the scanned
+// range, else a DMA of that range (dense) or mapped reads (sparse)
 int direct_sequences(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer)
 {
     CUDA_TRY(cudaEventSynchronize(s.ev_info));
@@ -302,9 +448,14 @@ int direct_sequences(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8
     struct Side { const uint8_t* host; long long base0; unsigned long long mn, mx, bases; Buf<uint8_t>* buf; const uint8_t** out; };
     Side sides[2] = {{seq_qer, base0_q, s.info.min_q, s.info.max_q, s.info.qbases, &s.qraw, &s.qbase},
                      {seq_ref, base0_r, s.info.min_r, s.info.max_r, s.info.tbases, &s.rraw, &s.rbase}};
-    for (Side& sd : sides) {
+    for (int k = 0; k < 2; ++k) {
+        Side& sd = sides[k];
         const long long lo = sd.base0 + ((long long)sd.mn - OFF_BIAS);       // absolute byte offsets [lo, hi)
         const long long hi = sd.base0 + ((long long)sd.mx - OFF_BIAS);
+        if (s.spec[k] && lo >= s.spec_lo[k] && hi <= s.spec_hi[k]) {
+            *sd.out = sd.buf->d + (sd.base0 - s.spec_lo[k]);
+            continue;
+        }
         const unsigned long long span = (unsigned long long)(hi - lo);
         const bool dense = span <= 2 * sd.bases + (1ull << 20);
         if (dense) {
@@ -321,6 +472,9 @@ int direct_sequences(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8
             eng->stats.h2d_bytes += (int64_t)sd.bases;
         }
     }
+    // (the chunk stream never overtakes its own speculative copies, used or not: the buffers are its own)
+    CUDA_TRY(cudaStreamWaitEvent(s.st, s.ev_seqd, 0));
+    if (g_timeline) CUDA_TRY(cudaEventRecord(s.ev_seq, s.st));
     return BSW_OK;
 }
 
@@ -396,8 +550,8 @@ int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t
     memset(s.qraw.h + qtot, 0, 64); memset(s.rraw.h + rtot, 0, 64);
     eng->stats.ms_pack += now_ms() - t0;
     // H2D
-    init_info(*s.h_info);
-    CUDA_TRY(cudaMemcpyAsync(s.d_info, s.h_info, sizeof(ChunkInfo), cudaMemcpyHostToDevice, s.st));
+    bsw_info_init<<<1, PREP_BLOCK, 0, s.st>>>(s.d_info);
+    eng->stats.kernel_launches++;
     CUDA_TRY(cudaMemcpyAsync(s.desc.d, s.desc.h, sizeof(int4) * (size_t)n, cudaMemcpyHostToDevice, s.st));
     CUDA_TRY(cudaMemcpyAsync(s.qraw.d, s.qraw.h, (size_t)qtot + 64, cudaMemcpyHostToDevice, s.st));
     CUDA_TRY(cudaMemcpyAsync(s.rraw.d, s.rraw.h, (size_t)rtot + 64, cudaMemcpyHostToDevice, s.st));
@@ -409,6 +563,7 @@ int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t
 // ------------------------------------------------------------------------------------------
 // stage C (both routes): bucket, pack in processing order, launch plan
 // ------------------------------------------------------------------------------------------
+#define TL_MARK(K) do { if (g_timeline) CUDA_TRY(cudaEventRecord(s.ev_tl[K], s.st)); } while (0)
 int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
 {
     const ChunkInfo& I = s.info;
@@ -436,20 +591,30 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
         K.short_max = eng->short_max;
         const int nbins = 1 << (total - K.drop);
         const int ntiles = (nbins + SCAN_TILE - 1) / SCAN_TILE;           // <= 256
-        if (int rc = ensure(eng, s.bins, (size_t)nbins + 1024)) return rc;   // bins, then the tile totals
-        uint32_t* totals = s.bins.d + nbins;
-        CUDA_TRY(cudaMemsetAsync(s.bins.d, 0, sizeof(uint32_t) * (size_t)nbins, s.st));
-        bsw_bucket_count<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, K, s.bins.d, s.rank.d, s.llist.d, s.d_info);
+        const size_t nb_pad = (size_t)ntiles * SCAN_TILE;                  // whole tiles, so the scan needs no edge cases
+        if (int rc = ensure(eng, s.bins, BINS_WORDS)) return rc;            // bins, tile totals, ticket counter
+        uint32_t* totals = s.bins.d + nb_pad;
+        unsigned int* ticket = totals + SCAN_MAX_TILES;
+        if (!s.bins_zeroed) {                                                // (direct route: cleared at open())
+            bsw_zero_words<<<64, PREP_BLOCK, 0, s.st>>>(reinterpret_cast<uint4*>(s.bins.d), (int)(BINS_WORDS / 4));
+            eng->stats.kernel_launches++;
+        }
+        s.bins_zeroed = false;
+        TL_MARK(0);
+        bsw_bucket_count<<<grid_for(c, n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.desc.d, n, K, s.bins.d, s.rank.d, s.llist.d, s.d_info);
         eng->stats.kernel_launches++;
+        TL_MARK(1);
         if (I.n_short > 0) {
-            bsw_bucket_scan_tiles<<<ntiles, 256, 0, s.st>>>(s.bins.d, nbins, totals);
-            bsw_bucket_scan_totals<<<1, 1024, 0, s.st>>>(totals, ntiles);
-            bsw_bucket_scatter<<<grid_for(c, n, 256), 256, 0, s.st>>>(s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d);
+            bsw_bucket_scan<<<ntiles, PREP_BLOCK, 0, s.st>>>(s.bins.d, nbins, totals, ticket);
+            TL_MARK(2);
+            bsw_bucket_scatter<<<grid_for(c, n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d);
+            TL_MARK(3);
             // 2-bit packing in processing order
-            bsw_pack_pairs<<<grid_for(c, I.n_short, 256), 256, 0, s.st>>>(s.desc.d, s.perm.d, I.n_short, s.qbase, s.rbase,
+            bsw_pack_pairs<<<grid_for(c, I.n_short, PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.desc.d, s.perm.d, I.n_short, s.qbase, s.rbase,
                                                                           s.meta.d, s.qpk.d, s.tpk.d, s.nlist.d, s.d_info,
                                                                           eng->use16 ? eng->p.match : 0);
-            eng->stats.kernel_launches += 4;
+            TL_MARK(4);
+            eng->stats.kernel_launches += 3;
             // launch plan: the processing order ascends in len2, so the shared-memory classes are
             // prefix ranges of it, read off the len2 histogram
             int pos = 0;
@@ -465,22 +630,32 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
     }
     CUDA_TRY(cudaGetLastError());
     // the pack kernel's counters (pairs for the byte kernels) travel back with the chunk
-    CUDA_TRY(cudaMemcpyAsync(s.h_info, s.d_info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, s.st));
+    // the DP launches fork here, ahead of the summary's trip to the host (a PCIe write that queues
+    // behind the result traffic)
+    CUDA_TRY(cudaEventRecord(s.ev_fork, s.st));
+    s.fork_recorded = true;
+    bsw_info_publish<<<1, PREP_BLOCK, 0, s.st>>>(s.d_info, s.h_info_dev);
+    CUDA_TRY(cudaGetLastError());
+    eng->stats.kernel_launches++;
+    CUDA_TRY(cudaEventRecord(s.ev_lists, s.st));
     return BSW_OK;
 }
 
-// DP launches of a chunk: fan out over the device's compute streams, longest class first
-int launch_dp(bsw_engine* eng, DevCtx& c, Slot& s)
+// DP launches of a chunk: fan out over the device's compute streams (those of the DP partition
+// when the batch runs partitioned), longest class first
+int launch_dp(bsw_engine* eng, DevCtx& c, Slot& s, bool partitioned = false)
 {
+    cudaStream_t* cs = partitioned ? c.cs_part : c.cs;
+    if (!s.fork_recorded) CUDA_TRY(cudaEventRecord(s.ev_fork, s.st));
+    s.fork_recorded = false;
     if (s.plan.empty()) return BSW_OK;
-    CUDA_TRY(cudaEventRecord(s.ev_fork, s.st));
     const int nl = (int)s.plan.size();
     const int used = std::min(nl, NSTREAMS);
-    for (int k = 0; k < used; ++k) CUDA_TRY(cudaStreamWaitEvent(c.cs[k], s.ev_fork, 0));
+    for (int k = 0; k < used; ++k) CUDA_TRY(cudaStreamWaitEvent(cs[k], s.ev_fork, 0));
     int li = 0;
     for (int k = nl - 1; k >= 0; --k, ++li) {
         const Launch& L = s.plan[(size_t)k];
-        cudaStream_t st = c.cs[li % NSTREAMS];
+        cudaStream_t st = cs[li % NSTREAMS];
         const int grid = (L.count + SHORT_BLOCK - 1) / SHORT_BLOCK;
         if (!eng->use16)
             bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, short_smem_bytes(L.qstride), st>>>(
@@ -495,7 +670,7 @@ int launch_dp(bsw_engine* eng, DevCtx& c, Slot& s)
     }
     CUDA_TRY(cudaGetLastError());
     for (int k = 0; k < used; ++k) {
-        CUDA_TRY(cudaEventRecord(c.ev_join[k], c.cs[k]));
+        CUDA_TRY(cudaEventRecord(c.ev_join[k], cs[k]));
         CUDA_TRY(cudaStreamWaitEvent(s.st, c.ev_join[k], 0));
     }
     return BSW_OK;
@@ -535,7 +710,7 @@ int output_chunk(bsw_engine* eng, DevCtx& c, Slot& s, SeqPair* pairs)
     if (s.direct) {
         // results go into the device copy of the records, which then returns by one DMA (the
         // input fields come back as they left; per-field writes over PCIe would be 4-byte TLPs)
-        bsw_writeback<<<grid_for(c, s.n, 256), 256, 0, s.st>>>(s.res.d, s.n, reinterpret_cast<SeqPair*>(s.raw_pairs.d));
+        bsw_writeback<<<grid_for(c, s.n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.res.d, s.n, reinterpret_cast<SeqPair*>(s.raw_pairs.d));
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(pairs + s.a, s.raw_pairs.d, (size_t)s.n * sizeof(SeqPair), cudaMemcpyDeviceToHost, s.st));
         eng->stats.kernel_launches++;
@@ -568,7 +743,7 @@ void unpack_chunk(bsw_engine* eng, Slot& s, SeqPair* pairs)
     eng->stats.ms_scatter += now_ms() - t0;
 }
 
-// after ev_dp: the pack kernel's counters are on the host
+// after ev_lists: the pack kernel's counters are on the host
 void read_lists(Slot& s)
 {
     s.n_nlist = s.h_info->n_nlist; s.n_llist = s.h_info->n_llist; s.qmax_n = s.h_info->qmax_n;
@@ -602,19 +777,45 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
     bsw_stats& S = eng->stats;
     const int ndev = (int)eng->devs.size();
     const bool direct = is_pinned(pairs) && is_pinned(seq_ref) && is_pinned(seq_qer);
-    // chunk boundaries: full-size chunks, then a geometric ramp-down so that the work left after
-    // the last H2D (its DP and its D2H) is small
+    // PCIe-bound or compute-bound?  A sample of the records gives DP time (nominal cells at the
+    // resident kernel rate) against transfer time (record + sequence bytes at PCIe rate) per pair.
+    // PCIe-bound batches run partitioned: chunk streams on the service SMs, DP on the rest.
+    bool partitioned = false, pcie_bound = false;
+    if (!keep && n >= 4 * CHUNK_MIN) {
+        double cells = 0, bytes = 0;
+        const int64_t step = std::max<int64_t>(1, n / 509);
+        for (int64_t i = 0; i < n; i += step) {
+            cells += (double)pairs[i].len1 * (double)pairs[i].len2;
+            bytes += (double)sizeof(SeqPair) + (double)pairs[i].len1 + (double)pairs[i].len2;
+        }
+        pcie_bound = partitioned = cells / 2.0e9 < 0.7 * (bytes / 50e6);
+        for (DevCtx& c : eng->devs) partitioned = partitioned && c.svc_sms > 0;
+    }
+    eng->stats.partitioned = partitioned ? 1 : 0;
+    // chunk boundaries: a small first chunk (the first DP starts after a short H2D), full-size
+    // chunks, then a geometric ramp-down so that the work left after the last H2D (its DP and its
+    // D2H) is small.  PCIe-bound batches use smaller full-size chunks, sized so that the DP of one
+    // chunk finishes while the next arrives; compute-bound ones ramp up to large chunks (fewer
+    // launch tails, better bucketing).
+    // (pageable buffers: the host passes are the bottleneck and want large chunks for their thread pool)
+    const bool small_chunks = pcie_bound && direct;
+    const int64_t big = small_chunks ? CHUNK_PCIE : chunk_pairs;
+    const int64_t tail_min = small_chunks ? CHUNK_MIN / 2 : CHUNK_MIN;    // the last chunk's latency is all tail
     std::vector<int64_t> cut{0};
+    int64_t ramp = keep ? big : CHUNK_MIN;
     for (int64_t rem = n; rem > 0;) {
         int64_t sz;
-        if (keep || rem > 2 * chunk_pairs) sz = std::min(rem, chunk_pairs);
-        else if (rem > 2 * CHUNK_MIN) sz = std::min(rem, ((rem + 1) / 2 + 4095) & ~(int64_t)4095);
+        if (ramp < big && rem > 4 * ramp) { sz = ramp; ramp = small_chunks ? big : ramp * 2; }
+        else if (keep || rem > 2 * big) sz = std::min(rem, big);
+        else if (rem > 2 * tail_min) sz = std::min(rem, ((rem + 1) / 2 + 4095) & ~(int64_t)4095);
         else sz = rem;
         cut.push_back(cut.back() + sz);
         rem -= sz;
     }
     const int64_t nchunks = (int64_t)cut.size() - 1;
     std::vector<ChunkRef> refs((size_t)nchunks);
+    const double tl_host0 = now_ms();
+    std::vector<std::string> tl_lines;
     eng->staged_chunks.clear();
     for (DevCtx& c : eng->devs) {
         CUDA_TRY(cudaSetDevice(c.dev));
@@ -637,20 +838,27 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
         Slot& s = *sp;
         s.a = cut[(size_t)k]; s.n = (int)(cut[(size_t)k + 1] - cut[(size_t)k]);
         s.direct = direct;
+        s.st = partitioned ? s.st_svc : s.st_plain;
+        if (g_timeline) { if (k == 0) CUDA_TRY(cudaEventRecord(eng->devs[0].ev_t0, s.st)); s.host_t[0] = now_ms() - tl_host0; }
         CUDA_TRY(cudaEventRecord(s.ev_k0, s.st));
-        if (direct) return direct_begin(eng, c, s, pairs);
+        if (direct) return direct_begin(eng, c, s, pairs, seq_ref, seq_qer);
         return BSW_OK;
     };
     // finish: the chunk's DP is enqueued; learn the byte-kernel lists, run them, send results out
     auto finish = [&](int64_t k) -> int {
         DevCtx& c = dev_of(k); Slot& s = slot_of(k);
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaEventSynchronize(s.ev_dp));
+        // only the pack kernel's counters are needed here, not the DP: the byte kernels and the
+        // results' way out are stream-ordered behind the DP launches, the host does not wait for them
+        CUDA_TRY(cudaEventSynchronize(s.ev_lists));
+        if (g_timeline) s.host_t[3] = now_ms() - tl_host0;
         read_lists(s);
         S.n_short += s.n_sorted - (int)s.n_nlist; S.n_long += (int)s.n_llist;
         if (int rc = launch_bytes(eng, c, s)) return rc;
         CUDA_TRY(cudaEventRecord(s.ev_k1, s.st));
-        return output_chunk(eng, c, s, pairs);
+        const int rc = output_chunk(eng, c, s, pairs);
+        if (g_timeline) s.host_t[4] = now_ms() - tl_host0;
+        return rc;
     };
     auto retire = [&](int64_t k) -> int {
         DevCtx& c = dev_of(k); Slot& s = slot_of(k);
@@ -659,16 +867,45 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
         unpack_chunk(eng, s, pairs);
         float ms = 0;
         if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) S.ms_kernel += (double)ms;
+        if (g_timeline && ndev == 1) {
+            s.host_t[5] = now_ms() - tl_host0;
+            char line[512];
+            float t[7] = {};
+            cudaEvent_t evs[7] = {s.ev_k0, s.ev_info, s.ev_seq, s.ev_fork, s.ev_dp, s.ev_k1, s.ev_out};
+            for (int e = 0; e < 7; ++e)
+                if (cudaEventElapsedTime(&t[e], eng->devs[0].ev_t0, evs[e]) != cudaSuccess) { t[e] = -1; cudaGetLastError(); }
+            snprintf(line, sizeof(line),
+                     "chunk %2d n=%7d | dev: open %6.3f rec+scan %6.3f seq %6.3f prep %6.3f dp %6.3f bytes %6.3f out %6.3f"
+                     " | host: open %6.3f info %6.3f launched %6.3f dp-seen %6.3f out-enq %6.3f retired %6.3f",
+                     (int)k, s.n, t[0], t[1], t[2], t[3], t[4], t[5], t[6],
+                     s.host_t[0], s.host_t[1], s.host_t[2], s.host_t[3], s.host_t[4], s.host_t[5]);
+            tl_lines.emplace_back(line);
+            float p[5] = {};
+            for (int e = 0; e < 5; ++e)
+                if (cudaEventElapsedTime(&p[e], eng->devs[0].ev_t0, s.ev_tl[e]) != cudaSuccess) { p[e] = -1; cudaGetLastError(); }
+            snprintf(line, sizeof(line), "          prep detail: zero %6.3f count %6.3f scan %6.3f scatter %6.3f pack %6.3f fork %6.3f",
+                     p[0], p[1], p[2], p[3], p[4], t[3]);
+            tl_lines.emplace_back(line);
+        }
         return BSW_OK;
     };
 
-    // Per iteration k: records of chunk k + ndev go out (direct route) so the copy engine never
-    // waits for the host; chunk k gets its sequences, prep kernels and DP launches; chunk
-    // k - ndev drains (byte kernels, results out); chunk k - 2 ndev retires.
+    // Per iteration k: records (and the speculative sequence copy) of chunk k + 2 ndev go out (direct
+    // route) so the copy engine never waits for the host; chunk k gets its prep kernels and DP launches; chunk
+    // k - ndev drains (byte kernels, results out).  Chunks retire (results on the host; staged route:
+    // second host pass) as soon as their D2H has completed, without blocking -- the host only waits
+    // for a chunk when the slot it occupies is needed again, NSLOTS chunks later, so that a DP that
+    // runs long never keeps the host from feeding the copy engine.
     const int lag = ndev;
-    for (int64_t k = 0; k < std::min<int64_t>(lag, nchunks); ++k) if (int rc = open(k)) return rc;
-    for (int64_t k = 0; k < nchunks + 2 * lag; ++k) {
-        if (k + lag < nchunks) if (int rc = open(k + lag)) return rc;
+    const int ahead = direct && !keep ? 2 * ndev : ndev;     // chunks opened (records + speculative sequence copy) ahead of k
+    int64_t next_retire = 0;
+    for (int64_t k = 0; k < std::min<int64_t>(ahead, nchunks); ++k) if (int rc = open(k)) return rc;
+    for (int64_t k = 0; k < nchunks + lag; ++k) {
+        if (k + ahead < nchunks) {
+            if (!keep)
+                while (next_retire <= k + ahead - (int64_t)NSLOTS * ndev) if (int rc = retire(next_retire++)) return rc;
+            if (int rc = open(k + ahead)) return rc;
+        }
         if (k < nchunks) {
             DevCtx& c = dev_of(k); Slot& s = slot_of(k);
             CUDA_TRY(cudaSetDevice(c.dev));
@@ -676,13 +913,28 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
             if (rc) { if (rc == BSW_ERR_DOMAIN) eng->err = kDomainMsg; return rc; }
             S.cells_nominal += (int64_t)s.info.nominal;
             if ((rc = device_prepare(eng, c, s))) return rc;
-            if (!keep && (rc = launch_dp(eng, c, s))) return rc;
+            if (g_timeline) s.host_t[1] = now_ms() - tl_host0;      // (after the wait for the summary + planning)
+            if (!keep && (rc = launch_dp(eng, c, s, partitioned))) return rc;
             CUDA_TRY(cudaEventRecord(s.ev_dp, s.st));
+            if (g_timeline) s.host_t[2] = now_ms() - tl_host0;
+            if (keep) s.fork_recorded = false;                     // bsw_run_staged forks behind its own start event
             if (keep) eng->staged_chunks.emplace_back(refs[(size_t)k].dev, refs[(size_t)k].slot);
         }
         if (keep) continue;
         if (k - lag >= 0 && k - lag < nchunks) if (int rc = finish(k - lag)) return rc;
-        if (k - 2 * lag >= 0 && k - 2 * lag < nchunks) if (int rc = retire(k - 2 * lag)) return rc;
+        while (next_retire < k - lag) {                   // finished chunks whose results have arrived
+            Slot& s = slot_of(next_retire);
+            CUDA_TRY(cudaSetDevice(dev_of(next_retire).dev));
+            const cudaError_t q = cudaEventQuery(s.ev_out);
+            if (q == cudaErrorNotReady) break;
+            CUDA_TRY(q);
+            if (int rc = retire(next_retire++)) return rc;
+        }
+    }
+    if (!keep) while (next_retire < nchunks) if (int rc = retire(next_retire++)) return rc;
+    if (g_timeline && !keep) {
+        fprintf(stderr, "bsw timeline (ms; device times relative to the first chunk's open, host times to the call):\n");
+        for (const std::string& l : tl_lines) fprintf(stderr, "  %s\n", l.c_str());
     }
     if (keep) {
         for (int64_t k = 0; k < nchunks; ++k) {
@@ -747,6 +999,11 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
     std::string why;
     if (validate_params(params, why) != BSW_OK) return fail(BSW_ERR_PARAM, why);
 
+    // One hardware queue per stream the pipeline keeps busy (6 chunk streams + 16 DP streams + the
+    // H2D stream): with the default of 8 connections, streams share queues and a prep kernel of one
+    // chunk waits behind another chunk's result copy.  Only effective if this is the process's
+    // first CUDA call; a caller that initialises CUDA earlier exports the variable itself.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev_avail = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev_avail);
     if (ce != cudaSuccess || ndev_avail < 1)
@@ -785,9 +1042,17 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
         }
         c.sms = prop.multiProcessorCount;
         for (int s = 0; ok && s < NSTREAMS; ++s) {
-            ok = cudaStreamCreateWithFlags(&c.cs[s], cudaStreamNonBlocking) == cudaSuccess;
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            ok = cudaStreamCreateWithPriority(&c.cs[s], cudaStreamNonBlocking, prio_lo) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&c.ev_join[s], cudaEventDisableTiming) == cudaSuccess;
         }
+        if (ok) {
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            ok = cudaStreamCreateWithPriority(&c.h2d, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        }
+        if (ok) setup_partitions(c);
         ok = ok && cudaEventCreate(&c.ev_t0) == cudaSuccess && cudaEventCreate(&c.ev_t1) == cudaSuccess;
         ok = ok && cudaMalloc((void**)&c.d_cells, sizeof(unsigned long long)) == cudaSuccess;
         ok = ok && cudaHostAlloc((void**)&c.h_cells, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
@@ -810,8 +1075,12 @@ void bsw_destroy(bsw_engine* eng)
         for (Slot& s : c.slots) slot_destroy(s);
         for (int s = 0; s < NSTREAMS; ++s) {
             if (c.cs[s]) cudaStreamDestroy(c.cs[s]);
+            if (c.cs_part[s]) cudaStreamDestroy(c.cs_part[s]);
             if (c.ev_join[s]) cudaEventDestroy(c.ev_join[s]);
         }
+        if (c.h2d) cudaStreamDestroy(c.h2d);
+        if (c.g_svc) green_api().destroy(c.g_svc);
+        if (c.g_dp) green_api().destroy(c.g_dp);
         if (c.ev_t0) cudaEventDestroy(c.ev_t0);
         if (c.ev_t1) cudaEventDestroy(c.ev_t1);
         if (c.d_cells) cudaFree(c.d_cells);

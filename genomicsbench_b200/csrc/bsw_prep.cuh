@@ -11,6 +11,12 @@
 //   bsw_pack_pairs   2-bit pack query / reference bytes (16 bases per word) in processing order,
 //                    flag and list the pairs with N (and those outside the packed kernel's domain)
 //   bsw_writeback    unpack the 16-byte results into the caller's SeqPair records (input order)
+//
+// Every kernel here runs in blocks of PREP_BLOCK = 64 threads with little shared memory: they are
+// launched on high-priority streams while DP kernels of earlier chunks fill the SMs to their
+// register / shared-memory limit, and a block this small fits into the room ONE retiring DP block
+// frees (a 256- or 1024-thread block would wait for the DP backlog to drain; BSW_TIMELINE showed
+// the next chunk's preparation stuck behind it for half a millisecond).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -21,6 +27,7 @@
 namespace bsw {
 
 constexpr int LEN_HIST = 1024;        // len2 histogram bins 0..1022, 1023 = everything longer
+constexpr int PREP_BLOCK = 64;        // threads per block of the prep kernels
 
 // Chunk summary: written by bsw_scan_pairs / bsw_pack_pairs (or by the host pass for pageable
 // buffers), read by the host to size buffers and to plan the launches.
@@ -37,13 +44,46 @@ struct ChunkInfo {
     int qmax_all;                                    // longest query of the chunk
     unsigned int hist[LEN_HIST];                     // pairs per len2
 };
+static_assert(sizeof(ChunkInfo) % 16 == 0, "bsw_info_publish copies 16-byte words");
+
+// The chunk summary is reset and handed to the host by two tiny kernels instead of copy-engine
+// transfers: a 4 KB cudaMemcpyAsync queues behind the megabytes of sequence / result traffic of the
+// other chunks (BSW_TIMELINE showed the DP launches of a chunk waiting 0.5 ms for it), stores from an
+// SM into mapped page-locked memory do not.
+__global__ void __launch_bounds__(PREP_BLOCK)
+bsw_info_init(ChunkInfo* __restrict__ info)
+{
+    uint32_t* w = reinterpret_cast<uint32_t*>(info);
+    for (int k = threadIdx.x; k < (int)(sizeof(ChunkInfo) / 4); k += blockDim.x) w[k] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        info->min_r = info->min_q = ~0ull;
+        info->mn[0] = info->mn[1] = info->mn[2] = 0x7fffffff;
+    }
+}
+
+// zeroes the bin table (same reason: a cudaMemsetAsync may be served by a copy engine that is busy)
+__global__ void __launch_bounds__(PREP_BLOCK)
+bsw_zero_words(uint4* __restrict__ p, int n16)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n16; k += gridDim.x * blockDim.x) p[k] = make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(PREP_BLOCK)
+bsw_info_publish(const ChunkInfo* __restrict__ info, ChunkInfo* __restrict__ host_mapped)
+{
+    const uint4* src = reinterpret_cast<const uint4*>(info);
+    uint4* dst = reinterpret_cast<uint4*>(host_mapped);
+    for (int k = threadIdx.x; k < (int)(sizeof(ChunkInfo) / 16); k += blockDim.x) dst[k] = __ldcg(src + k);
+    __threadfence_system();
+}
 
 __device__ __forceinline__ unsigned long long bsw_umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 __device__ __forceinline__ unsigned long long bsw_umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
 // desc[i] = {query byte offset, reference byte offset (both relative to base0_q / base0_r, as
 // signed 32-bit), len2 | len1 << 16, h0}.  info must be zeroed except mn[] = INT_MAX, min_* = ~0.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PREP_BLOCK)
 bsw_scan_pairs(const SeqPair* __restrict__ pairs, int n, long long base0_r, long long base0_q,
                int match, int short_max, int4* __restrict__ desc, ChunkInfo* __restrict__ info)
 {
@@ -82,14 +122,28 @@ bsw_scan_pairs(const SeqPair* __restrict__ pairs, int n, long long base0_r, long
             mn2 = min(mn2, len1); mx2 = max(mx2, len1);
         }
     }
-    atomicMin(&s_u64[0], min_r); atomicMax(&s_u64[1], max_r);
-    atomicMin(&s_u64[2], min_q); atomicMax(&s_u64[3], max_q);
-    atomicAdd(&s_u64[4], nominal); atomicAdd(&s_u64[5], qb); atomicAdd(&s_u64[6], tb);
-    atomicMin(&s_i[0], mn0); atomicMin(&s_i[1], mn1); atomicMin(&s_i[2], mn2);
-    atomicMax(&s_i[3], mx0); atomicMax(&s_i[4], mx1); atomicMax(&s_i[5], mx2);
-    if (bad) atomicAdd(&s_i[6], 1);
-    atomicAdd(&s_i[7], nshort);
-    atomicMax(&s_i[8], qall);
+    // warp reductions first (shuffles), then one shared-memory atomic per warp and value: 64-bit
+    // min / max atomics in shared memory are CAS loops, 256 threads on one address serialise badly
+    const unsigned FULL = 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        min_r = bsw_umin64(min_r, __shfl_xor_sync(FULL, min_r, o)); max_r = bsw_umax64(max_r, __shfl_xor_sync(FULL, max_r, o));
+        min_q = bsw_umin64(min_q, __shfl_xor_sync(FULL, min_q, o)); max_q = bsw_umax64(max_q, __shfl_xor_sync(FULL, max_q, o));
+        nominal += __shfl_xor_sync(FULL, nominal, o); qb += __shfl_xor_sync(FULL, qb, o); tb += __shfl_xor_sync(FULL, tb, o);
+    }
+    mn0 = __reduce_min_sync(FULL, mn0); mn1 = __reduce_min_sync(FULL, mn1); mn2 = __reduce_min_sync(FULL, mn2);
+    mx0 = __reduce_max_sync(FULL, mx0); mx1 = __reduce_max_sync(FULL, mx1); mx2 = __reduce_max_sync(FULL, mx2);
+    bad = __reduce_max_sync(FULL, bad); nshort = __reduce_add_sync(FULL, nshort); qall = __reduce_max_sync(FULL, qall);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&s_u64[0], min_r); atomicMax(&s_u64[1], max_r);
+        atomicMin(&s_u64[2], min_q); atomicMax(&s_u64[3], max_q);
+        atomicAdd(&s_u64[4], nominal); atomicAdd(&s_u64[5], qb); atomicAdd(&s_u64[6], tb);
+        atomicMin(&s_i[0], mn0); atomicMin(&s_i[1], mn1); atomicMin(&s_i[2], mn2);
+        atomicMax(&s_i[3], mx0); atomicMax(&s_i[4], mx1); atomicMax(&s_i[5], mx2);
+        if (bad) atomicAdd(&s_i[6], 1);
+        atomicAdd(&s_i[7], nshort);
+        atomicMax(&s_i[8], qall);
+    }
     __syncthreads();
     for (int k = threadIdx.x; k < LEN_HIST; k += blockDim.x)
         if (s_hist[k]) atomicAdd(&info->hist[k], s_hist[k]);
@@ -143,22 +197,24 @@ __device__ __forceinline__ uint32_t bsw_pack16(const uint8_t* src, int nb, int r
 // the DP kernel later reads descriptors and sequences of neighbouring threads from neighbouring
 // addresses.  The word counts are scanned across the warp, one atomicAdd per sequence kind
 // reserves the output range, then the lanes sweep the concatenated word list (lane -> word, pair
-// found by binary search), so loads stay coalesced for short and long sequences alike.
+// found by binary search), so loads stay coalesced for short and long sequences alike.  The output
+// range is reserved once per block tile (two atomics on the chunk's cursors per block).
 // meta[s] (processing order) gets word offsets; desc[i] (input order) keeps byte offsets.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PREP_BLOCK)
 bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm, int n_sorted,
                const uint8_t* __restrict__ qraw, const uint8_t* __restrict__ rraw, int4* __restrict__ meta,
                uint32_t* __restrict__ qpk, uint32_t* __restrict__ tpk,
                uint32_t* __restrict__ nlist, ChunkInfo* __restrict__ info, int packed16_match)
 {
-    __shared__ uint32_t s_pre[8][2][33];
-    __shared__ uint32_t s_bad[8][32];
-    __shared__ int4 s_desc[8][32];
+    constexpr int NW = PREP_BLOCK / 32;
+    __shared__ uint32_t s_pre[NW][2][33];
+    __shared__ uint32_t s_bad[NW][32];
+    __shared__ int4 s_desc[NW][32];
+    __shared__ uint32_t s_tot[NW][2], s_base[NW][2];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int nwarps = gridDim.x * (blockDim.x >> 5);
-    for (int base = (blockIdx.x * (blockDim.x >> 5) + wib) * 32; base < n_sorted; base += nwarps * 32) {
-        const int s = base + lane;
+    for (int tile = blockIdx.x * PREP_BLOCK; tile < n_sorted; tile += gridDim.x * PREP_BLOCK) {
+        const int s = tile + wib * 32 + lane;
         int4 d = make_int4(0, 0, 0, 0);
         int len2 = 0, len1 = 0, pi = 0;
         if (s < n_sorted) {
@@ -176,9 +232,18 @@ bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm,
             if (lane >= o) { pq += a; pt += b; }
         }
         const uint32_t totq = __shfl_sync(FULL, pq, 31), tott = __shfl_sync(FULL, pt, 31);
-        uint32_t bq = 0, bt = 0;
-        if (lane == 0) { bq = atomicAdd(&info->qcursor, totq); bt = atomicAdd(&info->tcursor, tott); }
-        bq = __shfl_sync(FULL, bq, 0); bt = __shfl_sync(FULL, bt, 0);
+        if (lane == 0) { s_tot[wib][0] = totq; s_tot[wib][1] = tott; }
+        __syncthreads();
+        if (threadIdx.x < 2) {                      // thread 0: query words, thread 1: reference words
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) { s_base[k][threadIdx.x] = sum; sum += s_tot[k][threadIdx.x]; }
+            const uint32_t b0 = atomicAdd(threadIdx.x ? &info->tcursor : &info->qcursor, sum);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) s_base[k][threadIdx.x] += b0;
+        }
+        __syncthreads();
+        const uint32_t bq = s_base[wib][0], bt = s_base[wib][1];
         s_pre[wib][0][lane + 1] = pq; s_pre[wib][1][lane + 1] = pt;
         if (lane == 0) { s_pre[wib][0][0] = 0; s_pre[wib][1][0] = 0; }
         s_bad[wib][lane] = 0;
@@ -212,7 +277,7 @@ bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm,
             meta[s] = make_int4((int)(bq + pq - nq), (int)(bt + pt - nt), d.z, d.w | (has_n ? BSW_META_NFLAG : 0));
             if (has_n) { nlist[atomicAdd(&info->n_nlist, 1u)] = (uint32_t)pi; atomicMax(&info->qmax_n, len2); }
         }
-        __syncwarp();
+        __syncthreads();                            // s_tot / s_base / s_desc are reused by the next tile
     }
 }
 
@@ -233,7 +298,7 @@ __device__ __forceinline__ uint32_t bsw_bucket_of(const BucketKey& K, const int4
 
 // rank[i] = arrival order of pair i inside its bin; bins[] accumulates the bin sizes; pairs whose
 // query is too long for the short kernel are listed for the warp-per-pair kernel instead
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PREP_BLOCK)
 bsw_bucket_count(const int4* __restrict__ desc, int n, const __grid_constant__ BucketKey K,
                  uint32_t* __restrict__ bins, uint32_t* __restrict__ rank,
                  uint32_t* __restrict__ llist, ChunkInfo* __restrict__ info)
@@ -245,22 +310,30 @@ bsw_bucket_count(const int4* __restrict__ desc, int n, const __grid_constant__ B
     }
 }
 
-// Exclusive prefix sum of the bin table in two levels.  bsw_bucket_scan_tiles: every block scans one
-// tile of 1024 bins in place and leaves the tile total; bsw_bucket_scan_totals: one block scans the
-// (<= 1024) tile totals; the scatter adds the two.
+// Exclusive prefix sum of the bin table in two levels, one launch.  Every block scans one tile of
+// 1024 bins in place (64 threads x 16 bins) and leaves the tile total; the block that finishes last
+// (a ticket counter behind the totals, zeroed with the bin table) scans the <= 256 tile totals.
+// The scatter adds the two levels.
 constexpr int SCAN_TILE = 1024;
+constexpr int SCAN_MAX_TILES = 256;
 
-__global__ void __launch_bounds__(256)
-bsw_bucket_scan_tiles(uint32_t* __restrict__ bins, int nbins, uint32_t* __restrict__ totals)
+__global__ void __launch_bounds__(PREP_BLOCK)
+bsw_bucket_scan(uint32_t* __restrict__ bins, int nbins, uint32_t* __restrict__ totals, unsigned int* __restrict__ ticket)
 {
-    __shared__ uint32_t s_warp[8];
+    constexpr int PER = SCAN_TILE / PREP_BLOCK;         // 16 bins per thread
+    __shared__ uint32_t s_warp[PREP_BLOCK / 32];
+    __shared__ bool s_last;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
-    uint32_t v[4];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * PER;
+    uint32_t v[PER];
+    uint32_t mine = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = base + k < nbins ? bins[base + k] : 0u;
-    const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+    for (int k = 0; k < PER; k += 4) {
+        const uint4 q = base + k < nbins ? *reinterpret_cast<const uint4*>(bins + base + k) : make_uint4(0, 0, 0, 0);   // nbins is a power of two >= 1; the table is padded
+        v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
+        mine += q.x + q.y + q.z + q.w;
+    }
     uint32_t inc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -273,30 +346,52 @@ bsw_bucket_scan_tiles(uint32_t* __restrict__ bins, int nbins, uint32_t* __restri
     for (int k = 0; k < wib; ++k) wbase += s_warp[k];
     uint32_t run = wbase + inc - mine;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (base + k < nbins) bins[base + k] = run;
-        run += v[k];
+    for (int k = 0; k < PER; ++k) {
+        const uint32_t t = v[k];
+        v[k] = run;
+        run += t;
     }
-    if (threadIdx.x == 255) totals[blockIdx.x] = run;
-}
-
-__global__ void __launch_bounds__(1024)
-bsw_bucket_scan_totals(uint32_t* __restrict__ totals, int ntiles)
-{
-    __shared__ uint32_t s_part[1024];
-    const uint32_t mine = (int)threadIdx.x < ntiles ? totals[threadIdx.x] : 0u;
-    s_part[threadIdx.x] = mine;
+#pragma unroll
+    for (int k = 0; k < PER; k += 4)
+        if (base + k < nbins) *reinterpret_cast<uint4*>(bins + base + k) = make_uint4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+    if (threadIdx.x == PREP_BLOCK - 1) {
+        totals[blockIdx.x] = run;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {            // Hillis-Steele inclusive scan
-        const uint32_t v = (int)threadIdx.x >= o ? s_part[threadIdx.x - o] : 0u;
-        __syncthreads();
-        s_part[threadIdx.x] += v;
-        __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // second level: exclusive scan of the tile totals, 4 per thread
+    const int ntiles = (int)gridDim.x;
+    uint32_t t4[4];
+    uint32_t sum4 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x * 4 + k;
+        t4[k] = idx < ntiles ? __ldcg(totals + idx) : 0u;
+        sum4 += t4[k];
     }
-    if ((int)threadIdx.x < ntiles) totals[threadIdx.x] = s_part[threadIdx.x] - mine;
+    uint32_t inc2 = sum4;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, inc2, o);
+        if (lane >= o) inc2 += y;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[wib] = inc2;
+    __syncthreads();
+    uint32_t run2 = inc2 - sum4;
+    for (int k = 0; k < wib; ++k) run2 += s_warp[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x * 4 + k;
+        if (idx < ntiles) totals[idx] = run2;
+        run2 += t4[k];
+    }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PREP_BLOCK)
 bsw_bucket_scatter(const int4* __restrict__ desc, int n, const __grid_constant__ BucketKey K,
                    const uint32_t* __restrict__ bins, const uint32_t* __restrict__ totals,
                    const uint32_t* __restrict__ rank, uint32_t* __restrict__ perm)
@@ -311,7 +406,7 @@ bsw_bucket_scatter(const int4* __restrict__ desc, int n, const __grid_constant__
 
 // res[i] (8 x int16) -> the six int32 result fields of the caller's record i (score@44 tle@48
 // gtle@52 qle@56 gscore@60 max_off@64, bandedSWA.h:91-100); pairs may be host-mapped memory.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PREP_BLOCK)
 bsw_writeback(const int4* __restrict__ res, int n, SeqPair* __restrict__ pairs)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

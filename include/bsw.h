@@ -93,7 +93,8 @@ typedef struct bsw_stats {
     int64_t h2d_bytes, d2h_bytes;
     int32_t kernel_launches;     /* kernels launched by the last call (prep + DP + write-back) */
     int32_t n_short, n_long;     /* pairs routed to the thread-per-pair / warp-per-pair kernel */
-    int32_t reserved[5];
+    int32_t partitioned;         /* 1: the call ran with the SMs split into a service and a DP partition (PCIe-bound batch) */
+    int32_t reserved[4];
 } bsw_stats;
 
 typedef struct bsw_engine bsw_engine;
