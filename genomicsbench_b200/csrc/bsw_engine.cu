@@ -39,7 +39,7 @@ namespace {
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
 constexpr int SHORT_MAX_QLEN = 824;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
 constexpr int NSTREAMS = 16;              // DP compute streams per device (one shared-memory class each, run concurrently)
-constexpr int NSLOTS = 6;                 // chunks in flight per device (records ahead / prepare / compute / drain, + slack before a slot is reused)
+constexpr int NSLOTS = 8;                 // chunks in flight per device (records ahead / prepare / compute / drain, + slack before a slot is reused)
 constexpr int64_t CHUNK_EXTEND = 1 << 18; // largest chunk of bsw_extend (overlap vs bucketing quality)
 constexpr int64_t CHUNK_MIN = 1 << 15;    // the last chunks of a batch shrink towards this (short pipeline drain)
 constexpr int64_t CHUNK_STAGE = 1 << 20;  // pairs per chunk of bsw_stage (resident: best bucketing)
@@ -890,14 +890,14 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
         return BSW_OK;
     };
 
-    // Per iteration k: records (and the speculative sequence copy) of chunk k + 2 ndev go out (direct
+    // Per iteration k: records (and the speculative sequence copy) of chunk k + 3 ndev go out (direct
     // route) so the copy engine never waits for the host; chunk k gets its prep kernels and DP launches; chunk
     // k - ndev drains (byte kernels, results out).  Chunks retire (results on the host; staged route:
     // second host pass) as soon as their D2H has completed, without blocking -- the host only waits
     // for a chunk when the slot it occupies is needed again, NSLOTS chunks later, so that a DP that
     // runs long never keeps the host from feeding the copy engine.
     const int lag = ndev;
-    const int ahead = direct && !keep ? 2 * ndev : ndev;     // chunks opened (records + speculative sequence copy) ahead of k
+    const int ahead = direct && !keep ? 3 * ndev : ndev;     // chunks opened (records + speculative sequence copy) ahead of k
     int64_t next_retire = 0;
     for (int64_t k = 0; k < std::min<int64_t>(ahead, nchunks); ++k) if (int rc = open(k)) return rc;
     for (int64_t k = 0; k < nchunks + lag; ++k) {

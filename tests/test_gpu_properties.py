@@ -94,6 +94,41 @@ def test_direct_route_equals_staged_route(lib, oracle):
         assert np.array_equal(results_matrix(pb), results_matrix(a)[perm])
 
 
+def test_pcie_bound_batch_runs_partitioned(lib, oracle):
+    """A batch whose DP is shorter than its transfer (short pairs) runs with the SMs split into a
+    service partition (copies, scan, bucket, pack, write-back) and a DP partition, small chunks, one
+    FIFO H2D stream and speculative sequence copies.  Same results as the staged route and the
+    oracle; records in reverse and in random order (the speculative range then misses and the
+    scanned range is copied instead) give the same results too."""
+    cfg = lib.gen_named_config("short8")
+    pairs, ref, qer = lib.gen_pairs(cfg, 0, 400_000)
+    want = pairs[:20_000].copy()
+    oracle.batch(make_params(), want, ref, qer, 100)
+    with lib.Engine() as eng:
+        a = pairs.copy()
+        eng.extend(a, ref, qer, 100)                                 # pageable: staged route
+        assert np.array_equal(results_matrix(a[:20_000]), results_matrix(want))
+        pp, pr, pq = lib.pinned_copy(pairs), lib.pinned_copy(ref), lib.pinned_copy(qer)
+        eng.extend(pp, pr, pq, 100)
+        st = eng.stats()
+        assert st["partitioned"] == 1, "green-context SM partitions unavailable on this box?"
+        assert np.array_equal(results_matrix(pp), results_matrix(a))
+        assert st["h2d_bytes"] < 1.02 * (pairs.nbytes + ref.nbytes + qer.nbytes)     # nothing copied twice
+        for order in (np.arange(len(pairs))[::-1].copy(), np.random.default_rng(11).permutation(len(pairs))):
+            pb = lib.pinned_copy(pairs[order])
+            eng.extend(pb, pr, pq, 100)
+            assert np.array_equal(results_matrix(pb), results_matrix(a)[order])
+        # a compute-bound batch on the same engine goes back to whole-device streams
+        cfg2 = lib.gen_named_config("long16")
+        p2, r2, q2 = lib.gen_pairs(cfg2, 0, 140_000)
+        b = p2.copy()
+        eng.extend(b, r2, q2, 100)
+        pp2, pr2, pq2 = lib.pinned_copy(p2), lib.pinned_copy(r2), lib.pinned_copy(q2)
+        eng.extend(pp2, pr2, pq2, 100)
+        assert eng.stats()["partitioned"] == 0
+        assert np.array_equal(results_matrix(pp2), results_matrix(b))
+
+
 def test_sparse_sequence_buffers_are_read_in_place(lib, oracle):
     """The reference loader's layout (main_banded.cpp:55-58,244-246: one 2048-byte slot per
     reference, 256 per query): on the direct route the engine must not DMA the whole slots."""
