@@ -17,13 +17,14 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 
-from ._lib import (ABI, BSW_ZDROP_SCALAR, BSW_ZDROP_VECTOR, RESULT_FIELDS, SEQPAIR_DTYPE, BswGenConfig,
-                   BswParams, BswStats, LIB_PATH, load_library, ptr)
+from ._lib import (ABI, ALNREG_DTYPE, ALNREG_FIELDS, BSW_ZDROP_SCALAR, BSW_ZDROP_VECTOR, CHAIN_DTYPE, RESULT_FIELDS,
+                   SEED_DTYPE, SEQPAIR_DTYPE, BswChainOpt, BswGenConfig, BswParams, BswStats, LIB_PATH, load_library, ptr)
 
 __all__ = [
     "BandedPairWiseSW", "Engine", "BswError", "SEQPAIR_DTYPE", "RESULT_FIELDS", "default_params",
     "gen_named_config", "gen_pairs", "bucket_order", "partition", "read_pairs_file",
     "write_pairs_file", "load_library", "NAMED_CONFIGS", "pinned_empty", "pinned_copy",
+    "SEED_DTYPE", "CHAIN_DTYPE", "ALNREG_DTYPE", "ALNREG_FIELDS",
 ]
 
 NAMED_CONFIGS = {"small": 0, "short8": 1, "long16": 2, "large": 3, "sweep": 4}
@@ -105,6 +106,31 @@ class Engine:
         self._rc(self._lib.bsw_extend_retry(self._h, ptr(pairs), ptr(seq_ref), ptr(seq_qer), len(pairs), w,
                                             max_try, ptr(prev) if prev is not None else None, ptr(band)))
         return band
+
+    def chain_window(self, w: int, l_pac: int, seeds: np.ndarray, l_query: int) -> tuple:
+        """Reference window [rmax0, rmax1) of a chain of seeds (tools/bwa/bwamem.c:643-659)."""
+        seeds = np.ascontiguousarray(seeds, dtype=SEED_DTYPE)
+        r0, r1 = C.c_int64(0), C.c_int64(0)
+        self._rc(self._lib.bsw_chain_window(C.byref(self.params), w, l_pac, ptr(seeds), len(seeds), l_query,
+                                            C.byref(r0), C.byref(r1)))
+        return int(r0.value), int(r1.value)
+
+    def extend_chains(self, chains: np.ndarray, seeds: np.ndarray, query: np.ndarray, ref: np.ndarray, w: int,
+                      pen_clip5: int = 5, pen_clip3: int = 5, max_band_try: int = 2):
+        """mem_chain2aln for a batch of chains (tools/bwa/bwamem.c:632-822): seed -> left / right pair
+        construction, band-doubling retry, local-vs-to-end decision.  chains = CHAIN_DTYPE, seeds = SEED_DTYPE;
+        returns (regs ALNREG_DTYPE[len(seeds)], count int32[len(chains)]): the regions of chain c are
+        regs[chains[c].seed_first : + count[c]] in the order the reference pushes them."""
+        chains = np.ascontiguousarray(chains, dtype=CHAIN_DTYPE)
+        seeds = np.ascontiguousarray(seeds, dtype=SEED_DTYPE)
+        if query.dtype != np.uint8 or ref.dtype != np.uint8 or not query.flags.c_contiguous or not ref.flags.c_contiguous:
+            raise ValueError("query / ref must be contiguous uint8 arrays (one base code per byte)")
+        regs = np.zeros(max(len(seeds), 1), dtype=ALNREG_DTYPE)
+        count = np.zeros(max(len(chains), 1), dtype=np.int32)
+        opt = BswChainOpt(w, pen_clip5, pen_clip3, max_band_try)
+        self._rc(self._lib.bsw_extend_chains(self._h, ptr(chains), len(chains), ptr(seeds), ptr(query), ptr(ref),
+                                             C.byref(opt), ptr(regs), ptr(count)))
+        return regs[:len(seeds)], count[:len(chains)]
 
     def stage(self, pairs, seq_ref, seq_qer, w: int) -> None:
         _check_arrays(pairs, seq_ref, seq_qer)

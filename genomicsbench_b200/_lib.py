@@ -57,6 +57,19 @@ class BswStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+# include/bsw.h: bsw_seed (= mem_seed_t), bsw_chain, bsw_alnreg, bsw_chain_opt
+SEED_DTYPE = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4"), ("score", "<i4"), ("reserved", "<i4")])
+CHAIN_DTYPE = np.dtype([("seed_first", "<i8"), ("n_seeds", "<i4"), ("l_query", "<i4"), ("query_off", "<i8"),
+                        ("rmax0", "<i8"), ("rmax1", "<i8"), ("ref_off", "<i8")])
+ALNREG_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("score", "<i4"), ("truesc", "<i4"),
+                         ("w", "<i4"), ("seedcov", "<i4"), ("seedlen0", "<i4"), ("reserved", "<i4")])
+ALNREG_FIELDS = ("rb", "re", "qb", "qe", "score", "truesc", "w", "seedcov", "seedlen0")
+
+
+class BswChainOpt(C.Structure):
+    _fields_ = [("w", C.c_int32), ("pen_clip5", C.c_int32), ("pen_clip3", C.c_int32), ("max_band_try", C.c_int32)]
+
+
 class BswGenConfig(C.Structure):
     _fields_ = [
         ("seed", C.c_uint64), ("n_pairs", C.c_int64),
@@ -78,6 +91,9 @@ ABI = [
     ("bsw_default_params", None, [C.POINTER(BswParams)]),
     ("bsw_extend", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32]),
     ("bsw_extend_retry", C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    ("bsw_chain_window", C.c_int, [C.POINTER(BswParams), C.c_int32, C.c_int64, _P, C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("bsw_extend_chains", C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     ("bsw_host_alloc", _P, [C.c_size_t]),
     ("bsw_host_free", None, [_P]),
     ("bsw_host_register", C.c_int, [_P, C.c_size_t]),

@@ -1,0 +1,286 @@
+// bsw_chain.inl -- seed -> pair construction and the local / to-end decision of the aligner around the
+// extension kernels; included by bsw_engine.cu inside extern "C".
+//
+// Stands in for the body of mem_chain2aln (tools/bwa/bwamem.c:632-822).  The reference walks the
+// seeds of one chain sequentially and calls ksw_extend2 twice per seed; here every round takes the
+// next surviving seed of EVERY chain, builds all left-flank pairs (reversed copies) and runs them as
+// one bsw_extend_retry batch on the GPU, applies the local / to-end decision, then does the same for
+// the right flanks (which read the caller's read and window bytes in place: no copy).  The seeds of
+// one chain stay sequential because the containment test (:667-700) looks at the alignments already
+// made from that chain.
+namespace {
+
+inline int chain_max_gap(const bsw_params& p, int w, int qlen)                  // cal_max_gap, bwamem.c:620-628
+{
+    const int l_del = (int)((double)(qlen * p.match - p.o_del) / p.e_del + 1.);
+    const int l_ins = (int)((double)(qlen * p.match - p.o_ins) / p.e_ins + 1.);
+    int l = l_del > l_ins ? l_del : l_ins;
+    l = l > 1 ? l : 1;
+    return l < (w << 1) ? l : (w << 1);
+}
+
+// ksw_extend2 over an empty target (tlen == 0: the row loop never runs, ksw.c:413-473) inside the
+// MAX_BAND_TRY loop: score = h0, every end = 0, gscore = -1, max_off = 0
+inline void chain_empty_target(int h0, int w, int max_try, int prev0, SeqPair& r, int& band)
+{
+    int score = prev0;
+    for (int t = 0; t < max_try; ++t) {
+        const int prev = score;
+        band = w << t;
+        score = h0;
+        if (score == prev || 0 < (band >> 1) + (band >> 2)) break;
+    }
+    r.score = score; r.qle = 0; r.tle = 0; r.gtle = 0; r.gscore = -1; r.max_off = 0;
+}
+
+struct ChainRun {
+    std::vector<uint64_t> srt;      // score << 32 | index, ascending (bwamem.c:661-665)
+    int k = -1;                     // next position in srt, walking down
+};
+
+struct ChainCand {                  // one seed being extended in the current round
+    int64_t chain; int seed;        // seed index inside the chain
+    int lpair = -1, rpair = -1;     // positions in the round's left / right batch, -1 = none
+    int aw0, aw1;
+};
+
+} // namespace
+
+int bsw_chain_window(const bsw_params* p, int32_t w, int64_t l_pac, const bsw_seed* seeds, int32_t n,
+                     int32_t l_query, int64_t* rmax0, int64_t* rmax1)
+{
+    if (!p || !seeds || n < 1 || !rmax0 || !rmax1 || p->e_del < 1 || p->e_ins < 1) return BSW_ERR_PARAM;
+    int64_t r0 = l_pac << 1, r1 = 0;
+    for (int i = 0; i < n; ++i) {                                               // bwamem.c:643-652
+        const bsw_seed& t = seeds[i];
+        const int64_t b = t.rbeg - (t.qbeg + chain_max_gap(*p, w, t.qbeg));
+        const int64_t e = t.rbeg + t.len + ((l_query - t.qbeg - t.len) + chain_max_gap(*p, w, l_query - t.qbeg - t.len));
+        r0 = r0 < b ? r0 : b;
+        r1 = r1 > e ? r1 : e;
+    }
+    r0 = r0 > 0 ? r0 : 0;
+    r1 = r1 < (l_pac << 1) ? r1 : (l_pac << 1);
+    if (r0 < l_pac && l_pac < r1) {                                             // :655-658: stay on the seeds' strand
+        if (seeds[0].rbeg < l_pac) r1 = l_pac;
+        else r0 = l_pac;
+    }
+    *rmax0 = r0; *rmax1 = r1;
+    return BSW_OK;
+}
+
+int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains, const bsw_seed* seeds,
+                      const uint8_t* query, const uint8_t* ref, const bsw_chain_opt* opt,
+                      bsw_alnreg* out, int32_t* out_count)
+{
+    if (!eng) return BSW_ERR_PARAM;
+    eng->err.clear();
+    if (n_chains < 0 || !opt || (n_chains > 0 && (!chains || !seeds || !query || !ref || !out || !out_count))) {
+        eng->err = "bsw_extend_chains: bad arguments";
+        return BSW_ERR_PARAM;
+    }
+    const int w = opt->w, max_try = opt->max_band_try;
+    if (w < 0 || max_try < 1 || max_try > 8) { eng->err = "bsw_extend_chains: w >= 0 and max_band_try in 1..8"; return BSW_ERR_PARAM; }
+    if (opt->pen_clip5 != eng->p.end_bonus || opt->pen_clip3 != eng->p.end_bonus) {
+        eng->err = "bsw_extend_chains: pen_clip5 and pen_clip3 must equal the engine's end_bonus "
+                   "(ksw_extend2 receives them as end_bonus, bwamem.c:746,793)";
+        return BSW_ERR_PARAM;
+    }
+    const bsw_params& P = eng->p;
+    std::vector<ChainRun> run((size_t)n_chains);
+    for (int64_t c = 0; c < n_chains; ++c) {
+        const bsw_chain& ch = chains[c];
+        out_count[c] = 0;
+        if (ch.n_seeds < 0 || ch.l_query < 1 || ch.rmax1 < ch.rmax0) { eng->err = "bsw_extend_chains: malformed chain"; return BSW_ERR_PARAM; }
+        ChainRun& R = run[(size_t)c];
+        R.srt.resize((size_t)ch.n_seeds);
+        for (int i = 0; i < ch.n_seeds; ++i) {
+            const bsw_seed& s = seeds[ch.seed_first + i];
+            if (s.len < 1 || s.qbeg < 0 || s.qbeg + s.len > ch.l_query || s.score < 1 || s.rbeg < ch.rmax0 ||
+                s.rbeg + s.len > ch.rmax1) {
+                eng->err = "bsw_extend_chains: seed outside its read or reference window";
+                return BSW_ERR_PARAM;
+            }
+            R.srt[(size_t)i] = (uint64_t)(uint32_t)s.score << 32 | (uint32_t)i;
+        }
+        std::sort(R.srt.begin(), R.srt.end());
+        R.k = ch.n_seeds - 1;
+    }
+
+    bsw_stats total;
+    memset(&total, 0, sizeof(total));
+    std::vector<ChainCand> cand;
+    std::vector<SeqPair> lp, rp;
+    std::vector<uint8_t> lq, lr;
+    std::vector<int32_t> band, prev;
+    auto add_stats = [&]() {
+        const bsw_stats& s = eng->stats;
+        total.pairs += s.pairs; total.cells_nominal += s.cells_nominal; total.cells_effective += s.cells_effective;
+        total.kernel_launches += s.kernel_launches; total.h2d_bytes += s.h2d_bytes; total.d2h_bytes += s.d2h_bytes;
+        total.ms_kernel += s.ms_kernel; total.ms_pack += s.ms_pack; total.ms_scatter += s.ms_scatter;
+        total.n_short += s.n_short; total.n_long += s.n_long;
+    };
+
+    for (;;) {
+        // ---- next surviving seed of every chain (containment test, bwamem.c:667-700) ------------
+        cand.clear();
+        for (int64_t c = 0; c < n_chains; ++c) {
+            const bsw_chain& ch = chains[c];
+            ChainRun& R = run[(size_t)c];
+            const bsw_seed* S = seeds + ch.seed_first;
+            bsw_alnreg* av = out + ch.seed_first;
+            while (R.k >= 0) {
+                const int k = R.k;
+                const bsw_seed& s = S[(uint32_t)R.srt[(size_t)k]];
+                int i;
+                for (i = 0; i < out_count[c]; ++i) {
+                    const bsw_alnreg& p = av[i];
+                    if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
+                    if (s.len - p.seedlen0 > .1 * ch.l_query) continue;
+                    int qd = s.qbeg - p.qb; int64_t rd = s.rbeg - p.rb;
+                    int max_gap = chain_max_gap(P, w, qd < rd ? qd : (int)rd);
+                    int ww = max_gap < p.w ? max_gap : p.w;
+                    if (qd - rd < ww && rd - qd < ww) break;
+                    qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
+                    max_gap = chain_max_gap(P, w, qd < rd ? qd : (int)rd);
+                    ww = max_gap < p.w ? max_gap : p.w;
+                    if (qd - rd < ww && rd - qd < ww) break;
+                }
+                if (i < out_count[c]) {
+                    for (i = k + 1; i < ch.n_seeds; ++i) {
+                        if (R.srt[(size_t)i] == 0) continue;
+                        const bsw_seed& t = S[(uint32_t)R.srt[(size_t)i]];
+                        if (t.len < s.len * .95) continue;
+                        if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+                        if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+                    }
+                    if (i == ch.n_seeds) { R.srt[(size_t)k] = 0; --R.k; continue; }     // contained: no extension
+                }
+                ChainCand cd;
+                cd.chain = c; cd.seed = (int)(uint32_t)R.srt[(size_t)k]; cd.aw0 = cd.aw1 = w;
+                cand.push_back(cd);
+                break;
+            }
+        }
+        if (cand.empty()) break;
+
+        // ---- left flanks: reversed query prefix and reference flank, h0 = len * a (:709-753) -----
+        lp.clear();
+        size_t qbytes = 0, rbytes = 0;
+        for (ChainCand& cd : cand) {
+            const bsw_chain& ch = chains[cd.chain];
+            const bsw_seed& s = seeds[ch.seed_first + cd.seed];
+            bsw_alnreg& a = out[ch.seed_first + out_count[cd.chain]];
+            memset(&a, 0, sizeof(a));
+            a.w = w; a.score = a.truesc = -1;
+            const int64_t tmp = s.rbeg - ch.rmax0;
+            if (s.qbeg > 0 && tmp > 0) {
+                SeqPair sp;
+                memset(&sp, 0, sizeof(sp));
+                sp.idq = (int64_t)qbytes; sp.idr = (int64_t)rbytes; sp.id = (int64_t)lp.size();
+                sp.len2 = s.qbeg; sp.len1 = (int32_t)std::min<int64_t>(tmp, 0x7fffffff); sp.h0 = s.len * P.match;
+                if (tmp > 32767) { eng->err = "bsw_extend_chains: left reference flank longer than 32767"; return BSW_ERR_DOMAIN; }
+                cd.lpair = (int)lp.size();
+                lp.push_back(sp);
+                qbytes += (size_t)s.qbeg; rbytes += (size_t)tmp;
+            }
+        }
+        if (!lp.empty()) {
+            lq.resize(qbytes + 64); lr.resize(rbytes + 64);
+            eng->pool->for_range((int64_t)cand.size(), 256, [&](int64_t b, int64_t e, int) {
+                for (int64_t x = b; x < e; ++x) {
+                    const ChainCand& cd = cand[(size_t)x];
+                    if (cd.lpair < 0) continue;
+                    const bsw_chain& ch = chains[cd.chain];
+                    const bsw_seed& s = seeds[ch.seed_first + cd.seed];
+                    const SeqPair& sp = lp[(size_t)cd.lpair];
+                    const uint8_t* q = query + ch.query_off;
+                    const uint8_t* r = ref + ch.ref_off;
+                    uint8_t* dq = lq.data() + sp.idq; uint8_t* dr = lr.data() + sp.idr;
+                    for (int i = 0; i < s.qbeg; ++i) dq[i] = q[s.qbeg - 1 - i];
+                    const int64_t tmp = s.rbeg - ch.rmax0;
+                    for (int64_t i = 0; i < tmp; ++i) dr[i] = r[tmp - 1 - i];
+                }
+            });
+            band.assign(lp.size(), w);
+            if (int rc = bsw_extend_retry(eng, lp.data(), lr.data(), lq.data(), (int64_t)lp.size(), w, max_try, nullptr, band.data()))
+                return rc;
+            add_stats();
+        }
+        for (ChainCand& cd : cand) {
+            const bsw_chain& ch = chains[cd.chain];
+            const bsw_seed& s = seeds[ch.seed_first + cd.seed];
+            bsw_alnreg& a = out[ch.seed_first + out_count[cd.chain]];
+            if (s.qbeg > 0) {
+                SeqPair r;
+                if (cd.lpair >= 0) { r = lp[(size_t)cd.lpair]; cd.aw0 = band[(size_t)cd.lpair]; }
+                else chain_empty_target(s.len * P.match, w, max_try, -1, r, cd.aw0);
+                a.score = r.score;
+                if (r.gscore <= 0 || r.gscore <= a.score - opt->pen_clip5) {    // local extension (:755-758)
+                    a.qb = s.qbeg - r.qle; a.rb = s.rbeg - r.tle;
+                    a.truesc = a.score;
+                } else {                                                        // to-end extension (:759-761)
+                    a.qb = 0; a.rb = s.rbeg - r.gtle;
+                    a.truesc = r.gscore;
+                }
+            } else { a.score = a.truesc = s.len * P.match; a.qb = 0; a.rb = s.rbeg; }       // :763
+        }
+
+        // ---- right flanks: read in place, h0 = the left score (:765-800) -------------------------
+        rp.clear(); prev.clear();
+        for (ChainCand& cd : cand) {
+            const bsw_chain& ch = chains[cd.chain];
+            const bsw_seed& s = seeds[ch.seed_first + cd.seed];
+            const bsw_alnreg& a = out[ch.seed_first + out_count[cd.chain]];
+            if (s.qbeg + s.len == ch.l_query) continue;
+            const int qe = s.qbeg + s.len;
+            const int64_t re = s.rbeg + s.len - ch.rmax0;
+            const int64_t tlen = ch.rmax1 - ch.rmax0 - re;
+            if (tlen <= 0) continue;
+            if (tlen > 32767) { eng->err = "bsw_extend_chains: right reference flank longer than 32767"; return BSW_ERR_DOMAIN; }
+            SeqPair sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.idq = ch.query_off + qe; sp.idr = ch.ref_off + re; sp.id = (int64_t)rp.size();
+            sp.len2 = ch.l_query - qe; sp.len1 = (int32_t)tlen; sp.h0 = a.score;
+            cd.rpair = (int)rp.size();
+            rp.push_back(sp); prev.push_back(a.score);
+        }
+        if (!rp.empty()) {
+            band.assign(rp.size(), w);
+            if (int rc = bsw_extend_retry(eng, rp.data(), ref, query, (int64_t)rp.size(), w, max_try, prev.data(), band.data()))
+                return rc;
+            add_stats();
+        }
+        for (ChainCand& cd : cand) {
+            const bsw_chain& ch = chains[cd.chain];
+            const bsw_seed* S = seeds + ch.seed_first;
+            const bsw_seed& s = S[cd.seed];
+            bsw_alnreg& a = out[ch.seed_first + out_count[cd.chain]];
+            if (s.qbeg + s.len != ch.l_query) {
+                const int qe = s.qbeg + s.len, sc0 = a.score;
+                const int64_t re = s.rbeg + s.len - ch.rmax0;
+                SeqPair r;
+                if (cd.rpair >= 0) { r = rp[(size_t)cd.rpair]; cd.aw1 = band[(size_t)cd.rpair]; }
+                else chain_empty_target(sc0, w, max_try, sc0, r, cd.aw1);
+                a.score = r.score;
+                if (r.gscore <= 0 || r.gscore <= a.score - opt->pen_clip3) {    // :802-805
+                    a.qe = qe + r.qle; a.re = ch.rmax0 + re + r.tle;
+                    a.truesc += a.score - sc0;
+                } else {                                                        // :806-808
+                    a.qe = ch.l_query; a.re = ch.rmax0 + re + r.gtle;
+                    a.truesc += r.gscore - sc0;
+                }
+            } else { a.qe = ch.l_query; a.re = s.rbeg + s.len; }                // :810
+            a.seedcov = 0;                                                      // :812-818
+            for (int i = 0; i < ch.n_seeds; ++i) {
+                const bsw_seed& t = S[i];
+                if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
+            }
+            a.w = cd.aw0 > cd.aw1 ? cd.aw0 : cd.aw1;
+            a.seedlen0 = s.len;
+            ++out_count[cd.chain];
+            --run[(size_t)cd.chain].k;
+        }
+    }
+    eng->stats = total;
+    return BSW_OK;
+}

@@ -1161,6 +1161,8 @@ int bsw_extend_retry(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, co
     return BSW_OK;
 }
 
+#include "bsw_chain.inl"
+
 // ------------------------------------------------------------------------------------------
 // resident form: stage (host -> HBM, packed + bucketed), run (DP kernels only, repeatable),
 // fetch (results -> SeqPair[])

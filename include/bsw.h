@@ -128,6 +128,50 @@ int bsw_extend_retry(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref,
                      const uint8_t* seq_qer, int64_t n_pairs, int32_t w, int32_t max_try,
                      const int32_t* prev_score, int32_t* band_used);
 
+/* ---- (f.3) seed -> pair construction and the local / to-end decision --------
+ * replaces: the body of mem_chain2aln, tools/bwa/bwamem.c:632-822 -- for every seed of a chain, in
+ * the reference's order (by score, :661-665) and with its containment test (:667-700): the left
+ * extension over the REVERSED query prefix and reference flank with h0 = len * match (:709-753),
+ * the local-vs-to-end decision against pen_clip5 (:755-761), the right extension with h0 = the left
+ * score (:765-800), its decision against pen_clip3 (:802-808), seedcov / w / seedlen0 (:812-822).
+ * Batched over chains: round r extends the r-th surviving seed of every chain in two
+ * bsw_extend_retry calls (all left flanks, then all right flanks); the containment test makes the
+ * seeds of ONE chain sequential, chains are independent.
+ *
+ * bsw_seed = mem_seed_t (bwamem.c:168-172); coordinates are the reference's: rbeg in [0, 2 l_pac)
+ * (forward strand, then the reverse complement), qbeg on the read.  A chain names its read
+ * (query + query_off, l_query codes 0-4) and its reference window [rmax0, rmax1) -- what
+ * bns_fetch_seq returned (bwamem.c:660) -- as ref + ref_off.  bsw_chain_window computes that
+ * window (:643-659); the caller intersects it with the contig as bns_fetch_seq does
+ * (bntseq.c:436-444) and fetches the bases.
+ * out_regs must hold one bsw_alnreg per seed: the regions of chain c are written to
+ * out_regs[chains[c].seed_first ...] in the order the reference pushes them, out_count[c] of them.
+ * The engine's end_bonus must equal pen_clip5 and pen_clip3 (ksw_extend2 receives them as end_bonus,
+ * :746,:793; bwa's default is 5 for all three).  zdrop_mode BSW_ZDROP_SCALAR reproduces ksw_extend2's
+ * z-drop rule for e_del / e_ins != 1. */
+typedef struct bsw_seed { int64_t rbeg; int32_t qbeg, len, score, reserved; } bsw_seed;
+typedef struct bsw_chain {
+    int64_t seed_first;          /* first seed of the chain in seeds[]                     */
+    int32_t n_seeds, l_query;
+    int64_t query_off;           /* the read: query[query_off .. query_off + l_query)      */
+    int64_t rmax0, rmax1;        /* reference window, coordinates as rbeg                  */
+    int64_t ref_off;             /* its bases: ref[ref_off .. ref_off + rmax1 - rmax0)     */
+} bsw_chain;
+typedef struct bsw_alnreg {      /* the fields of mem_alnreg_t that mem_chain2aln computes (bwamem.h:71-91) */
+    int64_t rb, re;
+    int32_t qb, qe, score, truesc, w, seedcov, seedlen0, reserved;
+} bsw_alnreg;
+typedef struct bsw_chain_opt {
+    int32_t w;                   /* opt->w                                                 */
+    int32_t pen_clip5, pen_clip3;
+    int32_t max_band_try;        /* MAX_BAND_TRY, bwamem.c:630 (2)                         */
+} bsw_chain_opt;
+int bsw_chain_window(const bsw_params* params, int32_t w, int64_t l_pac, const bsw_seed* seeds,
+                     int32_t n_seeds, int32_t l_query, int64_t* rmax0, int64_t* rmax1);
+int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains, const bsw_seed* seeds,
+                      const uint8_t* query, const uint8_t* ref, const bsw_chain_opt* opt,
+                      bsw_alnreg* out_regs, int32_t* out_count);
+
 /* Pinned host memory.  bsw_extend takes any host pointers; when all three buffers (pairs,
  * seq_ref, seq_qer) are page-locked -- allocated here, or registered, or pinned by the caller's
  * own CUDA / torch allocator -- the engine DMAs them as they are and DMAs the records back with

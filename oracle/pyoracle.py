@@ -23,6 +23,12 @@ REF_SO = HERE / "_ref" / "libbswref.so"
 KSW_SO = HERE / "_ref" / "libkswref.so"
 
 
+CHAIN_SEED_DTYPE = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4"), ("score", "<i4"), ("pad", "<i4")])   # mem_seed_t
+CHAIN_REG_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("score", "<i4"), ("truesc", "<i4"),
+                            ("w", "<i4"), ("seedcov", "<i4"), ("seedlen0", "<i4"), ("pad", "<i4")])
+CHAIN_REG_FIELDS = ("rb", "re", "qb", "qe", "score", "truesc", "w", "seedcov", "seedlen0")
+
+
 class OracleParams(C.Structure):
     _fields_ = [(k, C.c_int32) for k in
                 ("o_del", "e_del", "o_ins", "e_ins", "zdrop", "end_bonus", "match", "mismatch", "ambig",
@@ -55,6 +61,13 @@ class Oracle:
         self.lib.bsw_oracle_row_trips.argtypes = [C.POINTER(OracleParams), C.c_void_p, C.c_int, C.c_void_p,
                                                   C.c_int, C.c_int, C.c_int, C.c_void_p]
         self.lib.bsw_oracle_max_threads.restype = C.c_int
+        self.lib.bsw_oracle_chain_window.restype = None
+        self.lib.bsw_oracle_chain_window.argtypes = [C.POINTER(OracleParams), C.c_int, C.c_int64, C.c_void_p, C.c_int,
+                                                     C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        self.lib.bsw_oracle_chain.restype = C.c_int
+        self.lib.bsw_oracle_chain.argtypes = [C.POINTER(OracleParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
+                                              C.c_void_p]
 
     def max_threads(self) -> int:
         return int(self.lib.bsw_oracle_max_threads())
@@ -66,6 +79,26 @@ class Oracle:
             nthreads = self.max_threads()
         return int(self.lib.bsw_oracle_batch(C.byref(params), pairs.ctypes.data, seq_ref.ctypes.data,
                                              seq_qer.ctypes.data, len(pairs), w, nthreads))
+
+    # ---- seed -> pair construction / chain extension (chain_oracle.c) ----------------------------
+    def chain_window(self, params: OracleParams, w: int, l_pac: int, seeds: np.ndarray, l_query: int):
+        """Reference window [rmax0, rmax1) of a chain (tools/bwa/bwamem.c:643-659); seeds = CHAIN_SEED_DTYPE."""
+        r0, r1 = C.c_int64(0), C.c_int64(0)
+        seeds = np.ascontiguousarray(seeds)
+        self.lib.bsw_oracle_chain_window(C.byref(params), w, C.c_int64(l_pac), seeds.ctypes.data, len(seeds), l_query,
+                                         C.byref(r0), C.byref(r1))
+        return int(r0.value), int(r1.value)
+
+    def chain(self, params: OracleParams, w: int, pen_clip5: int, pen_clip3: int, max_band_try: int,
+              query: np.ndarray, seeds: np.ndarray, rmax0: int, rmax1: int, rseq: np.ndarray) -> np.ndarray:
+        """mem_chain2aln of one chain (tools/bwa/bwamem.c:632-822) -> CHAIN_REG_DTYPE array, reference order."""
+        seeds = np.ascontiguousarray(seeds)
+        query = np.ascontiguousarray(query); rseq = np.ascontiguousarray(rseq)
+        out = np.zeros(max(len(seeds), 1), dtype=CHAIN_REG_DTYPE)
+        n = self.lib.bsw_oracle_chain(C.byref(params), w, pen_clip5, pen_clip3, max_band_try, len(query),
+                                      query.ctypes.data, seeds.ctypes.data, len(seeds), C.c_int64(rmax0),
+                                      C.c_int64(rmax1), rseq.ctypes.data, out.ctypes.data)
+        return out[:n]
 
     def band_retry(self, params: OracleParams, pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray,
                    w: int, max_try: int = 2, prev_score=None) -> np.ndarray:
