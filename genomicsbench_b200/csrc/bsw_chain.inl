@@ -111,7 +111,7 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
     std::vector<ChainCand> cand;
     std::vector<SeqPair> lp, rp;
     std::vector<uint8_t> lq, lr;
-    std::vector<int32_t> band, prev;
+    std::vector<int32_t> band, prev, pick;
     auto add_stats = [&]() {
         const bsw_stats& s = eng->stats;
         total.pairs += s.pairs; total.cells_nominal += s.cells_nominal; total.cells_effective += s.cells_effective;
@@ -123,7 +123,9 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
     for (;;) {
         // ---- next surviving seed of every chain (containment test, bwamem.c:667-700) ------------
         cand.clear();
-        for (int64_t c = 0; c < n_chains; ++c) {
+        pick.assign((size_t)n_chains, -1);
+        eng->pool->for_range(n_chains, 512, [&](int64_t cb, int64_t ce, int) {
+        for (int64_t c = cb; c < ce; ++c) {
             const bsw_chain& ch = chains[c];
             ChainRun& R = run[(size_t)c];
             const bsw_seed* S = seeds + ch.seed_first;
@@ -155,11 +157,16 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
                     }
                     if (i == ch.n_seeds) { R.srt[(size_t)k] = 0; --R.k; continue; }     // contained: no extension
                 }
-                ChainCand cd;
-                cd.chain = c; cd.seed = (int)(uint32_t)R.srt[(size_t)k]; cd.aw0 = cd.aw1 = w;
-                cand.push_back(cd);
+                pick[(size_t)c] = (int)(uint32_t)R.srt[(size_t)k];
                 break;
             }
+        }
+        });
+        for (int64_t c = 0; c < n_chains; ++c) {
+            if (pick[(size_t)c] < 0) continue;
+            ChainCand cd;
+            cd.chain = c; cd.seed = pick[(size_t)c]; cd.aw0 = cd.aw1 = w;
+            cand.push_back(cd);
         }
         if (cand.empty()) break;
 
@@ -206,7 +213,9 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
                 return rc;
             add_stats();
         }
-        for (ChainCand& cd : cand) {
+        eng->pool->for_range((int64_t)cand.size(), 1024, [&](int64_t xb, int64_t xe, int) {
+        for (int64_t x = xb; x < xe; ++x) {
+            ChainCand& cd = cand[(size_t)x];
             const bsw_chain& ch = chains[cd.chain];
             const bsw_seed& s = seeds[ch.seed_first + cd.seed];
             bsw_alnreg& a = out[ch.seed_first + out_count[cd.chain]];
@@ -224,6 +233,7 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
                 }
             } else { a.score = a.truesc = s.len * P.match; a.qb = 0; a.rb = s.rbeg; }       // :763
         }
+        });
 
         // ---- right flanks: read in place, h0 = the left score (:765-800) -------------------------
         rp.clear(); prev.clear();
@@ -250,7 +260,9 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
                 return rc;
             add_stats();
         }
-        for (ChainCand& cd : cand) {
+        eng->pool->for_range((int64_t)cand.size(), 1024, [&](int64_t xb, int64_t xe, int) {
+        for (int64_t x = xb; x < xe; ++x) {
+            ChainCand& cd = cand[(size_t)x];
             const bsw_chain& ch = chains[cd.chain];
             const bsw_seed* S = seeds + ch.seed_first;
             const bsw_seed& s = S[cd.seed];
@@ -280,6 +292,7 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
             ++out_count[cd.chain];
             --run[(size_t)cd.chain].k;
         }
+        });
     }
     eng->stats = total;
     return BSW_OK;
