@@ -60,7 +60,7 @@ class BswStats(C.Structure):
 # include/bsw.h: bsw_seed (= mem_seed_t), bsw_chain, bsw_alnreg, bsw_chain_opt
 SEED_DTYPE = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4"), ("score", "<i4"), ("reserved", "<i4")])
 CHAIN_DTYPE = np.dtype([("seed_first", "<i8"), ("n_seeds", "<i4"), ("l_query", "<i4"), ("query_off", "<i8"),
-                        ("rmax0", "<i8"), ("rmax1", "<i8"), ("ref_off", "<i8")])
+                        ("rmax0", "<i8"), ("rmax1", "<i8"), ("ref_off", "<i8"), ("same_read", "<i4"), ("reserved", "<i4")])
 ALNREG_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("score", "<i4"), ("truesc", "<i4"),
                          ("w", "<i4"), ("seedcov", "<i4"), ("seedlen0", "<i4"), ("reserved", "<i4")])
 ALNREG_FIELDS = ("rb", "re", "qb", "qe", "score", "truesc", "w", "seedcov", "seedlen0")

@@ -87,9 +87,15 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
     }
     const bsw_params& P = eng->p;
     std::vector<ChainRun> run((size_t)n_chains);
+    std::vector<int64_t> group_first((size_t)n_chains);         // first chain of the read a chain belongs to
     for (int64_t c = 0; c < n_chains; ++c) {
         const bsw_chain& ch = chains[c];
         out_count[c] = 0;
+        group_first[(size_t)c] = (c > 0 && ch.same_read) ? group_first[(size_t)c - 1] : c;
+        if (ch.same_read && (c == 0 || chains[c - 1].l_query != ch.l_query || chains[c - 1].query_off != ch.query_off)) {
+            eng->err = "bsw_extend_chains: same_read set on a chain whose predecessor is another read";
+            return BSW_ERR_PARAM;
+        }
         if (ch.n_seeds < 0 || ch.l_query < 1 || ch.rmax1 < ch.rmax0) { eng->err = "bsw_extend_chains: malformed chain"; return BSW_ERR_PARAM; }
         ChainRun& R = run[(size_t)c];
         R.srt.resize((size_t)ch.n_seeds);
@@ -112,6 +118,7 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
     std::vector<SeqPair> lp, rp;
     std::vector<uint8_t> lq, lr;
     std::vector<int32_t> band, prev, pick;
+    std::vector<uint8_t> done_before((size_t)n_chains, 0);      // chain had no seed left when the round began
     auto add_stats = [&]() {
         const bsw_stats& s = eng->stats;
         total.pairs += s.pairs; total.cells_nominal += s.cells_nominal; total.cells_effective += s.cells_effective;
@@ -124,18 +131,33 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
         // ---- next surviving seed of every chain (containment test, bwamem.c:667-700) ------------
         cand.clear();
         pick.assign((size_t)n_chains, -1);
+        for (int64_t c = 0; c < n_chains; ++c) done_before[(size_t)c] = run[(size_t)c].k < 0 ? 1 : 0;
         eng->pool->for_range(n_chains, 512, [&](int64_t cb, int64_t ce, int) {
         for (int64_t c = cb; c < ce; ++c) {
             const bsw_chain& ch = chains[c];
             ChainRun& R = run[(size_t)c];
             const bsw_seed* S = seeds + ch.seed_first;
-            bsw_alnreg* av = out + ch.seed_first;
+            // the chains of a read run one after the other: this chain acts once its predecessors are done
+            // (a predecessor that finishes in this very search leaves k < 0 only after its own loop, so the
+            // chain waits for the next round -- chains of a group may sit in different pool ranges)
+            bool blocked = false;
+            for (int64_t g = group_first[(size_t)c]; g < c; ++g) blocked = blocked || done_before[(size_t)g] == 0;
+            if (blocked) continue;
+            // regions the containment test looks at: those of the read's earlier chains, then this chain's
+            int n_av = 0;
+            for (int64_t g = group_first[(size_t)c]; g <= c; ++g) n_av += out_count[g];
+            auto reg_at = [&](int i) -> const bsw_alnreg& {
+                for (int64_t g = group_first[(size_t)c];; ++g) {
+                    if (i < out_count[g]) return out[chains[g].seed_first + i];
+                    i -= out_count[g];
+                }
+            };
             while (R.k >= 0) {
                 const int k = R.k;
                 const bsw_seed& s = S[(uint32_t)R.srt[(size_t)k]];
                 int i;
-                for (i = 0; i < out_count[c]; ++i) {
-                    const bsw_alnreg& p = av[i];
+                for (i = 0; i < n_av; ++i) {
+                    const bsw_alnreg& p = reg_at(i);
                     if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
                     if (s.len - p.seedlen0 > .1 * ch.l_query) continue;
                     int qd = s.qbeg - p.qb; int64_t rd = s.rbeg - p.rb;
@@ -147,7 +169,7 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
                     ww = max_gap < p.w ? max_gap : p.w;
                     if (qd - rd < ww && rd - qd < ww) break;
                 }
-                if (i < out_count[c]) {
+                if (i < n_av) {
                     for (i = k + 1; i < ch.n_seeds; ++i) {
                         if (R.srt[(size_t)i] == 0) continue;
                         const bsw_seed& t = S[(uint32_t)R.srt[(size_t)i]];

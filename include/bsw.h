@@ -136,7 +136,8 @@ int bsw_extend_retry(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref,
  * score (:765-800), its decision against pen_clip3 (:802-808), seedcov / w / seedlen0 (:812-822).
  * Batched over chains: round r extends the r-th surviving seed of every chain in two
  * bsw_extend_retry calls (all left flanks, then all right flanks); the containment test makes the
- * seeds of ONE chain sequential, chains are independent.
+ * seeds of ONE chain -- and the chains of one read (bsw_chain.same_read) -- sequential; reads are
+ * independent.
  *
  * bsw_seed = mem_seed_t (bwamem.c:168-172); coordinates are the reference's: rbeg in [0, 2 l_pac)
  * (forward strand, then the reverse complement), qbeg on the read.  A chain names its read
@@ -156,6 +157,10 @@ typedef struct bsw_chain {
     int64_t query_off;           /* the read: query[query_off .. query_off + l_query)      */
     int64_t rmax0, rmax1;        /* reference window, coordinates as rbeg                  */
     int64_t ref_off;             /* its bases: ref[ref_off .. ref_off + rmax1 - rmax0)     */
+    int32_t same_read;           /* 1: same read as chains[c - 1] -- mem_align1_core pushes the regions of all
+                                    chains of a read into ONE vector (bwamem.c:1105-1112), so this chain starts
+                                    when the previous one is done and its containment test sees those regions */
+    int32_t reserved;
 } bsw_chain;
 typedef struct bsw_alnreg {      /* the fields of mem_alnreg_t that mem_chain2aln computes (bwamem.h:71-91) */
     int64_t rb, re;

@@ -73,10 +73,14 @@ static int cmp_u64(const void *a, const void *b)
     return (x > y) - (x < y);
 }
 
-/* One chain.  rseq = the window bytes [rmax0, rmax1).  out must hold n entries; returns how many were made. */
+/* One chain.  rseq = the window bytes [rmax0, rmax1).  prior[0..n_prior) = the regions the earlier chains
+ * of the same read pushed into the shared mem_alnreg_v (mem_align1_core calls mem_chain2aln once per chain with
+ * ONE vector, bwamem.c:1105-1112): the containment test sees them first.  out must hold n entries; returns how
+ * many were made. */
 int bsw_oracle_chain(const oracle_params *p0, int w, int pen_clip5, int pen_clip3, int max_band_try,
                      int l_query, const uint8_t *query, const oracle_seed *seeds, int n,
-                     int64_t rmax0, int64_t rmax1, const uint8_t *rseq, oracle_alnreg *out)
+                     int64_t rmax0, int64_t rmax1, const uint8_t *rseq,
+                     const oracle_alnreg *prior, int n_prior, oracle_alnreg *out)
 {
     int n_out = 0;
     if (n == 0) return 0;
@@ -86,8 +90,8 @@ int bsw_oracle_chain(const oracle_params *p0, int w, int pen_clip5, int pen_clip
     for (int k = n - 1; k >= 0; --k) {
         const oracle_seed *s = &seeds[(uint32_t)srt[k]];
         int i;
-        for (i = 0; i < n_out; ++i) {                                                              /* :667-683 */
-            const oracle_alnreg *q = &out[i];
+        for (i = 0; i < n_prior + n_out; ++i) {                                                    /* :667-683 */
+            const oracle_alnreg *q = i < n_prior ? &prior[i] : &out[i - n_prior];
             int64_t rd; int qd, ww, max_gap;
             if (s->rbeg < q->rb || s->rbeg + s->len > q->re || s->qbeg < q->qb || s->qbeg + s->len > q->qe) continue;
             if (s->len - q->seedlen0 > .1 * l_query) continue;
@@ -100,7 +104,7 @@ int bsw_oracle_chain(const oracle_params *p0, int w, int pen_clip5, int pen_clip
             ww = max_gap < q->w ? max_gap : q->w;
             if (qd - rd < ww && rd - qd < ww) break;
         }
-        if (i < n_out) {                                                                           /* :684-700 */
+        if (i < n_prior + n_out) {                                                                 /* :684-700 */
             for (i = k + 1; i < n; ++i) {
                 const oracle_seed *t;
                 if (srt[i] == 0) continue;

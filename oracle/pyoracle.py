@@ -12,6 +12,7 @@ May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 from __future__ import annotations
 
 import ctypes as C
+from typing import Optional
 import subprocess
 from pathlib import Path
 
@@ -67,7 +68,7 @@ class Oracle:
         self.lib.bsw_oracle_chain.restype = C.c_int
         self.lib.bsw_oracle_chain.argtypes = [C.POINTER(OracleParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
-                                              C.c_void_p]
+                                              C.c_void_p, C.c_int, C.c_void_p]
 
     def max_threads(self) -> int:
         return int(self.lib.bsw_oracle_max_threads())
@@ -90,14 +91,17 @@ class Oracle:
         return int(r0.value), int(r1.value)
 
     def chain(self, params: OracleParams, w: int, pen_clip5: int, pen_clip3: int, max_band_try: int,
-              query: np.ndarray, seeds: np.ndarray, rmax0: int, rmax1: int, rseq: np.ndarray) -> np.ndarray:
-        """mem_chain2aln of one chain (tools/bwa/bwamem.c:632-822) -> CHAIN_REG_DTYPE array, reference order."""
+              query: np.ndarray, seeds: np.ndarray, rmax0: int, rmax1: int, rseq: np.ndarray,
+              prior: Optional[np.ndarray] = None) -> np.ndarray:
+        """mem_chain2aln of one chain (tools/bwa/bwamem.c:632-822) -> CHAIN_REG_DTYPE array, reference order.
+        prior = the regions of the read's earlier chains (one shared mem_alnreg_v, bwamem.c:1105-1112)."""
+        prior = np.zeros(0, dtype=CHAIN_REG_DTYPE) if prior is None else np.ascontiguousarray(prior, dtype=CHAIN_REG_DTYPE)
         seeds = np.ascontiguousarray(seeds)
         query = np.ascontiguousarray(query); rseq = np.ascontiguousarray(rseq)
         out = np.zeros(max(len(seeds), 1), dtype=CHAIN_REG_DTYPE)
         n = self.lib.bsw_oracle_chain(C.byref(params), w, pen_clip5, pen_clip3, max_band_try, len(query),
                                       query.ctypes.data, seeds.ctypes.data, len(seeds), C.c_int64(rmax0),
-                                      C.c_int64(rmax1), rseq.ctypes.data, out.ctypes.data)
+                                      C.c_int64(rmax1), rseq.ctypes.data, prior.ctypes.data, len(prior), out.ctypes.data)
         return out[:n]
 
     def band_retry(self, params: OracleParams, pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray,

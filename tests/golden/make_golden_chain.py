@@ -73,6 +73,9 @@ CASES = {
     "chain_w8_div":   dict(seed=0xB5B20302, L=40_000, reads=350, err=(0.08, 0.12), opt=dict(w=8)),
     "chain_gaps_e2":  dict(seed=0xB5B20303, L=40_000, reads=250, err=(0.03, 0.08),
                            opt=dict(o_del=4, e_del=2, o_ins=5, e_ins=1, zdrop=60)),
+    # several chains per read pushing into ONE mem_alnreg_v, as mem_align1_core does (bwamem.c:1105-1112): the
+    # containment test of a later chain sees the regions of the earlier ones
+    "chain_multi":    dict(seed=0xB5B20304, L=40_000, reads=400, err=(0.03, 0.09), opt={}, split=True),
 }
 
 
@@ -164,25 +167,33 @@ def main():
             setattr(opt.contents, k, v)
         lib.bwa_fill_scmat(opt.contents.a, opt.contents.b, opt.contents.mat)
         reads = make_reads(rng, D, L, spec["reads"], spec["err"])
-        q_all, q_off, l_query, seed_rows, chain_first, chain_n, reg_rows, reg_n = [], [], [], [], [], [], [], []
+        q_all, q_off, l_query, seed_rows, chain_first, chain_n, reg_rows, reg_n, chain_read = [], [], [], [], [], [], [], [], []
         qpos = 0
         devnull = os.open(os.devnull, os.O_WRONLY)
         os.dup2(devnull, 1)
         try:
-            for read, seeds in reads:
-                arr = (MemSeed * len(seeds))(*[MemSeed(rb, qb, ln, ln * opt.contents.a) for rb, qb, ln in seeds])
-                ch = MemChain(len(seeds), len(seeds), 0, 0, 0, 0.0, 0, arr)
-                av = MemAlnRegV(0, 0, None)
+            for rid, (read, seeds) in enumerate(reads):
                 q = np.ascontiguousarray(read)
-                lib.mem_chain2aln(opt, C.byref(bns), pac.ctypes.data, len(q), q.ctypes.data, C.byref(ch), C.byref(av))
-                chain_first.append(len(seed_rows)); chain_n.append(len(seeds))
-                seed_rows += [(rb, qb, ln, ln * opt.contents.a) for rb, qb, ln in seeds]
-                reg_n.append(av.n)
-                for i in range(av.n):
-                    reg_rows.append([getattr(av.a[i], f) for f in REG_FIELDS])
+                parts = [seeds]
+                if spec.get("split") and len(seeds) >= 2:
+                    cut = rng.integers(0, 3)
+                    parts = [seeds[0::2], seeds[1::2]] if cut == 0 else [seeds[:len(seeds) // 2], seeds[len(seeds) // 2:]] \
+                        if cut == 1 else [seeds[len(seeds) // 2:], seeds[:len(seeds) // 2]]
+                av = MemAlnRegV(0, 0, None)
+                for part in parts:
+                    arr = (MemSeed * len(part))(*[MemSeed(rb, qb, ln, ln * opt.contents.a) for rb, qb, ln in part])
+                    ch = MemChain(len(part), len(part), 0, 0, 0, 0.0, 0, arr)
+                    before = av.n
+                    lib.mem_chain2aln(opt, C.byref(bns), pac.ctypes.data, len(q), q.ctypes.data, C.byref(ch), C.byref(av))
+                    chain_first.append(len(seed_rows)); chain_n.append(len(part)); chain_read.append(rid)
+                    seed_rows += [(rb, qb, ln, ln * opt.contents.a) for rb, qb, ln in part]
+                    reg_n.append(av.n - before)
+                    for i in range(before, av.n):
+                        reg_rows.append([getattr(av.a[i], f) for f in REG_FIELDS])
+                    q_off.append(qpos); l_query.append(len(q))
                 if av.a:
                     libc.free(av.a)
-                q_all.append(q); q_off.append(qpos); l_query.append(len(q)); qpos += len(q)
+                q_all.append(q); qpos += len(q)
             libc.fflush(None)
         finally:
             os.dup2(saved, 1)
@@ -193,10 +204,11 @@ def main():
         np.savez_compressed(OUT / f"{name}.npz", genome=G, query=np.concatenate(q_all), query_off=np.array(q_off, np.int64),
                             l_query=np.array(l_query, np.int32), seeds=np.array(seed_rows, np.int64),
                             chain_first=np.array(chain_first, np.int64), chain_n=np.array(chain_n, np.int32),
-                            regs=regs, reg_n=np.array(reg_n, np.int32), params=params)
+                            regs=regs, reg_n=np.array(reg_n, np.int32), params=params,
+                            chain_read=np.array(chain_read, np.int32))
         retried = int((regs[:, 6] > o.w).sum())
         to_end = int(((regs[:, 2] == 0)).sum())
-        print(f"{name}: chains={len(reads)} seeds={len(seed_rows)} regs={len(regs)} "
+        print(f"{name}: reads={len(reads)} chains={len(chain_n)} seeds={len(seed_rows)} regs={len(regs)} "
               f"skipped seeds={len(seed_rows) - len(regs)} band-retried regs={retried} qb==0 regs={to_end}")
         libc.free(opt)
 

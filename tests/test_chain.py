@@ -26,6 +26,7 @@ def load_chain_case(name):
         seeds[f] = z["seeds"][:, k]
     return dict(D=D, l_pac=len(G), query=z["query"], query_off=z["query_off"], l_query=z["l_query"], seeds=seeds,
                 chain_first=z["chain_first"], chain_n=z["chain_n"], regs=z["regs"], reg_n=z["reg_n"],
+                chain_read=z["chain_read"],
                 P=dict(match=a, mismatch=b, o_del=o_del, e_del=e_del, o_ins=o_ins, e_ins=e_ins, zdrop=zdrop),
                 clip5=clip5, clip3=clip3, w=w)
 
@@ -36,12 +37,16 @@ def test_chain_oracle_matches_reference_golden(oracle, case):
     # ksw_extend2's z-drop rule is the scalar one (ksw.c:462-470): zdrop_mode = 1
     P = make_params(end_bonus=c["clip5"], ambig=-1, zdrop_mode=1, **c["P"])
     pos = 0
+    prior = None
     for k in range(len(c["chain_n"])):
         sd = c["seeds"][c["chain_first"][k]: c["chain_first"][k] + c["chain_n"][k]]
         lq = int(c["l_query"][k])
         q = c["query"][c["query_off"][k]: c["query_off"][k] + lq]
         r0, r1 = oracle.chain_window(P, c["w"], c["l_pac"], sd, lq)
-        got = oracle.chain(P, c["w"], c["clip5"], c["clip3"], 2, q, sd, r0, r1, c["D"][r0:r1])
+        if k == 0 or c["chain_read"][k] != c["chain_read"][k - 1]:
+            prior = None                                            # a new read: a new mem_alnreg_v
+        got = oracle.chain(P, c["w"], c["clip5"], c["clip3"], 2, q, sd, r0, r1, c["D"][r0:r1], prior)
+        prior = got if prior is None else np.concatenate([prior, got])
         want = c["regs"][pos: pos + c["reg_n"][k]]
         pos += int(c["reg_n"][k])
         assert len(got) == len(want), f"chain {k}: {len(got)} regions, reference made {len(want)}"
@@ -62,7 +67,8 @@ def _build_batch(lib, eng, c):
     for k in range(n):
         first, ns, lq = int(c["chain_first"][k]), int(c["chain_n"][k]), int(c["l_query"][k])
         r0, r1 = eng.chain_window(c["w"], c["l_pac"], seeds[first: first + ns], lq)
-        chains[k] = (first, ns, lq, int(c["query_off"][k]), r0, r1, off)
+        same = int(k > 0 and c["chain_read"][k] == c["chain_read"][k - 1])
+        chains[k] = (first, ns, lq, int(c["query_off"][k]), r0, r1, off, same, 0)
         parts.append(c["D"][r0:r1]); off += r1 - r0
     return chains, seeds, np.ascontiguousarray(c["query"]), np.ascontiguousarray(np.concatenate(parts))
 
