@@ -23,6 +23,7 @@
 #include "bsw_kernels.cuh"
 #include "bsw_kernel16.cuh"
 #include "bsw_prep.cuh"
+#include "bsw_global.cuh"
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -163,6 +164,7 @@ struct bsw_engine {
     int64_t n = 0;
     int32_t w = 0;
     std::vector<std::pair<int, int>> staged_chunks;   // (device, slot) per chunk, batch order
+    void* gbufs = nullptr;                // device buffers of bsw_global (GlobalBufs, bsw_global.inl)
 };
 
 namespace {
@@ -1066,9 +1068,12 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
     return eng;
 }
 
+static void bsw_global_release(bsw_engine* eng);      // bsw_global.inl
+
 void bsw_destroy(bsw_engine* eng)
 {
     if (!eng) return;
+    bsw_global_release(eng);
     for (DevCtx& c : eng->devs) {
         cudaSetDevice(c.dev);
         cudaDeviceSynchronize();
@@ -1162,6 +1167,7 @@ int bsw_extend_retry(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, co
 }
 
 #include "bsw_chain.inl"
+#include "bsw_global.inl"
 
 // ------------------------------------------------------------------------------------------
 // resident form: stage (host -> HBM, packed + bucketed), run (DP kernels only, repeatable),

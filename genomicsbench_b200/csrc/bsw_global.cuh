@@ -1,0 +1,116 @@
+// bsw_global.cuh -- banded global alignment with traceback -> CIGAR, sm_100a.
+//
+// Stands in for ksw_global2 (tools/bwa/ksw.c:502-606; push_cigar :489-500), which bwa_gen_cigar2 calls
+// once per alignment region.  One alignment per thread: the row sweep over the fixed band |i - j| <= w
+// keeps the reference's int32 arithmetic and its order of comparisons (the direction byte
+// f << 4 | e << 2 | h of every cell depends on which side wins a tie), stores the byte matrix in
+// HBM (n_col x tlen per alignment), then the same thread walks it back from the last cell and
+// writes the merged operations, reversed into read order.
+// Row state eh[] lives in a scratch array interleaved over the threads of the launch
+// (eh[j * stride + thread]) so that the lanes of a warp, all at column j of their own alignment
+// give or take the band offset, touch neighbouring words.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bsw {
+
+constexpr int G_MINUS_INF = -0x40000000;         // ksw.c:487
+
+struct GlobalDesc {                              // one alignment of a chunk
+    uint32_t qoff, roff;                         // byte offsets into the chunk's gathered query / target bytes
+    int32_t qlen, tlen, w, pad;
+    long long zoff;                              // byte offset of its direction matrix
+    long long coff;                              // word offset of its (uncompacted) operation list: qlen + tlen entries
+};
+
+struct GlobalParams { int o_del, e_del, o_ins, e_ins, match, mismatch_neg, ambig; };
+
+__global__ void __launch_bounds__(128)
+bsw_global_kernel(const GlobalDesc* __restrict__ desc, int n, const uint8_t* __restrict__ qraw,
+                  const uint8_t* __restrict__ rraw, int2* __restrict__ eh, int stride, uint8_t* __restrict__ z,
+                  uint32_t* __restrict__ cigar, int32_t* __restrict__ score, int32_t* __restrict__ n_cigar,
+                  const GlobalParams P)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const GlobalDesc d = desc[t];
+    const int qlen = d.qlen, tlen = d.tlen, w = d.w;
+    const uint8_t* q = qraw + d.qoff;
+    const uint8_t* r = rraw + d.roff;
+    uint8_t* zm = z + d.zoff;
+    int2* row = eh + t;                          // row[j * stride] = {h, e} of column j
+    const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
+    const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+    // first row (ksw.c:521-525)
+    row[0] = make_int2(0, G_MINUS_INF);
+    int j;
+    for (j = 1; j <= qlen && j <= w; ++j) row[(size_t)j * stride] = make_int2(-(P.o_ins + P.e_ins * j), G_MINUS_INF);
+    for (; j <= qlen; ++j) row[(size_t)j * stride] = make_int2(G_MINUS_INF, G_MINUS_INF);
+    for (int i = 0; i < tlen; ++i) {                                            // ksw.c:527-589
+        int f = G_MINUS_INF;
+        const int beg = i > w ? i - w : 0;
+        const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        int h1 = beg == 0 ? -(P.o_del + P.e_del * (i + 1)) : G_MINUS_INF;
+        const int tb = r[i];
+        uint8_t* zi = zm + (size_t)i * n_col;
+        for (j = beg; j < end; ++j) {
+            int2* p = &row[(size_t)j * stride];
+            const int2 c = *p;
+            int m = c.x, e = c.y;
+            const int qb = q[j];
+            m += (tb >= 4 || qb >= 4) ? P.ambig : (tb == qb ? P.match : P.mismatch_neg);
+            int dd = m >= e ? 0 : 1;
+            int h = m >= e ? m : e;
+            dd = h >= f ? dd : 2;
+            h = h >= f ? h : f;
+            int tt = m - oe_del;
+            e -= P.e_del;
+            dd |= e > tt ? 1 << 2 : 0;
+            e = e > tt ? e : tt;
+            *p = make_int2(h1, e);
+            h1 = h;
+            tt = m - oe_ins;
+            f -= P.e_ins;
+            dd |= f > tt ? 2 << 4 : 0;
+            f = f > tt ? f : tt;
+            zi[j - beg] = (uint8_t)dd;
+        }
+        int2* pe = &row[(size_t)end * stride];
+        *pe = make_int2(h1, G_MINUS_INF);
+    }
+    score[t] = row[(size_t)qlen * stride].x;
+    // backtrack (ksw.c:591-603)
+    uint32_t* cg = cigar + d.coff;
+    int n_op = 0, which = 0;
+    int i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+    auto push = [&](int op, int len) {                                          // push_cigar, ksw.c:489-500
+        if (n_op == 0 || op != (int)(cg[n_op - 1] & 0xf)) cg[n_op++] = (uint32_t)len << 4 | (uint32_t)op;
+        else cg[n_op - 1] += (uint32_t)len << 4;
+    };
+    while (i >= 0 && k >= 0) {
+        which = zm[(size_t)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+        if (which == 0) { push(0, 1); --i; --k; }
+        else if (which == 1) { push(2, 1); --i; }
+        else { push(1, 1); --k; }
+    }
+    if (i >= 0) push(2, i + 1);
+    if (k >= 0) push(1, k + 1);
+    for (i = 0; i < n_op >> 1; ++i) { const uint32_t tmp = cg[i]; cg[i] = cg[n_op - 1 - i]; cg[n_op - 1 - i] = tmp; }
+    n_cigar[t] = n_op;
+}
+
+// operation lists of a chunk, packed one after the other: out[out_off[t] ...] = the n_cigar[t] operations of t
+__global__ void __launch_bounds__(128)
+bsw_cigar_compact(const GlobalDesc* __restrict__ desc, int n, const uint32_t* __restrict__ cigar,
+                  const int32_t* __restrict__ n_cigar, const long long* __restrict__ out_off, uint32_t* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t* src = cigar + desc[t].coff;
+    uint32_t* dst = out + out_off[t];
+    const int m = n_cigar[t];
+    for (int k = 0; k < m; ++k) dst[k] = src[k];
+}
+
+} // namespace bsw

@@ -177,6 +177,20 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
                       const uint8_t* query, const uint8_t* ref, const bsw_chain_opt* opt,
                       bsw_alnreg* out_regs, int32_t* out_count);
 
+/* ---- (f.4) banded global alignment with traceback -> CIGAR -------------------
+ * replaces: ksw_global2 (tools/bwa/ksw.c:502-606, push_cigar :489-500) as bwa_gen_cigar2 calls it for
+ * every alignment region: global alignment of query[0, len2) against target[0, len1) inside the fixed
+ * band |i - j| <= w[i], int32 scores, gap costs and scoring of the engine (match / -mismatch / ambig),
+ * the reference's tie-breaking in every cell, its backtrack and its merged operation list.
+ * pairs[i] supplies idr / idq / len1 / len2 (h0 and the result fields are not used).  Outputs:
+ * score[i]; n_cigar[i]; the operations (len << 4 | op, op 0 = M, 1 = I, 2 = D, as in BAM and ksw.c) of
+ * alignment i at cigar[cigar_off[i] .. cigar_off[i + 1]) -- cigar_off has n + 1 entries, cigar_cap is the
+ * capacity of cigar in entries (sum of len1 + len2 always suffices; BSW_ERR_PARAM if it overflows).
+ * Domain: |len1 - len2| <= w[i] (outside it the reference's backtrack leaves its matrix). */
+int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
+               int64_t n_pairs, const int32_t* w, int32_t* score, int32_t* n_cigar, uint32_t* cigar,
+               int64_t cigar_cap, int64_t* cigar_off);
+
 /* Pinned host memory.  bsw_extend takes any host pointers; when all three buffers (pairs,
  * seq_ref, seq_qer) are page-locked -- allocated here, or registered, or pinned by the caller's
  * own CUDA / torch allocator -- the engine DMAs them as they are and DMAs the records back with

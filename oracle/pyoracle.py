@@ -81,6 +81,18 @@ class Oracle:
         return int(self.lib.bsw_oracle_batch(C.byref(params), pairs.ctypes.data, seq_ref.ctypes.data,
                                              seq_qer.ctypes.data, len(pairs), w, nthreads))
 
+    # ---- banded global alignment with traceback (global_oracle.c) ----------------------------------
+    def global_align(self, params: OracleParams, query: np.ndarray, target: np.ndarray, w: int):
+        """ksw_global2 (tools/bwa/ksw.c:502-606) -> (score, cigar uint32[n]: len << 4 | op, op 0 M / 1 I / 2 D)."""
+        query = np.ascontiguousarray(query); target = np.ascontiguousarray(target)
+        cig = np.zeros(len(query) + len(target) + 1, dtype=np.uint32)
+        n = C.c_int(0)
+        fn = self.lib.bsw_oracle_global
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(OracleParams), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        score = fn(C.byref(params), query.ctypes.data, len(query), target.ctypes.data, len(target), w, cig.ctypes.data, C.byref(n))
+        return int(score), cig[:n.value].copy()
+
     # ---- seed -> pair construction / chain extension (chain_oracle.c) ----------------------------
     def chain_window(self, params: OracleParams, w: int, l_pac: int, seeds: np.ndarray, l_query: int):
         """Reference window [rmax0, rmax1) of a chain (tools/bwa/bwamem.c:643-659); seeds = CHAIN_SEED_DTYPE."""
@@ -208,6 +220,22 @@ class KswReference:
     @staticmethod
     def available() -> bool:
         return KSW_SO.exists()
+
+    def global_align(self, params, query: np.ndarray, target: np.ndarray, w: int):
+        """The reference's ksw_global2 (tools/bwa/ksw.c:502-606) -> (score, cigar uint32[n])."""
+        mat = self.scmat(params.match, params.mismatch, params.ambig)
+        query = np.ascontiguousarray(query); target = np.ascontiguousarray(target)
+        fn = self.lib.ksw_global2
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                       C.c_int, C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint32))]
+        n = C.c_int(0); cg = C.POINTER(C.c_uint32)()
+        score = fn(len(query), query.ctypes.data, len(target), target.ctypes.data, 5, mat.ctypes.data, params.o_del,
+                   params.e_del, params.o_ins, params.e_ins, w, C.byref(n), C.byref(cg))
+        out = np.array([cg[i] for i in range(n.value)], dtype=np.uint32)
+        if cg:
+            C.CDLL(None).free(C.cast(cg, C.c_void_p))
+        return int(score), out
 
     @staticmethod
     def scmat(match: int, mismatch: int, ambig: int) -> np.ndarray:

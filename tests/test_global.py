@@ -1,0 +1,107 @@
+"""Banded global alignment + CIGAR (tools/bwa/ksw.c:489-606, ksw_global2).
+
+CPU: oracle/global_oracle.c against the golden scores / CIGARs the reference's own ksw_global2 produced
+(tests/golden/make_golden_global.py) and, where the reference tree is mounted, against live calls.
+GPU: bsw_global against the same goldens."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR
+from oracle.pyoracle import KswReference, make_params
+
+GLOBAL_CASES = sorted(p.stem for p in (GOLDEN_DIR / "global").glob("*.npz"))
+
+
+def load_global_case(name):
+    z = np.load(GOLDEN_DIR / "global" / f"{name}.npz")
+    o_del, e_del, o_ins, e_ins, match, mismatch, ambig = (int(v) for v in z["params"])
+    qoff = np.concatenate([[0], np.cumsum(z["len2"])]).astype(np.int64)
+    toff = np.concatenate([[0], np.cumsum(z["len1"])]).astype(np.int64)
+    coff = np.concatenate([[0], np.cumsum(z["n_cigar"])]).astype(np.int64)
+    return dict(z=z, qoff=qoff, toff=toff, coff=coff,
+                P=dict(o_del=o_del, e_del=e_del, o_ins=o_ins, e_ins=e_ins, match=match, mismatch=mismatch, ambig=ambig))
+
+
+@pytest.mark.parametrize("case", GLOBAL_CASES)
+def test_global_oracle_matches_reference_golden(oracle, case):
+    c = load_global_case(case); z = c["z"]
+    P = make_params(**c["P"])
+    for k in range(len(z["w"])):
+        q = z["query"][c["qoff"][k]: c["qoff"][k + 1]]; t = z["target"][c["toff"][k]: c["toff"][k + 1]]
+        score, cig = oracle.global_align(P, q, t, int(z["w"][k]))
+        assert score == int(z["score"][k]), f"pair {k}"
+        assert np.array_equal(cig, z["cigar"][c["coff"][k]: c["coff"][k + 1]]), f"pair {k}"
+        # a CIGAR consumes exactly the two sequences
+        ln, op = cig >> 4, cig & 0xf
+        assert ln[(op == 0) | (op == 1)].sum() == len(q) and ln[(op == 0) | (op == 2)].sum() == len(t)
+
+
+def test_global_oracle_matches_live_reference(oracle):
+    if not KswReference.available():
+        pytest.skip("oracle/_ref/libkswref.so not built (needs /root/reference)")
+    K = KswReference()
+    rng = np.random.default_rng(0xB5B20405)
+    for params in (dict(), dict(o_del=3, e_del=2, o_ins=7, e_ins=3, match=3, mismatch=5)):
+        P = make_params(**params)
+        for _ in range(150):
+            q = rng.integers(0, 5, int(rng.integers(1, 120))).astype(np.uint8)
+            t = rng.integers(0, 5, int(rng.integers(max(1, len(q) - 15), len(q) + 16))).astype(np.uint8)
+            w = abs(len(q) - len(t)) + int(rng.integers(0, 12))
+            a, b = oracle.global_align(P, q, t, w), K.global_align(P, q, t, w)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+def _pairs_of(lib, c):
+    z = c["z"]
+    n = len(z["w"])
+    pairs = np.zeros(n, dtype=lib.SEQPAIR_DTYPE)
+    pairs["len1"], pairs["len2"] = z["len1"], z["len2"]
+    pairs["idr"], pairs["idq"] = c["toff"][:-1], c["qoff"][:-1]
+    pairs["h0"] = 1
+    return pairs, np.ascontiguousarray(z["target"]), np.ascontiguousarray(z["query"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GLOBAL_CASES)
+def test_bsw_global_matches_reference_golden(lib, case):
+    c = load_global_case(case); z = c["z"]
+    pairs, ref, qer = _pairs_of(lib, c)
+    with lib.Engine(**c["P"]) as eng:
+        score, cigar, off = eng.global_align(pairs, ref, qer, z["w"])
+        st = eng.stats()
+    assert np.array_equal(score, z["score"])
+    assert np.array_equal(np.diff(off), z["n_cigar"])
+    assert np.array_equal(cigar, z["cigar"])
+    assert st["kernel_launches"] >= 2 and st["cells_effective"] > 0
+
+
+@pytest.mark.gpu
+def test_bsw_global_edges_and_errors(lib, oracle):
+    """Empty batch, one band for all pairs, order invariance, several chunks, domain errors."""
+    c = load_global_case("global_default"); z = c["z"]
+    pairs, ref, qer = _pairs_of(lib, c)
+    with lib.Engine(**c["P"]) as eng:
+        s0, c0, o0 = eng.global_align(pairs[:0], ref, qer, 10)
+        assert len(s0) == 0 and len(c0) == 0 and list(o0) == [0]
+        wide = int(np.abs(pairs["len1"] - pairs["len2"]).max()) + 5
+        score, cigar, off = eng.global_align(pairs, ref, qer, wide)            # scalar band
+        P = make_params(**c["P"])
+        for k in range(0, len(pairs), 37):
+            q = qer[pairs["idq"][k]: pairs["idq"][k] + pairs["len2"][k]]; t = ref[pairs["idr"][k]: pairs["idr"][k] + pairs["len1"][k]]
+            sc, cg = oracle.global_align(P, q, t, wide)
+            assert sc == score[k] and np.array_equal(cg, cigar[off[k]: off[k + 1]])
+        perm = np.random.default_rng(3).permutation(len(pairs))
+        s2, c2, o2 = eng.global_align(pairs[perm], ref, qer, z["w"][perm])
+        assert np.array_equal(s2, z["score"][perm])
+        for j in (0, 5, len(perm) - 1):
+            k = perm[j]
+            assert np.array_equal(c2[o2[j]: o2[j + 1]], z["cigar"][c["coff"][k]: c["coff"][k + 1]])
+        big = np.tile(pairs, 300)                                                # 210 000 alignments: several chunks
+        s3, c3, o3 = eng.global_align(big, ref, qer, np.tile(z["w"], 300))
+        assert np.array_equal(s3, np.tile(z["score"], 300)) and np.array_equal(c3, np.tile(z["cigar"], 300))
+        bad = pairs[:4].copy(); bad["len1"][2] = bad["len2"][2] + 50
+        with pytest.raises(lib.BswError) as ei:
+            eng.global_align(bad, ref, qer, 10)
+        assert ei.value.code == -2
