@@ -4,8 +4,10 @@
 // once per alignment region.  One alignment per thread: the row sweep over the fixed band |i - j| <= w
 // keeps the reference's int32 arithmetic and its order of comparisons (the direction byte
 // f << 4 | e << 2 | h of every cell depends on which side wins a tie), stores the byte matrix in
-// HBM (n_col x tlen per alignment), then the same thread walks it back from the last cell and
-// writes the merged operations, reversed into read order.
+// HBM (tlen rows of n_col bytes, row pitch rounded up to 8 so that eight cells leave in one 64-bit
+// store -- byte stores of 32 lanes into 32 different sectors were the first version's bound), then
+// the same thread walks it back from the last cell and writes the merged operations, reversed into
+// read order.
 // Row state eh[] lives in a scratch array interleaved over the threads of the launch
 // (eh[j * stride + thread]) so that the lanes of a warp, all at column j of their own alignment
 // give or take the band offset, touch neighbouring words.
@@ -42,6 +44,7 @@ bsw_global_kernel(const GlobalDesc* __restrict__ desc, int n, const uint8_t* __r
     int2* row = eh + t;                          // row[j * stride] = {h, e} of column j
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
     const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+    const int pitch = (n_col + 7) & ~7;          // bytes per row of the direction matrix (zoff is 8-aligned)
     // first row (ksw.c:521-525)
     row[0] = make_int2(0, G_MINUS_INF);
     int j;
@@ -53,7 +56,8 @@ bsw_global_kernel(const GlobalDesc* __restrict__ desc, int n, const uint8_t* __r
         const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
         int h1 = beg == 0 ? -(P.o_del + P.e_del * (i + 1)) : G_MINUS_INF;
         const int tb = r[i];
-        uint8_t* zi = zm + (size_t)i * n_col;
+        unsigned long long* zi = reinterpret_cast<unsigned long long*>(zm + (size_t)i * pitch);
+        unsigned long long acc = 0;
         for (j = beg; j < end; ++j) {
             int2* p = &row[(size_t)j * stride];
             const int2 c = *p;
@@ -74,8 +78,11 @@ bsw_global_kernel(const GlobalDesc* __restrict__ desc, int n, const uint8_t* __r
             f -= P.e_ins;
             dd |= f > tt ? 2 << 4 : 0;
             f = f > tt ? f : tt;
-            zi[j - beg] = (uint8_t)dd;
+            const int col = j - beg;
+            acc |= (unsigned long long)dd << ((col & 7) * 8);
+            if ((col & 7) == 7) { zi[col >> 3] = acc; acc = 0; }
         }
+        if ((end - beg) & 7) zi[(end - beg) >> 3] = acc;
         int2* pe = &row[(size_t)end * stride];
         *pe = make_int2(h1, G_MINUS_INF);
     }
@@ -89,7 +96,7 @@ bsw_global_kernel(const GlobalDesc* __restrict__ desc, int n, const uint8_t* __r
         else cg[n_op - 1] += (uint32_t)len << 4;
     };
     while (i >= 0 && k >= 0) {
-        which = zm[(size_t)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+        which = zm[(size_t)i * pitch + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
         if (which == 0) { push(0, 1); --i; --k; }
         else if (which == 1) { push(2, 1); --i; }
         else { push(1, 1); --k; }

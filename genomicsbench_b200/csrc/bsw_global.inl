@@ -76,7 +76,7 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
             const SeqPair& sp = pairs[done + m];
             const int wv = w[done + m];
             const long long n_col = sp.len2 < 2 * wv + 1 ? sp.len2 : 2 * wv + 1;
-            const long long zi = n_col * sp.len1, ci = (long long)sp.len1 + sp.len2;
+            const long long zi = ((n_col + 7) & ~7ll) * sp.len1, ci = (long long)sp.len1 + sp.len2;   // row pitch of bsw_global_kernel
             const int qm = std::max(qmax, sp.len2);
             if (m > 0 && (zb + zi > Z_CAP || cw + ci > C_CAP || (long long)(qm + 1) * (m + 1) > EH_CAP)) break;
             GlobalDesc d;
@@ -87,13 +87,22 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
             ++m;
         }
         hq.resize((size_t)qb); hr.resize((size_t)rb);
-        eng->pool->for_range(m, 1024, [&](int64_t b, int64_t e, int) {
+        std::vector<long long> cells_part((size_t)eng->pool->size(), 0);
+        eng->pool->for_range(m, 1024, [&](int64_t b, int64_t e, int tid) {
+            long long cells = 0;
             for (int64_t k = b; k < e; ++k) {
                 const SeqPair& sp = pairs[done + k];
-                memcpy(hq.data() + hd[(size_t)k].qoff, seq_qer + sp.idq, (size_t)sp.len2);
-                memcpy(hr.data() + hd[(size_t)k].roff, seq_ref + sp.idr, (size_t)sp.len1);
+                const GlobalDesc& d = hd[(size_t)k];
+                memcpy(hq.data() + d.qoff, seq_qer + sp.idq, (size_t)sp.len2);
+                memcpy(hr.data() + d.roff, seq_ref + sp.idr, (size_t)sp.len1);
+                for (int i = 0; i < d.tlen; ++i) {                   // DP cells inside the band
+                    const int beg = i > d.w ? i - d.w : 0, end = i + d.w + 1 < d.qlen ? i + d.w + 1 : d.qlen;
+                    if (end > beg) cells += end - beg;
+                }
             }
+            cells_part[(size_t)tid] += cells;
         });
+        for (long long v : cells_part) S.cells_effective += v;
         const int threads = (int)m, stride = ((threads + 31) / 32) * 32;
         if (int rc = ensure(eng, B.desc, (size_t)m)) return rc;
         if (int rc = ensure(eng, B.q, (size_t)qb + 16)) return rc;
@@ -137,7 +146,7 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
         S.kernel_launches += 2;
         S.h2d_bytes += (int64_t)(sizeof(GlobalDesc) * (size_t)m + (size_t)qb + (size_t)rb);
         S.d2h_bytes += (int64_t)(8 * m + 4 * run);
-        S.cells_effective += zb;                     // one DP cell per direction byte
+
         for (int64_t k = 0; k < m; ++k) S.cells_nominal += (int64_t)pairs[done + k].len1 * pairs[done + k].len2;
         out_pos += run;
         done += m;

@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Throughput of bsw_global (banded global alignment + CIGAR) next to the reference's own
+ksw_global2 on one host thread.  Workload: the pairs of tests/golden/global/global_default.npz tiled T
+times; results are checked against the tiled golden.  Usage: python scripts/global_bench.py [tiles=300] [reps=5]"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import genomicsbench_b200 as gb
+from test_global import load_global_case, _pairs_of
+from oracle.pyoracle import KswReference, make_params
+
+tiles = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+c = load_global_case("global_default"); z = c["z"]
+pairs, ref, qer = _pairs_of(gb, c)
+big, wbig = np.tile(pairs, tiles), np.tile(z["w"], tiles)
+eng = gb.Engine(**c["P"])
+best, st = 1e9, None
+for r in range(reps + 1):
+    t0 = time.perf_counter()
+    score, cigar, off = eng.global_align(big, ref, qer, wbig)
+    dt = time.perf_counter() - t0
+    if r: best = min(best, dt)
+    st = eng.stats()
+assert np.array_equal(score, np.tile(z["score"], tiles)) and np.array_equal(cigar, np.tile(z["cigar"], tiles))
+line = {"metric": "global_alignments_per_sec", "alignments": int(len(big)), "seconds": best, "value": len(big) / best,
+        "band_cells": int(st["cells_effective"]), "gcups_band": st["cells_effective"] / best / 1e9,
+        "kernel_ms": st["ms_kernel"], "gcups_band_kernel_only": st["cells_effective"] / (st["ms_kernel"] * 1e-3) / 1e9,
+        "cigar_ops": int(len(cigar)), "gpu_launches": int(st["kernel_launches"]), "buffers": "pageable numpy arrays"}
+if KswReference.available():
+    K = KswReference(); P = make_params(**c["P"])
+    t0 = time.perf_counter(); done = 0
+    while time.perf_counter() - t0 < 3.0:
+        for k in range(len(pairs)):
+            K.global_align(P, qer[c["qoff"][k]: c["qoff"][k + 1]], ref[c["toff"][k]: c["toff"][k + 1]], int(z["w"][k]))
+        done += len(pairs)
+    dt = time.perf_counter() - t0
+    line["cpu_baseline"] = {"kind": "reference", "what": "ksw_global2 (tools/bwa/ksw.c, unmodified) called per pair through ctypes",
+                            "cores": 1, "value": done / dt, "unit": "alignments/s"}
+print(json.dumps(line))
+eng.close()
