@@ -165,6 +165,7 @@ struct bsw_engine {
     int32_t w = 0;
     std::vector<std::pair<int, int>> staged_chunks;   // (device, slot) per chunk, batch order
     void* gbufs = nullptr;                // device buffers of bsw_global (GlobalBufs, bsw_global.inl)
+    bool global_attr_set = false;
 };
 
 namespace {

@@ -70,7 +70,7 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
         // chunk: as many alignments as fit the direction-matrix, operation-list and row-scratch budgets
         hd.clear();
         long long zb = 0, cw = 0, qb = 0, rb = 0;
-        int qmax = 0;
+        int qmax = 0, wmax = 0;
         int64_t m = 0;
         while (done + m < n && m < 131072) {
             const SeqPair& sp = pairs[done + m];
@@ -80,10 +80,10 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
             const int qm = std::max(qmax, sp.len2);
             if (m > 0 && (zb + zi > Z_CAP || cw + ci > C_CAP || (long long)(qm + 1) * (m + 1) > EH_CAP)) break;
             GlobalDesc d;
-            d.qoff = (uint32_t)qb; d.roff = (uint32_t)rb; d.qlen = sp.len2; d.tlen = sp.len1; d.w = wv; d.pad = 0;
+            d.qoff = (uint32_t)qb; d.roff = (uint32_t)rb; d.qlen = sp.len2; d.tlen = sp.len1; d.w = wv; d.idx = (int32_t)m;
             d.zoff = zb; d.coff = cw;
             hd.push_back(d);
-            zb += zi; cw += ci; qb += sp.len2; rb += sp.len1; qmax = qm;
+            zb += zi; cw += ci; qb += sp.len2; rb += sp.len1; qmax = qm; wmax = std::max(wmax, wv);
             ++m;
         }
         hq.resize((size_t)qb); hr.resize((size_t)rb);
@@ -103,13 +103,19 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
             cells_part[(size_t)tid] += cells;
         });
         for (long long v : cells_part) S.cells_effective += v;
+        // threads run in order of decreasing target length: the lanes of a warp then finish together and
+        // the longest alignments start first (idx keeps the input position for the outputs)
+        std::stable_sort(hd.begin(), hd.end(), [](const GlobalDesc& a, const GlobalDesc& b) { return a.tlen > b.tlen; });
         const int threads = (int)m, stride = ((threads + 31) / 32) * 32;
         if (int rc = ensure(eng, B.desc, (size_t)m)) return rc;
         if (int rc = ensure(eng, B.q, (size_t)qb + 16)) return rc;
         if (int rc = ensure(eng, B.r, (size_t)rb + 16)) return rc;
         if (int rc = ensure(eng, B.z, (size_t)zb + 16)) return rc;
         if (int rc = ensure(eng, B.cig, (size_t)cw + 16)) return rc;
-        if (int rc = ensure(eng, B.eh, (size_t)(qmax + 1) * (size_t)stride)) return rc;
+        const int W = std::max(2 * wmax + 2, 16);                    // live columns of a row (bsw_global.cuh; >= 16: its 8-column blocks wrap once)
+        const size_t smem = (size_t)W * GLOBAL_BLOCK * sizeof(int2);
+        const bool use_smem = smem <= 200 * 1024;
+        if (!use_smem) if (int rc = ensure(eng, B.eh, (size_t)(qmax + 1) * (size_t)stride)) return rc;
         if (int rc = ensure(eng, B.score, (size_t)m)) return rc;
         if (int rc = ensure(eng, B.ncig, (size_t)m)) return rc;
         if (int rc = ensure(eng, B.off, (size_t)m + 1)) return rc;
@@ -117,8 +123,18 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
         CUDA_TRY(cudaMemcpyAsync(B.q.d, hq.data(), (size_t)qb, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(B.r.d, hr.data(), (size_t)rb, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaEventRecord(c.ev_t0, st));
-        bsw_global_kernel<<<(threads + 127) / 128, 128, 0, st>>>(B.desc.d, threads, B.q.d, B.r.d, B.eh.d, stride, B.z.d,
-                                                                 B.cig.d, B.score.d, B.ncig.d, GP);
+        const int gblocks = (threads + GLOBAL_BLOCK - 1) / GLOBAL_BLOCK;
+        if (use_smem) {
+            if (!eng->global_attr_set) {
+                CUDA_TRY(cudaFuncSetAttribute(bsw_global_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                eng->global_attr_set = true;
+            }
+            bsw_global_kernel<true><<<gblocks, GLOBAL_BLOCK, smem, st>>>(B.desc.d, threads, B.q.d, B.r.d, nullptr, 0, W, B.z.d,
+                                                                         B.cig.d, B.score.d, B.ncig.d, GP);
+        } else {
+            bsw_global_kernel<false><<<gblocks, GLOBAL_BLOCK, 0, st>>>(B.desc.d, threads, B.q.d, B.r.d, B.eh.d, stride, 0, B.z.d,
+                                                                       B.cig.d, B.score.d, B.ncig.d, GP);
+        }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(c.ev_t1, st));
         CUDA_TRY(cudaMemcpyAsync(score + done, B.score.d, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, st));

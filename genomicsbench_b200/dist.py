@@ -39,9 +39,23 @@ def init_dist(backend: Optional[str] = None) -> DistCtx:
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world,
-                                device_id=torch.device("cuda", local_rank))
+        # NCCL prints to the process's stdout while the communicator is created (at least its one-line
+        # "NCCL version ..." banner; NCCL_DEBUG_FILE does not catch it), where rank 0's single JSON line
+        # belongs: create the communicator -- init + a first collective -- with fd 1 pointing at stderr.
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local_rank))
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     else:
         dist.init_process_group(backend, rank=rank, world_size=world)
     return DistCtx(rank, world, local_rank, backend)
