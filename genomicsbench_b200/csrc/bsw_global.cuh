@@ -36,7 +36,8 @@ constexpr int GLOBAL_BLOCK = 64;
 template <bool SMEM>
 __global__ void __launch_bounds__(GLOBAL_BLOCK)
 bsw_global_kernel(const GlobalDesc* __restrict__ desc, int n, const uint8_t* __restrict__ qraw,
-                  const uint8_t* __restrict__ rraw, int2* __restrict__ eh, int stride, int W, uint8_t* __restrict__ z,
+                  const uint8_t* __restrict__ rraw, int2* __restrict__ eh, int stride, int W, int qstride,
+                  uint8_t* __restrict__ z,
                   uint32_t* __restrict__ cigar, int32_t* __restrict__ score, int32_t* __restrict__ n_cigar,
                   const GlobalParams P)
 {
@@ -51,6 +52,13 @@ bsw_global_kernel(const GlobalDesc* __restrict__ desc, int n, const uint8_t* __r
     if (SMEM) { stride = GLOBAL_BLOCK; }
     else W = 0x7fffffff;                         // no wrap: slot == column
     int2* row = SMEM ? g_rows + threadIdx.x : eh + t;      // row[slot * stride] = {h, e} of the column in that slot
+    if (SMEM) {
+        // the query moves to shared memory once (behind the rows; qstride = 4 x odd bytes per thread: the
+        // byte loads of a warp at the same column hit 32 banks): no global load is left in the cell loop
+        uint8_t* qs = reinterpret_cast<uint8_t*>(g_rows + (size_t)W * GLOBAL_BLOCK) + (size_t)threadIdx.x * qstride;
+        for (int k = 0; k < qlen; ++k) qs[k] = q[k];
+        q = qs;
+    }
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
     const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
     const int pitch = (n_col + 7) & ~7;          // bytes per row of the direction matrix (zoff is 8-aligned)

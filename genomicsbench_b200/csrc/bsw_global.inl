@@ -60,7 +60,7 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
     cudaStream_t st = c.cs[0];
     GlobalParams GP{eng->p.o_del, eng->p.e_del, eng->p.o_ins, eng->p.e_ins, eng->p.match, -eng->p.mismatch, eng->p.ambig};
     std::vector<GlobalDesc> hd;
-    std::vector<uint8_t> hq, hr;
+    std::vector<uint64_t> order;
     std::vector<long long> hoff;
     std::vector<int32_t> hn;
     const long long Z_CAP = 3ll << 30, C_CAP = 1ll << 28, EH_CAP = 1ll << 27;      // bytes / words / cells per chunk
@@ -86,15 +86,18 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
             zb += zi; cw += ci; qb += sp.len2; rb += sp.len1; qmax = qm; wmax = std::max(wmax, wv);
             ++m;
         }
-        hq.resize((size_t)qb); hr.resize((size_t)rb);
+        if (int rc = ensure(eng, B.q, (size_t)qb + 16, true)) return rc;      // pinned staging twins: the H2D copies run at link speed
+        if (int rc = ensure(eng, B.r, (size_t)rb + 16, true)) return rc;
+        if (int rc = ensure(eng, B.desc, (size_t)m, true)) return rc;
+        uint8_t* const hq = B.q.h; uint8_t* const hr = B.r.h;
         std::vector<long long> cells_part((size_t)eng->pool->size(), 0);
         eng->pool->for_range(m, 1024, [&](int64_t b, int64_t e, int tid) {
             long long cells = 0;
             for (int64_t k = b; k < e; ++k) {
                 const SeqPair& sp = pairs[done + k];
                 const GlobalDesc& d = hd[(size_t)k];
-                memcpy(hq.data() + d.qoff, seq_qer + sp.idq, (size_t)sp.len2);
-                memcpy(hr.data() + d.roff, seq_ref + sp.idr, (size_t)sp.len1);
+                memcpy(hq + d.qoff, seq_qer + sp.idq, (size_t)sp.len2);
+                memcpy(hr + d.roff, seq_ref + sp.idr, (size_t)sp.len1);
                 for (int i = 0; i < d.tlen; ++i) {                   // DP cells inside the band
                     const int beg = i > d.w ? i - d.w : 0, end = i + d.w + 1 < d.qlen ? i + d.w + 1 : d.qlen;
                     if (end > beg) cells += end - beg;
@@ -105,23 +108,29 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
         for (long long v : cells_part) S.cells_effective += v;
         // threads run in order of decreasing target length: the lanes of a warp then finish together and
         // the longest alignments start first (idx keeps the input position for the outputs)
-        std::stable_sort(hd.begin(), hd.end(), [](const GlobalDesc& a, const GlobalDesc& b) { return a.tlen > b.tlen; });
+        // (band width first: the column loop's trip count is what the lanes of a warp share row by row)
+        order.resize((size_t)m);
+        for (int64_t k = 0; k < m; ++k) {
+            const GlobalDesc& d = hd[(size_t)k];
+            const uint64_t band = (uint64_t)(d.qlen < 2 * d.w + 1 ? d.qlen : 2 * d.w + 1);
+            order[(size_t)k] = ~((band << 16 | (uint64_t)d.tlen) << 20) & ~0xfffffull | (uint64_t)k;   // descending work, then input order
+        }
+        std::sort(order.begin(), order.end());
+        for (int64_t k = 0; k < m; ++k) B.desc.h[k] = hd[(size_t)(order[(size_t)k] & 0xfffff)];
         const int threads = (int)m, stride = ((threads + 31) / 32) * 32;
-        if (int rc = ensure(eng, B.desc, (size_t)m)) return rc;
-        if (int rc = ensure(eng, B.q, (size_t)qb + 16)) return rc;
-        if (int rc = ensure(eng, B.r, (size_t)rb + 16)) return rc;
         if (int rc = ensure(eng, B.z, (size_t)zb + 16)) return rc;
         if (int rc = ensure(eng, B.cig, (size_t)cw + 16)) return rc;
         const int W = std::max(2 * wmax + 2, 16);                    // live columns of a row (bsw_global.cuh; >= 16: its 8-column blocks wrap once)
-        const size_t smem = (size_t)W * GLOBAL_BLOCK * sizeof(int2);
+        const int qstride = 4 * (((qmax + 3) / 4) | 1);               // query bytes per thread in shared memory
+        const size_t smem = (size_t)W * GLOBAL_BLOCK * sizeof(int2) + (size_t)qstride * GLOBAL_BLOCK;
         const bool use_smem = smem <= 200 * 1024;
         if (!use_smem) if (int rc = ensure(eng, B.eh, (size_t)(qmax + 1) * (size_t)stride)) return rc;
         if (int rc = ensure(eng, B.score, (size_t)m)) return rc;
         if (int rc = ensure(eng, B.ncig, (size_t)m)) return rc;
         if (int rc = ensure(eng, B.off, (size_t)m + 1)) return rc;
-        CUDA_TRY(cudaMemcpyAsync(B.desc.d, hd.data(), sizeof(GlobalDesc) * (size_t)m, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(B.q.d, hq.data(), (size_t)qb, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(B.r.d, hr.data(), (size_t)rb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(B.desc.d, B.desc.h, sizeof(GlobalDesc) * (size_t)m, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(B.q.d, hq, (size_t)qb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(B.r.d, hr, (size_t)rb, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaEventRecord(c.ev_t0, st));
         const int gblocks = (threads + GLOBAL_BLOCK - 1) / GLOBAL_BLOCK;
         if (use_smem) {
@@ -129,10 +138,10 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
                 CUDA_TRY(cudaFuncSetAttribute(bsw_global_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 eng->global_attr_set = true;
             }
-            bsw_global_kernel<true><<<gblocks, GLOBAL_BLOCK, smem, st>>>(B.desc.d, threads, B.q.d, B.r.d, nullptr, 0, W, B.z.d,
+            bsw_global_kernel<true><<<gblocks, GLOBAL_BLOCK, smem, st>>>(B.desc.d, threads, B.q.d, B.r.d, nullptr, 0, W, qstride, B.z.d,
                                                                          B.cig.d, B.score.d, B.ncig.d, GP);
         } else {
-            bsw_global_kernel<false><<<gblocks, GLOBAL_BLOCK, 0, st>>>(B.desc.d, threads, B.q.d, B.r.d, B.eh.d, stride, 0, B.z.d,
+            bsw_global_kernel<false><<<gblocks, GLOBAL_BLOCK, 0, st>>>(B.desc.d, threads, B.q.d, B.r.d, B.eh.d, stride, 0, 0, B.z.d,
                                                                        B.cig.d, B.score.d, B.ncig.d, GP);
         }
         CUDA_TRY(cudaGetLastError());

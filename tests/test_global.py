@@ -92,6 +92,20 @@ def test_bsw_global_edges_and_errors(lib, oracle):
             q = qer[pairs["idq"][k]: pairs["idq"][k] + pairs["len2"][k]]; t = ref[pairs["idr"][k]: pairs["idr"][k] + pairs["len1"][k]]
             sc, cg = oracle.global_align(P, q, t, wide)
             assert sc == score[k] and np.array_equal(cg, cigar[off[k]: off[k + 1]])
+        # a band too wide for the shared-memory rows (W = 2 w + 2 columns per thread): the kernel's
+        # global-scratch form runs instead
+        s300, c300, o300 = eng.global_align(pairs[:200], ref, qer, 300)
+        for k in range(0, 200, 7):
+            q = qer[pairs["idq"][k]: pairs["idq"][k] + pairs["len2"][k]]; t = ref[pairs["idr"][k]: pairs["idr"][k] + pairs["len1"][k]]
+            sc, cg = oracle.global_align(P, q, t, 300)
+            assert sc == s300[k] and np.array_equal(cg, c300[o300[k]: o300[k + 1]])
+        # w = 0: the diagonal only (equal lengths)
+        eq = np.flatnonzero(pairs["len1"] == pairs["len2"])[:50]
+        s0w, c0w, o0w = eng.global_align(pairs[eq], ref, qer, 0)
+        for j, k in enumerate(eq):
+            q = qer[pairs["idq"][k]: pairs["idq"][k] + pairs["len2"][k]]; t = ref[pairs["idr"][k]: pairs["idr"][k] + pairs["len1"][k]]
+            sc, cg = oracle.global_align(P, q, t, 0)
+            assert sc == s0w[j] and np.array_equal(cg, c0w[o0w[j]: o0w[j + 1]])
         perm = np.random.default_rng(3).permutation(len(pairs))
         s2, c2, o2 = eng.global_align(pairs[perm], ref, qer, z["w"][perm])
         assert np.array_equal(s2, z["score"][perm])
