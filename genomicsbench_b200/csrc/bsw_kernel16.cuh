@@ -518,7 +518,10 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
         }
         const int m = mkey >> 16;
         int mj = mkey & 0xffff;
-        if (m > st.max || st.max - m > P.zdrop) {
+        if (m > st.max || (m != 0 && st.max - m > P.zdrop)) {
+            // (m == 0 ends the pair in bsw_row_update before mj is looked at -- and an empty window leaves
+            // mkey = 0, whose "block" would lie in front of this thread's row: compute-sanitizer's racecheck
+            // flagged those reads against the neighbouring thread's stores)
             // the key names a block (its last column, mj + 1 a multiple of 8): the reference's mj is
             // the last column of [mj - 7, mj] whose H equals m (bandedSWA.cpp:202-203).  H(i, c) sits
             // in hs[c + 1]; the eight halves are flagged in parallel (1 where hs >= m: inside this
