@@ -34,17 +34,39 @@ inline void chain_empty_target(int h0, int w, int max_try, int prev0, SeqPair& r
 }
 
 struct ChainRun {
-    std::vector<uint64_t> srt;      // score << 32 | index, ascending (bwamem.c:661-665)
+    uint64_t* srt = nullptr;        // score << 32 | index, ascending (bwamem.c:661-665); a slice of one flat array
     int k = -1;                     // next position in srt, walking down
+};
+
+struct ChainBufs {                  // page-locked, grow-only staging of the left flanks; owned by the engine
+    void* lp = nullptr; void* lq = nullptr; void* lr = nullptr;
+    size_t lp_cap = 0, lq_cap = 0, lr_cap = 0;
+    static bool grow(void*& p, size_t& cap, size_t need)
+    {
+        if (need <= cap) return true;
+        if (p) bsw_host_free(p);
+        cap = need + need / 2;
+        p = bsw_host_alloc(cap);
+        if (!p) cap = 0;
+        return p != nullptr;
+    }
+    ~ChainBufs() { bsw_host_free(lp); bsw_host_free(lq); bsw_host_free(lr); }
 };
 
 struct ChainCand {                  // one seed being extended in the current round
     int64_t chain; int seed;        // seed index inside the chain
     int lpair = -1, rpair = -1;     // positions in the round's left / right batch, -1 = none
+    int64_t lq_off = 0, lr_off = 0; // byte offsets of the reversed left flanks in the staging buffers
     int aw0, aw1;
 };
 
 } // namespace
+
+static void bsw_chain_release(bsw_engine* eng)
+{
+    delete static_cast<ChainBufs*>(eng->cbufs);
+    eng->cbufs = nullptr;
+}
 
 int bsw_chain_window(const bsw_params* p, int32_t w, int64_t l_pac, const bsw_seed* seeds, int32_t n,
                      int32_t l_query, int64_t* rmax0, int64_t* rmax1)
@@ -88,35 +110,43 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
     const bsw_params& P = eng->p;
     std::vector<ChainRun> run((size_t)n_chains);
     std::vector<int64_t> group_first((size_t)n_chains);         // first chain of the read a chain belongs to
+    int64_t n_seeds_total = 0;
     for (int64_t c = 0; c < n_chains; ++c) {
         const bsw_chain& ch = chains[c];
         out_count[c] = 0;
+        if (ch.n_seeds < 0 || ch.l_query < 1 || ch.rmax1 < ch.rmax0 || ch.seed_first < 0) { eng->err = "bsw_extend_chains: malformed chain"; return BSW_ERR_PARAM; }
         group_first[(size_t)c] = (c > 0 && ch.same_read) ? group_first[(size_t)c - 1] : c;
         if (ch.same_read && (c == 0 || chains[c - 1].l_query != ch.l_query || chains[c - 1].query_off != ch.query_off)) {
             eng->err = "bsw_extend_chains: same_read set on a chain whose predecessor is another read";
             return BSW_ERR_PARAM;
         }
-        if (ch.n_seeds < 0 || ch.l_query < 1 || ch.rmax1 < ch.rmax0) { eng->err = "bsw_extend_chains: malformed chain"; return BSW_ERR_PARAM; }
-        ChainRun& R = run[(size_t)c];
-        R.srt.resize((size_t)ch.n_seeds);
-        for (int i = 0; i < ch.n_seeds; ++i) {
-            const bsw_seed& s = seeds[ch.seed_first + i];
-            if (s.len < 1 || s.qbeg < 0 || s.qbeg + s.len > ch.l_query || s.score < 1 || s.rbeg < ch.rmax0 ||
-                s.rbeg + s.len > ch.rmax1) {
-                eng->err = "bsw_extend_chains: seed outside its read or reference window";
-                return BSW_ERR_PARAM;
-            }
-            R.srt[(size_t)i] = (uint64_t)(uint32_t)s.score << 32 | (uint32_t)i;
-        }
-        std::sort(R.srt.begin(), R.srt.end());
-        R.k = ch.n_seeds - 1;
+        n_seeds_total = std::max(n_seeds_total, ch.seed_first + ch.n_seeds);
     }
+    std::vector<uint64_t> srt_all((size_t)n_seeds_total);       // every chain sorts its own slice [seed_first, + n_seeds)
+    std::atomic<int> bad_seed{0};
+    eng->pool->for_range(n_chains, 1024, [&](int64_t cb, int64_t ce, int) {
+        for (int64_t c = cb; c < ce; ++c) {
+            const bsw_chain& ch = chains[c];
+            ChainRun& R = run[(size_t)c];
+            R.srt = srt_all.data() + ch.seed_first;
+            for (int i = 0; i < ch.n_seeds; ++i) {
+                const bsw_seed& s = seeds[ch.seed_first + i];
+                if (s.len < 1 || s.qbeg < 0 || s.qbeg + s.len > ch.l_query || s.score < 1 || s.rbeg < ch.rmax0 ||
+                    s.rbeg + s.len > ch.rmax1) bad_seed.store(1, std::memory_order_relaxed);
+                R.srt[i] = (uint64_t)(uint32_t)s.score << 32 | (uint32_t)i;
+            }
+            std::sort(R.srt, R.srt + ch.n_seeds);
+            R.k = ch.n_seeds - 1;
+        }
+    });
+    if (bad_seed.load()) { eng->err = "bsw_extend_chains: seed outside its read or reference window"; return BSW_ERR_PARAM; }
 
     bsw_stats total;
     memset(&total, 0, sizeof(total));
     std::vector<ChainCand> cand;
-    std::vector<SeqPair> lp, rp;
-    std::vector<uint8_t> lq, lr;
+    std::vector<SeqPair> rp;
+    if (!eng->cbufs) eng->cbufs = new ChainBufs();
+    ChainBufs& CB = *static_cast<ChainBufs*>(eng->cbufs);
     std::vector<int32_t> band, prev, pick;
     std::vector<uint8_t> done_before((size_t)n_chains, 0);      // chain had no seed left when the round began
     auto add_stats = [&]() {
@@ -127,7 +157,12 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
         total.n_short += s.n_short; total.n_long += s.n_long;
     };
 
+    double tl[6] = {0, 0, 0, 0, 0, 0};          // BSW_TIMELINE: pick / left build / left GPU / right build / right GPU / finish
+    int rounds = 0;
+    double t_mark = now_ms();
+    auto lap = [&](int k) { const double t = now_ms(); tl[k] += t - t_mark; t_mark = t; };
     for (;;) {
+        ++rounds;
         // ---- next surviving seed of every chain (containment test, bwamem.c:667-700) ------------
         cand.clear();
         pick.assign((size_t)n_chains, -1);
@@ -154,7 +189,7 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
             };
             while (R.k >= 0) {
                 const int k = R.k;
-                const bsw_seed& s = S[(uint32_t)R.srt[(size_t)k]];
+                const bsw_seed& s = S[(uint32_t)R.srt[k]];
                 int i;
                 for (i = 0; i < n_av; ++i) {
                     const bsw_alnreg& p = reg_at(i);
@@ -171,15 +206,15 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
                 }
                 if (i < n_av) {
                     for (i = k + 1; i < ch.n_seeds; ++i) {
-                        if (R.srt[(size_t)i] == 0) continue;
-                        const bsw_seed& t = S[(uint32_t)R.srt[(size_t)i]];
+                        if (R.srt[i] == 0) continue;
+                        const bsw_seed& t = S[(uint32_t)R.srt[i]];
                         if (t.len < s.len * .95) continue;
                         if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
                         if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
                     }
-                    if (i == ch.n_seeds) { R.srt[(size_t)k] = 0; --R.k; continue; }     // contained: no extension
+                    if (i == ch.n_seeds) { R.srt[k] = 0; --R.k; continue; }     // contained: no extension
                 }
-                pick[(size_t)c] = (int)(uint32_t)R.srt[(size_t)k];
+                pick[(size_t)c] = (int)(uint32_t)R.srt[k];
                 break;
             }
         }
@@ -191,49 +226,60 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
             cand.push_back(cd);
         }
         if (cand.empty()) break;
+        lap(0);
 
         // ---- left flanks: reversed query prefix and reference flank, h0 = len * a (:709-753) -----
-        lp.clear();
-        size_t qbytes = 0, rbytes = 0;
+        // Offsets first (a running sum over the candidates), then pairs, region headers and the reversed
+        // copies on the thread pool, straight into page-locked buffers: the extension call then takes the
+        // engine's direct route (DMA of records and bytes as they are, no second host pass).
+        size_t qbytes = 0, rbytes = 0, n_left = 0;
         for (ChainCand& cd : cand) {
             const bsw_chain& ch = chains[cd.chain];
             const bsw_seed& s = seeds[ch.seed_first + cd.seed];
-            bsw_alnreg& a = out[ch.seed_first + out_count[cd.chain]];
-            memset(&a, 0, sizeof(a));
-            a.w = w; a.score = a.truesc = -1;
             const int64_t tmp = s.rbeg - ch.rmax0;
+            cd.lpair = -1;
             if (s.qbeg > 0 && tmp > 0) {
-                SeqPair sp;
-                memset(&sp, 0, sizeof(sp));
-                sp.idq = (int64_t)qbytes; sp.idr = (int64_t)rbytes; sp.id = (int64_t)lp.size();
-                sp.len2 = s.qbeg; sp.len1 = (int32_t)std::min<int64_t>(tmp, 0x7fffffff); sp.h0 = s.len * P.match;
                 if (tmp > 32767) { eng->err = "bsw_extend_chains: left reference flank longer than 32767"; return BSW_ERR_DOMAIN; }
-                cd.lpair = (int)lp.size();
-                lp.push_back(sp);
+                cd.lpair = (int)n_left++;
+                cd.lq_off = (int64_t)qbytes; cd.lr_off = (int64_t)rbytes;
                 qbytes += (size_t)s.qbeg; rbytes += (size_t)tmp;
             }
         }
-        if (!lp.empty()) {
-            lq.resize(qbytes + 64); lr.resize(rbytes + 64);
-            eng->pool->for_range((int64_t)cand.size(), 256, [&](int64_t b, int64_t e, int) {
-                for (int64_t x = b; x < e; ++x) {
-                    const ChainCand& cd = cand[(size_t)x];
-                    if (cd.lpair < 0) continue;
-                    const bsw_chain& ch = chains[cd.chain];
-                    const bsw_seed& s = seeds[ch.seed_first + cd.seed];
-                    const SeqPair& sp = lp[(size_t)cd.lpair];
-                    const uint8_t* q = query + ch.query_off;
-                    const uint8_t* r = ref + ch.ref_off;
-                    uint8_t* dq = lq.data() + sp.idq; uint8_t* dr = lr.data() + sp.idr;
-                    for (int i = 0; i < s.qbeg; ++i) dq[i] = q[s.qbeg - 1 - i];
-                    const int64_t tmp = s.rbeg - ch.rmax0;
-                    for (int64_t i = 0; i < tmp; ++i) dr[i] = r[tmp - 1 - i];
-                }
-            });
-            band.assign(lp.size(), w);
-            if (int rc = bsw_extend_retry(eng, lp.data(), lr.data(), lq.data(), (int64_t)lp.size(), w, max_try, nullptr, band.data()))
+        if (!CB.grow(CB.lp, CB.lp_cap, (n_left + 16) * sizeof(SeqPair)) || !CB.grow(CB.lq, CB.lq_cap, qbytes + 64) ||
+            !CB.grow(CB.lr, CB.lr_cap, rbytes + 64)) {
+            eng->err = "bsw_extend_chains: page-locked staging allocation failed";
+            return BSW_ERR_NOMEM;
+        }
+        SeqPair* lp = static_cast<SeqPair*>(CB.lp);
+        uint8_t* lq = static_cast<uint8_t*>(CB.lq); uint8_t* lr = static_cast<uint8_t*>(CB.lr);
+        eng->pool->for_range((int64_t)cand.size(), 256, [&](int64_t b, int64_t e, int) {
+            for (int64_t x = b; x < e; ++x) {
+                const ChainCand& cd = cand[(size_t)x];
+                const bsw_chain& ch = chains[cd.chain];
+                const bsw_seed& s = seeds[ch.seed_first + cd.seed];
+                bsw_alnreg& a = out[ch.seed_first + out_count[cd.chain]];
+                memset(&a, 0, sizeof(a));
+                a.w = w; a.score = a.truesc = -1;
+                if (cd.lpair < 0) continue;
+                const int64_t tmp = s.rbeg - ch.rmax0;
+                SeqPair& sp = lp[cd.lpair];
+                memset(&sp, 0, sizeof(sp));
+                sp.idq = cd.lq_off; sp.idr = cd.lr_off; sp.id = cd.lpair;
+                sp.len2 = s.qbeg; sp.len1 = (int32_t)tmp; sp.h0 = s.len * P.match;
+                const uint8_t* q = query + ch.query_off;
+                const uint8_t* r = ref + ch.ref_off;
+                uint8_t* dq = lq + cd.lq_off; uint8_t* dr = lr + cd.lr_off;
+                for (int i = 0; i < s.qbeg; ++i) dq[i] = q[s.qbeg - 1 - i];
+                for (int64_t i = 0; i < tmp; ++i) dr[i] = r[tmp - 1 - i];
+            }
+        });
+        if (n_left > 0) {
+            band.assign(n_left, w);
+            lap(1);
+            if (int rc = bsw_extend_retry(eng, lp, lr, lq, (int64_t)n_left, w, max_try, nullptr, band.data()))
                 return rc;
             add_stats();
+            lap(2);
         }
         eng->pool->for_range((int64_t)cand.size(), 1024, [&](int64_t xb, int64_t xe, int) {
         for (int64_t x = xb; x < xe; ++x) {
@@ -258,29 +304,41 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
         });
 
         // ---- right flanks: read in place, h0 = the left score (:765-800) -------------------------
-        rp.clear(); prev.clear();
+        size_t n_right = 0;
         for (ChainCand& cd : cand) {
             const bsw_chain& ch = chains[cd.chain];
             const bsw_seed& s = seeds[ch.seed_first + cd.seed];
-            const bsw_alnreg& a = out[ch.seed_first + out_count[cd.chain]];
+            cd.rpair = -1;
             if (s.qbeg + s.len == ch.l_query) continue;
-            const int qe = s.qbeg + s.len;
-            const int64_t re = s.rbeg + s.len - ch.rmax0;
-            const int64_t tlen = ch.rmax1 - ch.rmax0 - re;
+            const int64_t tlen = ch.rmax1 - ch.rmax0 - (s.rbeg + s.len - ch.rmax0);
             if (tlen <= 0) continue;
             if (tlen > 32767) { eng->err = "bsw_extend_chains: right reference flank longer than 32767"; return BSW_ERR_DOMAIN; }
-            SeqPair sp;
-            memset(&sp, 0, sizeof(sp));
-            sp.idq = ch.query_off + qe; sp.idr = ch.ref_off + re; sp.id = (int64_t)rp.size();
-            sp.len2 = ch.l_query - qe; sp.len1 = (int32_t)tlen; sp.h0 = a.score;
-            cd.rpair = (int)rp.size();
-            rp.push_back(sp); prev.push_back(a.score);
+            cd.rpair = (int)n_right++;
         }
+        rp.resize(n_right); prev.resize(n_right);
+        eng->pool->for_range((int64_t)cand.size(), 1024, [&](int64_t xb, int64_t xe, int) {
+            for (int64_t x = xb; x < xe; ++x) {
+                const ChainCand& cd = cand[(size_t)x];
+                if (cd.rpair < 0) continue;
+                const bsw_chain& ch = chains[cd.chain];
+                const bsw_seed& s = seeds[ch.seed_first + cd.seed];
+                const bsw_alnreg& a = out[ch.seed_first + out_count[cd.chain]];
+                const int qe = s.qbeg + s.len;
+                const int64_t re = s.rbeg + s.len - ch.rmax0;
+                SeqPair& sp = rp[(size_t)cd.rpair];
+                memset(&sp, 0, sizeof(sp));
+                sp.idq = ch.query_off + qe; sp.idr = ch.ref_off + re; sp.id = cd.rpair;
+                sp.len2 = ch.l_query - qe; sp.len1 = (int32_t)(ch.rmax1 - ch.rmax0 - re); sp.h0 = a.score;
+                prev[(size_t)cd.rpair] = a.score;
+            }
+        });
         if (!rp.empty()) {
             band.assign(rp.size(), w);
+            lap(3);
             if (int rc = bsw_extend_retry(eng, rp.data(), ref, query, (int64_t)rp.size(), w, max_try, prev.data(), band.data()))
                 return rc;
             add_stats();
+            lap(4);
         }
         eng->pool->for_range((int64_t)cand.size(), 1024, [&](int64_t xb, int64_t xe, int) {
         for (int64_t x = xb; x < xe; ++x) {
@@ -316,6 +374,10 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
         }
         });
     }
+    lap(5);
+    if (g_timeline)
+        fprintf(stderr, "bsw_extend_chains: %d rounds; ms: pick %.2f, left build %.2f, left GPU %.2f, right build + decisions %.2f, "
+                        "right GPU %.2f, finish %.2f\n", rounds, tl[0], tl[1], tl[2], tl[3], tl[4], tl[5]);
     eng->stats = total;
     return BSW_OK;
 }

@@ -166,6 +166,7 @@ struct bsw_engine {
     std::vector<std::pair<int, int>> staged_chunks;   // (device, slot) per chunk, batch order
     void* gbufs = nullptr;                // device buffers of bsw_global (GlobalBufs, bsw_global.inl)
     bool global_attr_set = false;
+    void* cbufs = nullptr;                // page-locked staging of bsw_extend_chains (ChainBufs, bsw_chain.inl)
 };
 
 namespace {
@@ -1070,11 +1071,13 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
 }
 
 static void bsw_global_release(bsw_engine* eng);      // bsw_global.inl
+static void bsw_chain_release(bsw_engine* eng);       // bsw_chain.inl
 
 void bsw_destroy(bsw_engine* eng)
 {
     if (!eng) return;
     bsw_global_release(eng);
+    bsw_chain_release(eng);
     for (DevCtx& c : eng->devs) {
         cudaSetDevice(c.dev);
         cudaDeviceSynchronize();
