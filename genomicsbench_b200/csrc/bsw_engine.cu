@@ -93,6 +93,7 @@ const GreenApi& green_api() { static GreenApi g; return g; }
 struct Launch {
     int first, count;     // range in the chunk's processing order
     int qstride;          // shared-memory rows per thread
+    int block;            // threads (= pairs) per block: 64, or 32 where that keeps more warps resident
 };
 
 template <class T>
@@ -224,6 +225,20 @@ inline int stride_for(int qmax, bool fine = false)
     return 4 * q;
 }
 
+// Block size of the packed kernel for a shared-memory class: a block's footprint (rows + query plane + 2 KB
+// score table + 1 KB the SM reserves) only fits the SM's 228 KB a whole number of times, and for some
+// classes 32-thread blocks leave less of it unused than 64-thread ones -- one more resident warp where
+// there are only four to seven.  BSW_SHORT_BLOCK=64 / 32 in the environment forces one size.
+inline int short16_block(int qstride)
+{
+    static const int forced = getenv("BSW_SHORT_BLOCK") ? atoi(getenv("BSW_SHORT_BLOCK")) : 0;
+    if (forced == 32 || forced == 64) return forced;
+    const int sm_bytes = 228 * 1024;
+    const int w64 = std::min((int)(sm_bytes / (k16::smem_bytes(64, qstride) + 1024)), 14) * 2;   // 71 registers: 14 blocks of 64
+    const int w32 = std::min((int)(sm_bytes / (k16::smem_bytes(32, qstride) + 1024)), 28);
+    return w32 > w64 ? 32 : 64;
+}
+
 // dynamic shared memory of one short-kernel block: eh words + the 2-bit query byte plane
 inline size_t short_smem_bytes(int qstride)
 {
@@ -249,6 +264,8 @@ int set_kernel_attrs(bsw_engine* eng, DevCtx& c)
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
     CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<SHORT_BLOCK, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
     c.attr_set = true;
     return BSW_OK;
 }
@@ -627,7 +644,7 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
                 if (!cnt) continue;
                 const int qs = stride_for(l, eng->use16);
                 if (!s.plan.empty() && s.plan.back().qstride == qs) s.plan.back().count += cnt;
-                else s.plan.push_back(Launch{pos, cnt, qs});
+                else s.plan.push_back(Launch{pos, cnt, qs, eng->use16 ? short16_block(qs) : SHORT_BLOCK});
                 pos += cnt;
             }
         }
@@ -660,8 +677,15 @@ int launch_dp(bsw_engine* eng, DevCtx& c, Slot& s, bool partitioned = false)
     for (int k = nl - 1; k >= 0; --k, ++li) {
         const Launch& L = s.plan[(size_t)k];
         cudaStream_t st = cs[li % NSTREAMS];
-        const int grid = (L.count + SHORT_BLOCK - 1) / SHORT_BLOCK;
-        if (!eng->use16)
+        const int grid = (L.count + L.block - 1) / L.block;
+        if (eng->use16 && L.block == 32) {
+            if (eng->kp.oe_del == eng->kp.oe_ins)
+                bsw_short16_kernel<32, true><<<grid, 32, k16::smem_bytes(32, L.qstride), st>>>(
+                    s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
+            else
+                bsw_short16_kernel<32, false><<<grid, 32, k16::smem_bytes(32, L.qstride), st>>>(
+                    s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
+        } else if (!eng->use16)
             bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, short_smem_bytes(L.qstride), st>>>(
                 s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
         else if (eng->kp.oe_del == eng->kp.oe_ins)

@@ -66,6 +66,56 @@ def test_no_cpu_fallback(lib):
 def test_product_does_not_reference_oracle():
     """The oracle is test infrastructure: nothing in the package may import / link it."""
     pkg = ROOT / "genomicsbench_b200"
-    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.h")) + list(pkg.rglob("*.cuh")):
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.h")) + \
+            list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.inl")):
         t = p.read_text()
-        assert "pyoracle" not in t and "ksw_oracle" not in t and "libbsw_oracle" not in t and "libbswref" not in t, p
+        for word in ("pyoracle", "ksw_oracle", "chain_oracle", "global_oracle", "libbsw_oracle", "libbswref", "libbwamemref",
+                     "libkswref"):
+            assert word not in t, (p, word)
+
+
+def test_header_compiles_as_c_and_layouts_match_the_mirrors(lib, tmp_path):
+    """include/bsw.h is a C header (plain pointers and sizes): compile it with gcc -std=c99 and compare the
+    sizes / offsets the C compiler sees with the numpy and ctypes mirrors the tests and the Python class use."""
+    import shutil
+    import subprocess
+    from genomicsbench_b200._lib import (ALNREG_DTYPE, CHAIN_DTYPE, SEED_DTYPE, BswChainOpt, BswGenConfig, BswParams,
+                                         BswStats)
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    src = tmp_path / "layout.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "bsw.h"
+#define S(T) printf(#T " %zu\\n", sizeof(T))
+#define O(T, F) printf(#T "." #F " %zu\\n", offsetof(T, F))
+int main(void) {
+    S(SeqPair); O(SeqPair, len1); O(SeqPair, h0); O(SeqPair, score); O(SeqPair, max_off);
+    S(bsw_params); S(bsw_stats); O(bsw_stats, kernel_launches); O(bsw_stats, partitioned); S(bsw_gen_config);
+    S(bsw_seed); O(bsw_seed, qbeg); O(bsw_seed, score);
+    S(bsw_chain); O(bsw_chain, l_query); O(bsw_chain, rmax0); O(bsw_chain, ref_off); O(bsw_chain, same_read);
+    S(bsw_alnreg); O(bsw_alnreg, qb); O(bsw_alnreg, truesc); O(bsw_alnreg, seedlen0);
+    S(bsw_chain_opt);
+    return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    got = {k: int(v) for k, v in got.items()}
+    sp = lib.SEQPAIR_DTYPE
+    assert got["SeqPair"] == sp.itemsize == 72
+    for f in ("len1", "h0", "score", "max_off"):
+        assert got[f"SeqPair.{f}"] == sp.fields[f][1]
+    assert got["bsw_params"] == C.sizeof(BswParams) and got["bsw_stats"] == C.sizeof(BswStats)
+    assert got["bsw_stats.kernel_launches"] == BswStats.kernel_launches.offset
+    assert got["bsw_stats.partitioned"] == BswStats.partitioned.offset
+    assert got["bsw_gen_config"] == C.sizeof(BswGenConfig) and got["bsw_chain_opt"] == C.sizeof(BswChainOpt)
+    for name, dt, fields in (("bsw_seed", SEED_DTYPE, ("qbeg", "score")),
+                             ("bsw_chain", CHAIN_DTYPE, ("l_query", "rmax0", "ref_off", "same_read")),
+                             ("bsw_alnreg", ALNREG_DTYPE, ("qb", "truesc", "seedlen0"))):
+        assert got[name] == dt.itemsize, name
+        for f in fields:
+            assert got[f"{name}.{f}"] == dt.fields[f][1], (name, f)
