@@ -124,6 +124,7 @@ struct Slot {
     // chunk state
     int64_t a = 0; int n = 0;             // pairs [a, a + n) of the batch
     bool direct = false;
+    bool seq_on_device = false;           // both sequence buffers are device copies with >= 64 bytes of slack behind them
     const uint8_t* qbase = nullptr;       // device-visible address of descriptor offset 0 (query / reference)
     const uint8_t* rbase = nullptr;
     ChunkInfo info;                       // host copy used for planning
@@ -469,6 +470,7 @@ int direct_sequences(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8
     struct Side { const uint8_t* host; long long base0; unsigned long long mn, mx, bases; Buf<uint8_t>* buf; const uint8_t** out; };
     Side sides[2] = {{seq_qer, base0_q, s.info.min_q, s.info.max_q, s.info.qbases, &s.qraw, &s.qbase},
                      {seq_ref, base0_r, s.info.min_r, s.info.max_r, s.info.tbases, &s.rraw, &s.rbase}};
+    s.seq_on_device = true;
     for (int k = 0; k < 2; ++k) {
         Side& sd = sides[k];
         const long long lo = sd.base0 + ((long long)sd.mn - OFF_BIAS);       // absolute byte offsets [lo, hi)
@@ -490,6 +492,7 @@ int direct_sequences(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8
             void* dp = nullptr;
             CUDA_TRY(cudaHostGetDevicePointer(&dp, const_cast<uint8_t*>(sd.host), 0));
             *sd.out = static_cast<const uint8_t*>(dp) + sd.base0;
+            s.seq_on_device = false;                                        // host memory read in place: it may end with the last base
             eng->stats.h2d_bytes += (int64_t)sd.bases;
         }
     }
@@ -577,6 +580,7 @@ int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t
     CUDA_TRY(cudaMemcpyAsync(s.qraw.d, s.qraw.h, (size_t)qtot + 64, cudaMemcpyHostToDevice, s.st));
     CUDA_TRY(cudaMemcpyAsync(s.rraw.d, s.rraw.h, (size_t)rtot + 64, cudaMemcpyHostToDevice, s.st));
     s.qbase = s.qraw.d; s.rbase = s.rraw.d;
+    s.seq_on_device = true;
     eng->stats.h2d_bytes += (int64_t)(sizeof(int4) * (size_t)n + qtot + rtot + 128);
     return BSW_OK;
 }
@@ -633,7 +637,8 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
             // 2-bit packing in processing order
             bsw_pack_pairs<<<grid_for(c, I.n_short, PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.desc.d, s.perm.d, I.n_short, s.qbase, s.rbase,
                                                                           s.meta.d, s.qpk.d, s.tpk.d, s.nlist.d, s.d_info,
-                                                                          eng->use16 ? eng->p.match : 0);
+                                                                          eng->use16 ? eng->p.match : 0,
+                                                                          s.seq_on_device ? 1 : 0);
             TL_MARK(4);
             eng->stats.kernel_launches += 3;
             // launch plan: the processing order ascends in len2, so the shared-memory classes are
@@ -821,21 +826,27 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
     }
     eng->stats.partitioned = partitioned ? 1 : 0;
     // chunk boundaries: a small first chunk (the first DP starts after a short H2D), full-size
-    // chunks, then a geometric ramp-down so that the work left after the last H2D (its DP and its
-    // D2H) is small.  PCIe-bound batches use smaller full-size chunks, sized so that the DP of one
+    // chunks, then -- where transfers or the host bound the batch -- a geometric ramp-down so that the
+    // work left after the last H2D (its DP and its D2H) is small.  PCIe-bound batches use smaller full-size chunks, sized so that the DP of one
     // chunk finishes while the next arrives; compute-bound ones ramp up to large chunks (fewer
     // launch tails, better bucketing).
     // (pageable buffers: the host passes are the bottleneck and want large chunks for their thread pool)
     const bool small_chunks = pcie_bound && direct;
-    const int64_t big = small_chunks ? CHUNK_PCIE : chunk_pairs;
+    static const int64_t env_chunk = getenv("BSW_CHUNK") ? atoll(getenv("BSW_CHUNK")) : 0;          // experiments
+    static const int env_rampdown = getenv("BSW_RAMPDOWN") ? atoi(getenv("BSW_RAMPDOWN")) : -1;
+    const int64_t big = small_chunks ? CHUNK_PCIE : (env_chunk > 0 && !keep ? env_chunk : chunk_pairs);
     const int64_t tail_min = small_chunks ? CHUNK_MIN / 2 : CHUNK_MIN;    // the last chunk's latency is all tail
+    // (a compute-bound batch on pinned buffers has all its data on the device long before the DP is done:
+    // small last chunks only add launches with few blocks -- scripts/chunk_probe.py: large mix 23.1 -> 21.9 ms)
+    const bool rampdown = env_rampdown >= 0 ? env_rampdown != 0 : (small_chunks || !direct);
     std::vector<int64_t> cut{0};
-    int64_t ramp = keep ? big : CHUNK_MIN;
+    static const int64_t env_first = getenv("BSW_FIRST_CHUNK") ? atoll(getenv("BSW_FIRST_CHUNK")) : 0;
+    int64_t ramp = keep ? big : (env_first > 0 && !small_chunks ? env_first : CHUNK_MIN);
     for (int64_t rem = n; rem > 0;) {
         int64_t sz;
         if (ramp < big && rem > 4 * ramp) { sz = ramp; ramp = small_chunks ? big : ramp * 2; }
         else if (keep || rem > 2 * big) sz = std::min(rem, big);
-        else if (rem > 2 * tail_min) sz = std::min(rem, ((rem + 1) / 2 + 4095) & ~(int64_t)4095);
+        else if (rampdown && rem > 2 * tail_min) sz = std::min(rem, ((rem + 1) / 2 + 4095) & ~(int64_t)4095);
         else sz = rem;
         cut.push_back(cut.back() + sz);
         rem -= sz;

@@ -163,10 +163,13 @@ bsw_scan_pairs(const SeqPair* __restrict__ pairs, int n, long long base0_r, long
 // `room` = bytes of the sequence from src on: the word-wise path may touch up to 3 bytes past its
 // 16 and is only taken when they still belong to the sequence (the buffer may be host memory
 // that ends with it).
-__device__ __forceinline__ uint32_t bsw_pack16(const uint8_t* src, int nb, int room, uint32_t& bad)
+// `overread` = the bytes behind the sequence may be read (device copy with slack behind it): the last,
+// partial word of a sequence then takes the word-wise path too, with the bytes past nb masked off --
+// otherwise every sequence ends in a byte loop that half the warp waits for.
+__device__ __forceinline__ uint32_t bsw_pack16(const uint8_t* src, int nb, int room, uint32_t& bad, bool overread)
 {
     uint32_t out = 0;
-    if (room >= 20) {
+    if (room >= 20 || overread) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(src);
         const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
         const unsigned sh = (unsigned)(a & 3) * 8u;
@@ -177,6 +180,8 @@ __device__ __forceinline__ uint32_t bsw_pack16(const uint8_t* src, int nb, int r
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             uint32_t v = __funnelshift_r(w[k], w[k + 1], sh);
+            const int valid = nb - 4 * k;                 // bytes of this word that belong to the sequence
+            if (valid < 4) v = valid <= 0 ? 0u : v & ((1u << (8 * valid)) - 1u);
             bad |= v & 0xFCFCFCFCu;
             v &= 0x03030303u;
             v = (v | (v >> 6)) & 0x000F000Fu;
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(PREP_BLOCK)
 bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm, int n_sorted,
                const uint8_t* __restrict__ qraw, const uint8_t* __restrict__ rraw, int4* __restrict__ meta,
                uint32_t* __restrict__ qpk, uint32_t* __restrict__ tpk,
-               uint32_t* __restrict__ nlist, ChunkInfo* __restrict__ info, int packed16_match)
+               uint32_t* __restrict__ nlist, ChunkInfo* __restrict__ info, int packed16_match, int overread)
 {
     constexpr int NW = PREP_BLOCK / 32;
     __shared__ uint32_t s_pre[NW][2][33];
@@ -263,7 +268,7 @@ bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm,
                 const uint8_t* src = (kind ? rraw + dd.y : qraw + dd.x) + 16 * (int)wi;
                 uint32_t bad = 0;
                 const int room = len - 16 * (int)wi;
-                const uint32_t word = bsw_pack16(src, min(16, room), room, bad);
+                const uint32_t word = bsw_pack16(src, min(16, room), room, bad, overread != 0);
                 (kind ? tpk + bt : qpk + bq)[wv] = word;
                 if (bad) atomicOr(&s_bad[wib][lo], 1u);
             }
