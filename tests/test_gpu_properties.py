@@ -66,6 +66,43 @@ def test_multi_engine_same_device(lib):
     e1.close(); e2.close()
 
 
+def test_concurrent_engines_from_threads(lib):
+    """The reference driver's OpenMP loop shape (main_banded.cpp:253-291): one engine per caller thread, all
+    on the same GPU at once, two on pinned buffers (direct route) and two on pageable ones (staged route).
+    Results equal a single engine's."""
+    import threading
+    cfg = lib.gen_named_config("large")
+    pairs, ref, qer = lib.gen_pairs(cfg, 0, 120_000)
+    with lib.Engine() as e0:
+        want = pairs.copy()
+        e0.extend(want, ref, qer, 100)
+    parts = np.array_split(np.arange(len(pairs)), 4)
+    outs = [pairs[p].copy() for p in parts]
+    pin = [(lib.pinned_copy(o), lib.pinned_copy(ref), lib.pinned_copy(qer)) for o in outs[:2]]
+    errors = []
+
+    def work(k):
+        try:
+            with lib.Engine() as e:
+                for _ in range(2):
+                    if k < 2:
+                        e.extend(pin[k][0], pin[k][1], pin[k][2], 100)
+                    else:
+                        e.extend(outs[k], ref, qer, 100)
+        except Exception as exc:                                     # surfaced below, in the main thread
+            errors.append((k, exc))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(4):
+        got = pin[k][0] if k < 2 else outs[k]
+        assert np.array_equal(results_matrix(got), results_matrix(want)[parts[k]]), k
+
+
 def test_direct_route_equals_staged_route(lib, oracle):
     """Pinned host buffers (bsw_host_alloc) take the engine's direct route -- records and sequences
     DMA'd as they are, results written into the records from the device; pageable buffers take the
