@@ -446,7 +446,8 @@ int direct_begin(bsw_engine* eng, DevCtx& c, Slot& s, const SeqPair* pairs, cons
     for (int k = 0; k < 2; ++k) {
         Side& sd = sides[k];
         s.spec[k] = false;
-        if (sd.lo < 0 || sd.hi <= sd.lo || f.len1 < 1 || f.len2 < 1 || l.len1 < 1 || l.len2 < 1) continue;
+        if (sd.lo < 0 || sd.hi <= sd.lo || f.len1 < 1 || f.len2 < 1 || l.len1 < 1 || l.len2 < 1 ||
+            f.len1 > 32767 || f.len2 > 32767 || l.len1 > 32767 || l.len2 > 32767) continue;     // out of domain: the scan reports it
         const long long lo_al = sd.lo & ~15ll;                              // keep the source's 16-byte phase
         const double span = (double)(sd.hi - lo_al);
         if (span > 2.0 * sd.est + (double)(1 << 20) || span > 3.0e9) continue;   // sparse (or not in record order): wait for the scan

@@ -187,6 +187,15 @@ def test_domain_errors(lib):
             with pytest.raises(lib.BswError) as ei:
                 eng.extend(bad, buf, buf, 100)
             assert ei.value.code == -2
+        # the same on page-locked buffers (direct route: the device-side scan finds it; the speculative
+        # sequence copy must not act on a malformed first / last record)
+        pbuf = lib.pinned_copy(np.zeros(1 << 16, np.uint8))
+        for field, val, at in (("len2", 40000, 0), ("len1", 0, 1), ("h0", 0, 1), ("len1", 50000, 1)):
+            bad = lib.pinned_copy(pairs)
+            bad[field][at] = val
+            with pytest.raises(lib.BswError) as ei:
+                eng.extend(bad, pbuf, pbuf, 100)
+            assert ei.value.code == -2, (field, val)
         with pytest.raises(lib.BswError) as ei:
             eng.run_staged()
         assert ei.value.code == -5
