@@ -175,8 +175,9 @@ class BandedPairWiseSW:
     def __init__(self, o_del: int, e_del: int, o_ins: int, e_ins: int, zdrop: int, end_bonus: int,
                  mat: Optional[Sequence[int]], w_match: int, w_mismatch: int, numThreads: int = 1,
                  devices: Optional[Sequence[int]] = None):
+        # tiny_batch: like the C++ class (csrc/bsw_shim.cpp) -- the reference driver's habit is -b 512 pairs per call
         self._kw = dict(o_del=o_del, e_del=e_del, o_ins=o_ins, e_ins=e_ins, zdrop=zdrop,
-                        end_bonus=end_bonus, match=w_match, mismatch=w_mismatch)
+                        end_bonus=end_bonus, match=w_match, mismatch=w_mismatch, tiny_batch=1536)
         if devices is not None:
             self._kw["devices"] = list(devices)
         self._mat = None if mat is None else [int(x) for x in mat]

@@ -124,6 +124,7 @@ struct Slot {
     // chunk state
     int64_t a = 0; int n = 0;             // pairs [a, a + n) of the batch
     bool direct = false;
+    bool tiny = false;                    // latency route: every pair goes to the warp-per-pair kernel (run_pipeline)
     bool seq_on_device = false;           // both sequence buffers are device copies with >= 64 bytes of slack behind them
     const uint8_t* qbase = nullptr;       // device-visible address of descriptor offset 0 (query / reference)
     const uint8_t* rbase = nullptr;
@@ -322,6 +323,7 @@ int validate_params(const bsw_params* p, std::string& why)
     if (p->n_devices < 0 || p->n_devices > 16) return bad("n_devices must be in 0..16");
     if (p->long_min_qlen < 0) return bad("long_min_qlen must be >= 0");
     if (p->short_variant != BSW_SHORT_PACKED16 && p->short_variant != BSW_SHORT_WIDE32) return bad("short_variant");
+    if (p->tiny_batch < 0) return bad("tiny_batch must be >= 0");
     return BSW_OK;
 }
 
@@ -592,8 +594,12 @@ int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t
 #define TL_MARK(K) do { if (g_timeline) CUDA_TRY(cudaEventRecord(s.ev_tl[K], s.st)); } while (0)
 int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
 {
-    const ChunkInfo& I = s.info;
+    ChunkInfo& I = s.info;
     const int n = s.n;
+    // Latency route (a batch too small to fill the machine one pair per thread, e.g. the reference
+    // driver's -b 512): no bucketing, no packing -- every pair is listed for the warp-per-pair kernel,
+    // whose rows live in shared memory; a pair then takes ~0.1 ms instead of ~0.35 ms.
+    if (s.tiny) I.n_short = 0;
     s.n_sorted = I.n_short;
     const size_t qwords = (size_t)(I.qbases / 16) + (size_t)I.n_short + 8;
     const size_t twords = (size_t)(I.tbases / 16) + (size_t)I.n_short + 8;
@@ -614,7 +620,7 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
         K.b_l1 = I.n_short ? bits_for((uint32_t)(I.mx[2] - I.mn[2])) : 0;
         const int total = b_l2 + K.b_h0 + K.b_l1;
         K.drop = std::max(0, total - BUCKET_BITS);          // only ever eats h0 / len1 bits: b_l2 <= 10
-        K.short_max = eng->short_max;
+        K.short_max = s.tiny ? 0 : eng->short_max;
         const int nbins = 1 << (total - K.drop);
         const int ntiles = (nbins + SCAN_TILE - 1) / SCAN_TILE;           // <= 256
         const size_t nb_pad = (size_t)ntiles * SCAN_TILE;                  // whole tiles, so the scan needs no edge cases
@@ -727,11 +733,18 @@ int launch_bytes(bsw_engine* eng, DevCtx& c, Slot& s)
         const int64_t cap_words = (int64_t)(256ll << 20) / 4;       // <= 256 MB of eh rows
         blocks = std::max<int64_t>(1, std::min(blocks, cap_words / ((int64_t)s.long_stride * LONG_WARPS)));
         s.long_blocks = (int)blocks;
-        if (int rc = ensure(eng, s.scratch, (size_t)blocks * LONG_WARPS * (size_t)s.long_stride)) return rc;
+        const size_t row_bytes = (size_t)LONG_WARPS * (size_t)s.long_stride * sizeof(uint32_t);
         CUDA_TRY(cudaMemsetAsync(s.d_queue, 0, sizeof(unsigned int), s.st));
-        bsw_long_kernel<<<s.long_blocks, LONG_WARPS * 32, 0, s.st>>>(
-            s.desc.d, s.llist.d, s.qbase, s.rbase, s.res.d, (int)s.n_llist, eng->kp, s.scratch.d, s.long_stride,
-            s.d_queue, c.d_cells);
+        if (row_bytes <= 48 * 1024) {                    // rows in shared memory (queries up to ~3000)
+            bsw_long_kernel<true><<<s.long_blocks, LONG_WARPS * 32, row_bytes, s.st>>>(
+                s.desc.d, s.llist.d, s.qbase, s.rbase, s.res.d, (int)s.n_llist, eng->kp, nullptr, s.long_stride,
+                s.d_queue, c.d_cells);
+        } else {
+            if (int rc = ensure(eng, s.scratch, (size_t)blocks * LONG_WARPS * (size_t)s.long_stride)) return rc;
+            bsw_long_kernel<false><<<s.long_blocks, LONG_WARPS * 32, 0, s.st>>>(
+                s.desc.d, s.llist.d, s.qbase, s.rbase, s.res.d, (int)s.n_llist, eng->kp, s.scratch.d, s.long_stride,
+                s.d_queue, c.d_cells);
+        }
         eng->stats.kernel_launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -826,6 +839,7 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
         for (DevCtx& c : eng->devs) partitioned = partitioned && c.svc_sms > 0;
     }
     eng->stats.partitioned = partitioned ? 1 : 0;
+    const bool tiny = !keep && eng->p.tiny_batch > 0 && n <= eng->p.tiny_batch;
     // chunk boundaries: a small first chunk (the first DP starts after a short H2D), full-size
     // chunks, then -- where transfers or the host bound the batch -- a geometric ramp-down so that the
     // work left after the last H2D (its DP and its D2H) is small.  PCIe-bound batches use smaller full-size chunks, sized so that the DP of one
@@ -878,6 +892,7 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
         Slot& s = *sp;
         s.a = cut[(size_t)k]; s.n = (int)(cut[(size_t)k + 1] - cut[(size_t)k]);
         s.direct = direct;
+        s.tiny = tiny;
         s.st = partitioned ? s.st_svc : s.st_plain;
         if (g_timeline) { if (k == 0) CUDA_TRY(cudaEventRecord(eng->devs[0].ev_t0, s.st)); s.host_t[0] = now_ms() - tl_host0; }
         CUDA_TRY(cudaEventRecord(s.ev_k0, s.st));

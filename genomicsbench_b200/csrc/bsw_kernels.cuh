@@ -360,11 +360,15 @@ bsw_short_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ per
 //   and chunks is one __shfl_up_sync.  Rows stay strictly sequential because the window,
 //   the m == 0 exit and z-drop need the complete previous row (SURVEY.md finding 0.6).
 //   Sequences are one base per byte (codes 0-4), read in place at any alignment; eh[] (h | e << 16 per cell)
-//   lives in a per-warp global scratch row that stays L1/L2 resident.
+//   lives in a per-warp row: shared memory when the launch's longest query fits (SMEM = true: a row
+//   sweep then costs no global round trip, which is what makes this the low-latency kernel for
+//   batches too small to fill the machine one pair per thread), else a global scratch row that
+//   stays L1/L2 resident.
 //   Pairs are pulled from an atomic queue, longest first.
 // ---------------------------------------------------------------------------------------
 constexpr int LONG_WARPS = 4;
 
+template <bool SMEM>
 __global__ void __launch_bounds__(LONG_WARPS * 32)
 bsw_long_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ perm,
                 const uint8_t* __restrict__ qbytes, const uint8_t* __restrict__ tbytes,
@@ -375,7 +379,9 @@ bsw_long_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ perm
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * LONG_WARPS + (threadIdx.x >> 5);
-    uint32_t* const eh = scratch + (size_t)gwarp * scratch_stride;
+    extern __shared__ __align__(16) uint32_t long_rows[];
+    uint32_t* const eh = SMEM ? long_rows + (size_t)(threadIdx.x >> 5) * scratch_stride
+                              : scratch + (size_t)gwarp * scratch_stride;
     const int e_ins4 = 4 * P.e_ins;
     long long my_cells = 0;
 

@@ -35,6 +35,7 @@ BandedPairWiseSW::BandedPairWiseSW(const int o_del, const int e_del, const int o
     params_.match = w_match;
     params_.mismatch = w_mismatch;         // positive penalty; the reference negates it at :66
     params_.ambig = DEFAULT_AMBIG;         // vector code hard-wires -1 (:69) and ignores `mat`
+    params_.tiny_batch = 1536;             // the driver feeds -b 512 pairs per call (scripts/run-cpu.sh:30): latency route
     memset(&stats_, 0, sizeof(stats_));
 }
 

@@ -73,7 +73,12 @@ typedef struct bsw_params {
                                              kernel; 0 => default (825, the short kernel's shared-
                                              memory limit + 1); 1 routes every pair to it          */
     int32_t short_variant;                /* BSW_SHORT_PACKED16 (default) | BSW_SHORT_WIDE32               */
-    int32_t reserved[6];
+    int32_t tiny_batch;                   /* latency route: calls with at most this many pairs skip bucketing and
+                                             packing and run every pair on the warp-per-pair kernel (rows in shared
+                                             memory), ~2x lower latency for batches that cannot fill the GPU one pair
+                                             per thread; 0 = off (default).  The BandedPairWiseSW class sets 1536: the
+                                             reference driver's habit is -b 512 (scripts/run-cpu.sh:30)              */
+    int32_t reserved[5];
 } bsw_params;
 
 /* Per-call statistics (replaces the rdtsc counters behind getTicks(),

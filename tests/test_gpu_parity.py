@@ -146,6 +146,29 @@ def test_cuda_matches_oracle_on_seeded_inputs(lib, oracle, idx):
     assert st2["cells_effective"] == cells and st2["n_long"] > 0
 
 
+@pytest.mark.parametrize("case", ["small_151bp", "with_N", "long_1k", "tiny_w3", "high_h0", "asym_gaps"])
+def test_latency_route_matches_reference_golden(lib, case):
+    """bsw_params.tiny_batch: calls with few pairs skip bucketing / packing and run every pair on the
+    warp-per-pair kernel with its rows in shared memory (what the BandedPairWiseSW class does for the
+    reference driver's -b 512 batches).  Same results, on pageable and on page-locked buffers."""
+    pairs, ref, qer, w, params, expect, _ = load_golden(case)
+    pairs = pairs[:1200].copy(); expect = expect[:1200]
+    with lib.Engine(tiny_batch=1536, **params) as eng:
+        a = pairs.copy()
+        eng.extend(a, ref, qer, w)
+        st = eng.stats()
+        assert np.array_equal(results_matrix(a), expect)
+        assert st["n_long"] == len(pairs) and st["n_short"] == 0          # every pair took the warp-per-pair kernel
+        pp, pr, pq = lib.pinned_copy(pairs), lib.pinned_copy(ref), lib.pinned_copy(qer)
+        eng.extend(pp, pr, pq, w)
+        assert np.array_equal(results_matrix(pp), expect)
+        reps = 2 + 1536 // len(pairs)                                     # above the threshold: the throughput kernels
+        big = np.tile(pairs, reps)
+        eng.extend(big, ref, qer, w)
+        assert eng.stats()["n_short"] > 0 or case == "long_1k"
+        assert np.array_equal(results_matrix(big), np.tile(expect, (reps, 1)))
+
+
 def test_edge_cases(lib, oracle):
     """Empty batch, single pair, 1-base sequences, ragged lengths, N-only sequences, h0 = 1."""
     from genomicsbench_b200 import SEQPAIR_DTYPE
