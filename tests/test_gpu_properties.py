@@ -168,6 +168,26 @@ def test_pcie_bound_batch_runs_partitioned(lib, oracle):
         assert np.array_equal(results_matrix(pp2), results_matrix(b))
 
 
+def test_pcie_bound_batch_on_a_multi_device_engine(lib):
+    """One engine over two device contexts (the same GPU twice when the box has one): a PCIe-bound batch on
+    pinned buffers is dealt chunk by chunk over both, each with its own FIFO H2D stream and SM partitions."""
+    import torch
+    devices = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    cfg = lib.gen_named_config("short8")
+    pairs, ref, qer = lib.gen_pairs(cfg, 0, 600_000)
+    with lib.Engine() as one:
+        want = pairs.copy()
+        one.extend(want, ref, qer, 100)
+    with lib.Engine(devices=devices) as eng:
+        pp, pr, pq = lib.pinned_copy(pairs), lib.pinned_copy(ref), lib.pinned_copy(qer)
+        for _ in range(2):
+            eng.extend(pp, pr, pq, 100)
+            assert np.array_equal(results_matrix(pp), results_matrix(want))
+        b = pairs.copy()
+        eng.extend(b, ref, qer, 100)                                  # staged route over both contexts
+        assert np.array_equal(results_matrix(b), results_matrix(want))
+
+
 def test_sparse_sequence_buffers_are_read_in_place(lib, oracle):
     """The reference loader's layout (main_banded.cpp:55-58,244-246: one 2048-byte slot per
     reference, 256 per query): on the direct route the engine must not DMA the whole slots."""
