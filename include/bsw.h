@@ -183,7 +183,7 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
                       bsw_alnreg* out_regs, int32_t* out_count);
 
 /* ---- (f.4) banded global alignment with traceback -> CIGAR -------------------
- * replaces: ksw_global2 (tools/bwa/ksw.c:502-606, push_cigar :489-500) as bwa_gen_cigar2 calls it for
+ * replaces: ksw_global2 (tools/bwa/ksw.c:502-606, push_cigar :489-500) as bwa_gen_cigar2 (bwa.c:167) calls it for
  * every alignment region: global alignment of query[0, len2) against target[0, len1) inside the fixed
  * band |i - j| <= w[i], int32 scores, gap costs and scoring of the engine (match / -mismatch / ambig),
  * the reference's tie-breaking in every cell, its backtrack and its merged operation list.
