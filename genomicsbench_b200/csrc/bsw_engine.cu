@@ -92,8 +92,10 @@ const GreenApi& green_api() { static GreenApi g; return g; }
 
 struct Launch {
     int first, count;     // range in the chunk's processing order
-    int qstride;          // shared-memory rows per thread
+    int qstride;          // shared-memory row words per thread
     int block;            // threads (= pairs) per block: 64, or 32 where that keeps more warps resident
+    int wcols = 0;        // packed kernel: columns of the circular row (then qstride = wcols + 4), 0 = the row holds the whole query
+    int plane = 0;        // packed kernel: query stride that sizes the 2-bit query plane (= qstride unless circular)
 };
 
 template <class T>
@@ -231,13 +233,14 @@ inline int stride_for(int qmax, bool fine = false)
 // score table + 1 KB the SM reserves) only fits the SM's 228 KB a whole number of times, and for some
 // classes 32-thread blocks leave less of it unused than 64-thread ones -- one more resident warp where
 // there are only four to seven.  BSW_SHORT_BLOCK=64 / 32 in the environment forces one size.
-inline int short16_block(int qstride)
+inline int short16_block(int qstride, int plane, bool circ)
 {
     static const int forced = getenv("BSW_SHORT_BLOCK") ? atoi(getenv("BSW_SHORT_BLOCK")) : 0;
     if (forced == 32 || forced == 64) return forced;
     const int sm_bytes = 228 * 1024;
-    const int w64 = std::min((int)(sm_bytes / (k16::smem_bytes(64, qstride) + 1024)), 14) * 2;   // 71 registers: 14 blocks of 64
-    const int w32 = std::min((int)(sm_bytes / (k16::smem_bytes(32, qstride) + 1024)), 28);
+    const int rb = circ ? 12 : 14;                    // register limit in blocks of 64: 71 registers, 77 with circular rows
+    const int w64 = std::min((int)(sm_bytes / (k16::smem_bytes(64, qstride, plane) + 1024)), rb) * 2;
+    const int w32 = std::min((int)(sm_bytes / (k16::smem_bytes(32, qstride, plane) + 1024)), 2 * rb);
     return w32 > w64 ? 32 : 64;
 }
 
@@ -262,12 +265,14 @@ int set_kernel_attrs(bsw_engine* eng, DevCtx& c)
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
     CUDA_TRY(cudaFuncSetAttribute(bsw_short_kernel<SHORT_BLOCK, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<SHORT_BLOCK, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<SHORT_BLOCK, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
-    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<32, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
+    CUDA_TRY(cudaFuncSetAttribute(bsw_short16_kernel<32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm));
     c.attr_set = true;
     return BSW_OK;
 }
@@ -650,15 +655,34 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
             eng->stats.kernel_launches += 3;
             // launch plan: the processing order ascends in len2, so the shared-memory classes are
             // prefix ranges of it, read off the len2 histogram
+            static const bool circ_ok = !(getenv("BSW_CIRC") && atoi(getenv("BSW_CIRC")) == 0);   // BSW_CIRC=0: rows always hold the whole query
             int pos = 0;
             for (int l = I.mn[0]; l <= std::min(I.mx[0], eng->short_max); ++l) {
                 const int cnt = (int)I.hist[l];
                 if (!cnt) continue;
-                const int qs = stride_for(l, eng->use16);
-                if (!s.plan.empty() && s.plan.back().qstride == qs) s.plan.back().count += cnt;
-                else s.plan.push_back(Launch{pos, cnt, qs, eng->use16 ? short16_block(qs) : SHORT_BLOCK});
+                int qs = stride_for(l, eng->use16);
+                int wc = 0;
+                const int plane = qs;
+                if (eng->use16 && circ_ok && eng->kp.w <= 4096 && (k16::circ_cols(eng->kp.w) + 4) * 10 <= qs * 7) {
+                    // the band is much narrower than the query: circular rows of the band's width (bsw_kernel16.cuh);
+                    // every longer class then shares one row stride and merges into one launch.  Only where the
+                    // rows shrink by 30 % or more: the wrap costs ~6 registers and a few instructions per block,
+                    // and measured at w = 100 / qlen <= 300 (rows 26 % smaller at best) it gains nothing
+                    // (long16 5 % slower), while at w = 32 it is worth +32 % (scripts/sweep_points.py)
+                    wc = k16::circ_cols(eng->kp.w);
+                    qs = wc + 4;
+                }
+                if (!s.plan.empty() && s.plan.back().qstride == qs && s.plan.back().wcols == wc) {
+                    s.plan.back().count += cnt;
+                    s.plan.back().plane = std::max(s.plan.back().plane, plane);
+                } else {
+                    Launch L{pos, cnt, qs, SHORT_BLOCK};
+                    L.wcols = wc; L.plane = plane;
+                    s.plan.push_back(L);
+                }
                 pos += cnt;
             }
+            if (eng->use16) for (Launch& L : s.plan) L.block = short16_block(L.qstride, L.plane, L.wcols != 0);
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -690,22 +714,28 @@ int launch_dp(bsw_engine* eng, DevCtx& c, Slot& s, bool partitioned = false)
         const Launch& L = s.plan[(size_t)k];
         cudaStream_t st = cs[li % NSTREAMS];
         const int grid = (L.count + L.block - 1) / L.block;
-        if (eng->use16 && L.block == 32) {
-            if (eng->kp.oe_del == eng->kp.oe_ins)
-                bsw_short16_kernel<32, true><<<grid, 32, k16::smem_bytes(32, L.qstride), st>>>(
-                    s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
-            else
-                bsw_short16_kernel<32, false><<<grid, 32, k16::smem_bytes(32, L.qstride), st>>>(
-                    s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
-        } else if (!eng->use16)
+        if (eng->use16) {
+            const bool sg = eng->kp.oe_del == eng->kp.oe_ins;
+            const size_t smem = k16::smem_bytes(L.block, L.qstride, L.plane);
+#define BSW_LAUNCH16(B, SG, CIRC)                                                                                     \
+            bsw_short16_kernel<B, SG, CIRC><<<grid, B, smem, st>>>(s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first,   \
+                                                                   L.count, L.qstride, eng->kp, c.d_cells, L.wcols)
+            const int variant = (L.block == 32 ? 4 : 0) | (sg ? 2 : 0) | (L.wcols ? 1 : 0);
+            switch (variant) {
+                case 0: BSW_LAUNCH16(64, false, false); break;
+                case 1: BSW_LAUNCH16(64, false, true); break;
+                case 2: BSW_LAUNCH16(64, true, false); break;
+                case 3: BSW_LAUNCH16(64, true, true); break;
+                case 4: BSW_LAUNCH16(32, false, false); break;
+                case 5: BSW_LAUNCH16(32, false, true); break;
+                case 6: BSW_LAUNCH16(32, true, false); break;
+                default: BSW_LAUNCH16(32, true, true); break;
+            }
+#undef BSW_LAUNCH16
+        } else {
             bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, short_smem_bytes(L.qstride), st>>>(
                 s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
-        else if (eng->kp.oe_del == eng->kp.oe_ins)
-            bsw_short16_kernel<SHORT_BLOCK, true><<<grid, SHORT_BLOCK, k16::smem_bytes(SHORT_BLOCK, L.qstride), st>>>(
-                s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
-        else
-            bsw_short16_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, k16::smem_bytes(SHORT_BLOCK, L.qstride), st>>>(
-                s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
+        }
         eng->stats.kernel_launches++;
     }
     CUDA_TRY(cudaGetLastError());

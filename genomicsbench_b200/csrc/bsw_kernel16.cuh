@@ -301,18 +301,33 @@ BSW_HD bool eligible(int match, int qlen, int h0)
 // columns whose (h | e) is non-zero; the next row's window (bandedSWA.cpp:230-233) is read off
 // these two maps and only falls back to scanning shared memory when a map is empty.
 // ------------------------------------------------------------------------------------------------
-template <bool SAMEGAP>
+// CIRC = true: the row is a circular buffer of wcols columns (a multiple of 8, >= 2 w + 16): a row sweep only
+// ever touches the columns [beg, end] with beg >= i - w and end <= i + w + 1, column j lives in slot j mod wcols,
+// and a column's slot is reused wcols columns later, when that column has been dead (left of the first block)
+// for good.  Columns that enter the band for the first time receive their first-row value
+// max(h0 - oe_ins - (j-1) e_ins, 0) (the closed form of bandedSWA.cpp:155-157) just before the first row whose
+// last block can cover them, so the stale-eh[] behaviour is unchanged.  Queries longer
+// than the band then cost the band's shared memory, not the query's.
+template <bool SAMEGAP, bool CIRC = false>
 BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restrict__ qw,
                        const uint32_t* __restrict__ tw, const uint32_t eh_sa, const uint32_t qp_sa,
-                       const uint32_t qp_stride, const uint32_t tab_sa, PairState& st, long long& my_cells)
+                       const uint32_t qp_stride, const uint32_t tab_sa, PairState& st, long long& my_cells,
+                       const uint32_t wcols = 0)
 {
     const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w & 0xffff;
 
     // ---- first row (bandedSWA.cpp:155-157) and the query plane; the row is initialised up to the
     // end of the block that holds column qlen
+    // x mod wcols for x < 2^16 (one IMAD.HI + one IMAD on the FMA pipe); identity when the row is not circular
+    const uint32_t rcpw = CIRC ? (uint32_t)((0x100000000ull + wcols - 1) / wcols) : 0u;
+#define K16_MODW(X) (CIRC ? (uint32_t)(X) - wcols * madhi_u((uint32_t)(X), rcpw, 0u) : (uint32_t)(X))
+#define K16_NEXT(SA) (CIRC ? ((SA) + 32u == row_end ? eh_sa : (SA) + 32u) : (SA) + 32u)
+    const uint32_t row_end = eh_sa + 4u * wcols;
+    const int init_cols = CIRC && (int)wcols < (qlen | 7) + 1 ? (int)wcols : (qlen | 7) + 1;
+    int init_next = init_cols;                        // CIRC: first column whose slot still holds an older column
     {
         int hv = h0;
-        for (int j0 = 0; j0 <= (qlen | 7); j0 += 4) {
+        for (int j0 = 0; j0 < init_cols; j0 += 4) {
             uint32_t v[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -350,7 +365,7 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
     (void)noe_ins2;
 
     // address of column j's h half (its e half is 8 bytes further)
-#define K16_HADDR(J) (eh_sa + (((uint32_t)(J) >> 2) << 4) + (((uint32_t)(J) & 3u) << 1))
+#define K16_HADDR(J) (eh_sa + ((K16_MODW(J) >> 2) << 4) + (((uint32_t)(J) & 3u) << 1))
     // score word of pair K (columns 2K, 2K+1 of the block) from the block's x halfword: the pair's
     // nibble is isolated by a left shift + IMAD.HI (x 16 = >> 28), scaled to the table stride by an IMAD
 #define K16_SCORE(X, K) lds32(mad_u(madhi_u((X) << (28 - 4 * (K)), k16c, 0u), k128, tab_sa))
@@ -385,7 +400,8 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
     // query halfword ^ target.  (The shared-memory accesses are volatile, so ptxas keeps the loads
     // ahead of the block's stores instead of sinking them to their use.)
 #define K16_PREFETCH(XA, N0, N1, T0, T1, T2, T3, XB)                                              \
-    N0 = lds128(sa + 32); N1 = lds128(sa + 48);                                                   \
+    const uint32_t san_ = K16_NEXT(sa);                                                           \
+    N0 = lds128(san_); N1 = lds128(san_ + 16);                                                    \
     T0 = K16_SCORE(XA, 0); T1 = K16_SCORE(XA, 1); T2 = K16_SCORE(XA, 2); T3 = K16_SCORE(XA, 3);   \
     XB = lds16(qa + 2 * qp_stride) ^ trep;
 #define K16_BLOCK(C0, C1, S0, S1, S2, S3, XA, N0, N1, T0, T1, T2, T3, XB)                         \
@@ -396,7 +412,7 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
         K16_GROUP(C1, S2, S3, sa + 16, hn2, hn3)                                                  \
         const uint32_t g_ = max2(max3(hn0, hn1, hn2), hn3);                                       \
         K16_KEY(g_, code)                                                                         \
-        sa += 32; qa += qp_stride; code += 8;                                                     \
+        sa = san_; qa += qp_stride; code += 8;                                                    \
     }
     // 8-bit map of the non-zero halfwords of four words (bit c = column c of the block)
 #define K16_ZMAP(Z0, Z1, Z2, Z3, ZMAP)                                                            \
@@ -425,7 +441,7 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
         const uint32_t g_ = max2(max3(hn0, hn1, hn2), hn3);                                       \
         K16_KEY(g_, code)                                                                         \
         K16_ZMAP(hw0 | en0, hw1 | en1, hw2 | en2, hw3 | en3, ZMAP)                                \
-        sa += 32; qa += qp_stride; code += 8;                                                     \
+        sa = san_; qa += qp_stride; code += 8;                                                    \
         c0 = n0; c1 = n1; s0 = t0; s1 = t1; s2 = t2; s3 = t3; xa = xb;                            \
     }
     // halfword mask of word K of a block: the columns >= D16 / 16 (D16 = 16 x a column count in 0..8)
@@ -470,6 +486,22 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
         end = end < qlen ? end : qlen;
         int h1 = 0;
         if (beg == 0) { h1 = h0 - (P.o_del + P.e_del * (i + 1)); h1 = h1 > 0 ? h1 : 0; }
+        if (CIRC) {
+            // first-row values for the columns this row's last block may reach for the first time
+            int need_hi = i + w + 1 < qlen ? i + w + 1 : qlen;
+            need_hi |= 7;
+            while (init_next <= need_hi) {
+                uint32_t v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = init_next + c;
+                    const int hv = h0 - P.oe_ins - (j - 1) * P.e_ins;
+                    v[c] = j <= qlen && hv > 0 ? (uint32_t)hv : 0u;
+                }
+                sts128(eh_sa + 4u * K16_MODW(init_next), v[0] | (v[1] << 16), v[2] | (v[3] << 16), 0u, 0u);
+                init_next += 4;
+            }
+        }
         int mkey = 0;                     // (row max << 16) | last column of the block that holds it
         uint32_t zf = 0, zl = 0;          // non-zero maps of the first / last block
         const int fb = beg & ~7, lb = end & ~7;
@@ -477,7 +509,7 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
             const uint32_t trep = (uint32_t)ti * 0x5555u;
             uint32_t fc = 0;                                  // high half: F entering the next column
             uint32_t carry = (uint32_t)h1 << 16;              // high half: H(i, j - 1)
-            uint32_t sa = eh_sa + 4u * (uint32_t)fb;
+            uint32_t sa = eh_sa + 4u * K16_MODW(fb);
             uint32_t qa = qp_sa + ((uint32_t)fb >> 3) * qp_stride;
             int code = fb + 7;
             uint4 c0 = lds128(sa), c1 = lds128(sa + 16);
@@ -527,8 +559,9 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
             // in hs[c + 1]; the eight halves are flagged in parallel (1 where hs >= m: inside this
             // row's sweep no H exceeds m; columns left of beg hold zeros, columns from end on are
             // masked out) and the highest flag taken.  The epilogue reads mj only under the condition above.
-            const uint32_t ga = eh_sa + (((uint32_t)(mj + 1) >> 2) << 4);
-            const uint32_t a0 = lds32(ga - 32), a1 = lds32(ga - 28), b0 = lds32(ga - 16), b1 = lds32(ga - 12), c0 = lds32(ga);
+            const uint32_t gb = eh_sa + 4u * K16_MODW(mj - 7);            // the block [mj - 7, mj] ...
+            const uint32_t ga = eh_sa + 4u * K16_MODW(mj + 1);            // ... and the first group of the next one
+            const uint32_t a0 = lds32(gb), a1 = lds32(gb + 4), b0 = lds32(gb + 16), b1 = lds32(gb + 20), c0 = lds32(ga);
             const uint32_t dm = pack2(1 - m, 1 - m), one2 = 0x00010001u;
             const uint32_t fa0 = addmin_relu(a0, dm, one2), fa1 = addmin_relu(a1, dm, one2);
             const uint32_t fb0 = addmin_relu(b0, dm, one2), fb1 = addmin_relu(b1, dm, one2), fc0 = addmin_relu(c0, dm, one2);
@@ -571,6 +604,8 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
         }
         // (an empty window has m == 0 and stopped the pair above)
     }
+#undef K16_MODW
+#undef K16_NEXT
 #undef K16_HADDR
 #undef K16_SCORE
 #undef K16_WORD
@@ -584,11 +619,16 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
 #undef K16_EDGE
 }
 
-// shared memory of one block: score table + rows + query plane
-BSW_HD size_t smem_bytes(int block, int qstride)
+// shared memory of one block: score table + rows (rowstride words per thread) + query plane (sized by
+// the class's full query stride qstride, which equals rowstride unless the rows are circular)
+BSW_HD size_t smem_bytes(int block, int rowstride, int qstride)
 {
-    return (size_t)TAB_BYTES + (size_t)qstride * block * 4 + (size_t)((qstride >> 3) + 2) * block * 2;
+    return (size_t)TAB_BYTES + (size_t)rowstride * block * 4 + (size_t)((qstride >> 3) + 2) * block * 2;
 }
+BSW_HD size_t smem_bytes(int block, int qstride) { return smem_bytes(block, qstride, qstride); }
+
+// columns of the circular row for band w (pair_sweep<.., true>): a multiple of 8, >= 2 w + 16
+BSW_HD int circ_cols(int w) { return (2 * w + 16 + 7) & ~7; }
 
 } // namespace k16
 
@@ -596,12 +636,14 @@ BSW_HD size_t smem_bytes(int block, int qstride)
 // Kernel: one pair per thread; same arguments as bsw_short_kernel<BLOCK, false>.
 // ------------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
-template <int BLOCK, bool SAMEGAP>
+// qstride = words per thread row; wcols = 0, or the columns of the circular row (then qstride = wcols + 4: the
+// padding keeps qstride / 4 odd, i.e. the 128-bit accesses of a quarter warp in distinct bank groups)
+template <int BLOCK, bool SAMEGAP, bool CIRC = false>
 __global__ void __launch_bounds__(BLOCK)
 bsw_short16_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ perm,
                    const uint32_t* __restrict__ qseq, const uint32_t* __restrict__ tseq,
                    int4* __restrict__ res, int first, int count, int qstride,
-                   const __grid_constant__ KParams P, unsigned long long* __restrict__ cell_counter)
+                   const __grid_constant__ KParams P, unsigned long long* __restrict__ cell_counter, int wcols = 0)
 {
     extern __shared__ __align__(16) uint32_t k16_smem[];
     const int tid = threadIdx.x;
@@ -617,8 +659,8 @@ bsw_short16_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ p
             const uint32_t qp_sa = smem_sa + k16::TAB_BYTES + (uint32_t)(BLOCK * qstride) * 4u + (uint32_t)tid * 2u;
             const uint32_t tab_sa = smem_sa + (uint32_t)(tid & 31) * 4u;
             PairState st;
-            k16::pair_sweep<SAMEGAP>(P, md, qseq + (uint32_t)md.x, tseq + (uint32_t)md.y, eh_sa, qp_sa, BLOCK * 2u,
-                                     tab_sa, st, my_cells);
+            k16::pair_sweep<SAMEGAP, CIRC>(P, md, qseq + (uint32_t)md.x, tseq + (uint32_t)md.y, eh_sa, qp_sa, BLOCK * 2u,
+                                           tab_sa, st, my_cells, (uint32_t)wcols);
             res[perm[first + local]] = bsw_pack_result(st);
         }
     }

@@ -17,6 +17,8 @@ with gb.Engine(long_min_qlen=200) as eng:        # queries >= 200 -> warp-per-pa
     eng.extend(pp, pr, pq, 100)
     assert all(np.array_equal(a[f], pp[f]) for f in gb.RESULT_FIELDS)
     print("stats", eng.stats())
+    b = pairs.copy(); eng.extend(b, ref, qer, 16)   # narrow band: the packed kernel's circular rows
+    print("w=16", int(b["score"].sum()))
     # banded global alignment: shared-memory rows (small bands) and the global-scratch form (w = 300)
     g = pairs[:1500].copy(); g["len1"] = np.minimum(g["len1"], g["len2"] + 20)
     for w in (25, 300):
