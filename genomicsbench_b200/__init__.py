@@ -17,14 +17,17 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 
-from ._lib import (ABI, ALNREG_DTYPE, ALNREG_FIELDS, BSW_ZDROP_SCALAR, BSW_ZDROP_VECTOR, CHAIN_DTYPE, RESULT_FIELDS,
-                   SEED_DTYPE, SEQPAIR_DTYPE, BswChainOpt, BswGenConfig, BswParams, BswStats, LIB_PATH, load_library, ptr)
+from ._lib import (ABI, ALNREG_DTYPE, ALNREG_FIELDS, BSW_PACKED_MAX_QLEN, BSW_PAIR_RAW, BSW_ZDROP_SCALAR, BSW_ZDROP_VECTOR,
+                   CHAIN_DTYPE, OUTSCORE_DTYPE, PAIR_DESC_DTYPE, RESULT_FIELDS, SCORE16_DTYPE, SEED_DTYPE, SEQPAIR_DTYPE,
+                   BswChainOpt, BswGenConfig, BswPackedBatch, BswParams, BswStats, LIB_PATH, load_host_library,
+                   load_library, ptr)
 
 __all__ = [
     "BandedPairWiseSW", "Engine", "BswError", "SEQPAIR_DTYPE", "RESULT_FIELDS", "default_params",
     "gen_named_config", "gen_pairs", "bucket_order", "partition", "read_pairs_file",
     "write_pairs_file", "load_library", "NAMED_CONFIGS", "pinned_empty", "pinned_copy",
-    "SEED_DTYPE", "CHAIN_DTYPE", "ALNREG_DTYPE", "ALNREG_FIELDS",
+    "SEED_DTYPE", "CHAIN_DTYPE", "ALNREG_DTYPE", "ALNREG_FIELDS", "PackedBatch", "PAIR_DESC_DTYPE", "OUTSCORE_DTYPE",
+    "SCORE16_DTYPE", "BSW_PAIR_RAW", "BSW_PACKED_MAX_QLEN", "load_host_library",
 ]
 
 NAMED_CONFIGS = {"small": 0, "short8": 1, "long16": 2, "large": 3, "sweep": 4}
@@ -146,6 +149,18 @@ class Engine:
                                              C.byref(opt), ptr(regs), ptr(count)))
         return regs[:len(seeds)], count[:len(chains)]
 
+    def extend_packed(self, batch: "PackedBatch", w: int, out: Optional[np.ndarray] = None, compact: bool = False) -> np.ndarray:
+        """bsw_extend_packed / bsw_extend_packed16: a packed batch in, OUTSCORE_DTYPE (24 B) or SCORE16_DTYPE (16 B)
+        records out, input order.  `out` = a caller-owned result array (page-locked for the DMA route)."""
+        dt = SCORE16_DTYPE if compact else OUTSCORE_DTYPE
+        if out is None:
+            out = np.zeros(max(batch.n_pairs, 1), dtype=dt)
+        if out.dtype != dt or not out.flags.c_contiguous or len(out) < batch.n_pairs:
+            raise TypeError(f"out must be a C-contiguous {dt} array with one entry per pair")
+        fn = self._lib.bsw_extend_packed16 if compact else self._lib.bsw_extend_packed
+        self._rc(fn(self._h, C.byref(batch.c), w, ptr(out)))
+        return out[:batch.n_pairs]
+
     def stage(self, pairs, seq_ref, seq_qer, w: int) -> None:
         _check_arrays(pairs, seq_ref, seq_qer)
         self._rc(self._lib.bsw_stage(self._h, ptr(pairs), ptr(seq_ref), ptr(seq_qer), len(pairs), w))
@@ -257,20 +272,123 @@ def pinned_copy(a: np.ndarray) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------------
+# the packed host format (include/bsw.h: bsw_packed_batch)
+# ---------------------------------------------------------------------------------------
+class PackedBatch:
+    """Owns one bsw_packed_batch built by the library (2 bits per base + 16-byte descriptors; RAW pairs keep one byte
+    per base).  pinned=True allocates the buffers with bsw_host_alloc (needs a CUDA device), else with malloc;
+    host_only=True builds through libbsw_host.so (no CUDA library mapped)."""
+
+    def __init__(self, pinned: bool = False, host_only: bool = False):
+        if pinned and host_only:
+            raise ValueError("page-locked buffers come from the CUDA library")
+        self._lib = load_host_library() if host_only else load_library()
+        self.c = BswPackedBatch()
+        if pinned:
+            cuda = load_library()
+            self._alloc = C.cast(cuda.bsw_host_alloc, C.c_void_p)
+            self._release = C.cast(cuda.bsw_host_free, C.c_void_p)
+        else:
+            self._alloc = self._release = None
+        self._built = False
+
+    def _done(self, rc: int, what: str):
+        if rc:
+            raise BswError(rc, what)
+        self._built = True
+        return self
+
+    @classmethod
+    def from_pairs(cls, pairs, seq_ref, seq_qer, raw_min_qlen: int = 0, pinned: bool = False, host_only: bool = False):
+        _check_arrays(pairs, seq_ref, seq_qer)
+        b = cls(pinned, host_only)
+        return b._done(b._lib.bsw_batch_from_pairs(ptr(pairs), ptr(seq_ref), ptr(seq_qer), len(pairs), raw_min_qlen,
+                                                   b._alloc, b._release, C.byref(b.c)), "bsw_batch_from_pairs")
+
+    @classmethod
+    def from_file(cls, path: str, max_pairs: int = -1, raw_min_qlen: int = 0, pinned: bool = False, host_only: bool = False):
+        b = cls(pinned, host_only)
+        return b._done(b._lib.bsw_batch_from_file(path.encode(), max_pairs, raw_min_qlen, b._alloc, b._release,
+                                                  C.byref(b.c)), f"bsw_batch_from_file({path})")
+
+    @classmethod
+    def gen(cls, cfg: BswGenConfig, first: int = 0, n: Optional[int] = None, raw_min_qlen: int = 0, pinned: bool = False,
+            host_only: bool = False):
+        b = cls(pinned, host_only)
+        n = int(cfg.n_pairs if n is None else n)
+        return b._done(b._lib.bsw_batch_gen(C.byref(cfg), first, n, raw_min_qlen, b._alloc, b._release, C.byref(b.c)),
+                       "bsw_batch_gen")
+
+    @property
+    def n_pairs(self) -> int:
+        return int(self.c.n_pairs)
+
+    def _view(self, p, count, dtype):
+        if not p or count <= 0:
+            return np.zeros(0, dtype=dtype)
+        dtype = np.dtype(dtype)
+        raw = (C.c_ubyte * (count * dtype.itemsize)).from_address(p)
+        raw._owner = self
+        return np.frombuffer(raw, dtype=dtype, count=count)
+
+    @property
+    def desc(self) -> np.ndarray:
+        return self._view(self.c.desc, self.n_pairs, PAIR_DESC_DTYPE)
+
+    @property
+    def q2(self) -> np.ndarray:
+        return self._view(self.c.q2, int(self.c.q2_words), np.uint32)
+
+    @property
+    def r2(self) -> np.ndarray:
+        return self._view(self.c.r2, int(self.c.r2_words), np.uint32)
+
+    @property
+    def raw_q(self) -> np.ndarray:
+        return self._view(self.c.raw_q, int(self.c.raw_q_bytes), np.uint8)
+
+    @property
+    def raw_r(self) -> np.ndarray:
+        return self._view(self.c.raw_r, int(self.c.raw_r_bytes), np.uint8)
+
+    def nbytes(self) -> int:
+        """bytes a call moves host -> device for this batch"""
+        return 16 * self.n_pairs + 4 * int(self.c.q2_words + self.c.r2_words) + int(self.c.raw_q_bytes + self.c.raw_r_bytes)
+
+    def to_pairs(self):
+        """-> (pairs, seq_ref, seq_qer) in the reference's layout (bsw_batch_to_pairs)."""
+        d = self.desc
+        pairs = np.zeros(max(self.n_pairs, 1), dtype=SEQPAIR_DTYPE)
+        rcap, qcap = int(d["len1"].astype(np.int64).sum()) + 64, int(d["len2"].astype(np.int64).sum()) + 64
+        ref, qer = np.zeros(rcap, dtype=np.uint8), np.zeros(qcap, dtype=np.uint8)
+        rc = self._lib.bsw_batch_to_pairs(C.byref(self.c), ptr(pairs), ptr(ref), rcap, ptr(qer), qcap)
+        if rc:
+            raise BswError(rc, "bsw_batch_to_pairs")
+        return pairs[:self.n_pairs], ref, qer
+
+    def close(self):
+        if getattr(self, "_built", False):
+            self._lib.bsw_batch_release(C.byref(self.c), self._release)
+            self._built = False
+
+    __del__ = close
+
+
+# ---------------------------------------------------------------------------------------
 # host utilities (no GPU needed)
 # ---------------------------------------------------------------------------------------
-def gen_named_config(which) -> BswGenConfig:
+def gen_named_config(which, host_only: bool = False) -> BswGenConfig:
     idx = NAMED_CONFIGS[which] if isinstance(which, str) else int(which)
     cfg = BswGenConfig()
-    rc = load_library().bsw_gen_named_config(idx, C.byref(cfg))
+    rc = (load_host_library() if host_only else load_library()).bsw_gen_named_config(idx, C.byref(cfg))
     if rc:
         raise BswError(rc, "unknown named config")
     return cfg
 
 
-def gen_pairs(cfg: BswGenConfig, first: int = 0, n: Optional[int] = None):
+def gen_pairs(cfg: BswGenConfig, first: int = 0, n: Optional[int] = None, host_only: bool = False):
     """Returns (pairs, seq_ref, seq_qer) for pairs [first, first+n) of the config's stream."""
-    lib = load_library()
+    lib = load_host_library() if host_only else load_library()
     n = int(cfg.n_pairs if n is None else n)
     sub = BswGenConfig.from_buffer_copy(cfg)
     sub.n_pairs = n

@@ -82,9 +82,41 @@ class BswGenConfig(C.Structure):
     ]
 
 
-# every symbol include/bsw.h declares: (name, restype, argtypes)
+# include/bsw.h: the packed host format
+PAIR_DESC_DTYPE = np.dtype([("q_off", "<u4"), ("r_off", "<u4"), ("len2", "<u2"), ("len1", "<u2"), ("h0", "<u2"), ("flags", "<u2")])
+OUTSCORE_DTYPE = np.dtype([("score", "<i4"), ("tle", "<i4"), ("gtle", "<i4"), ("qle", "<i4"), ("gscore", "<i4"), ("max_off", "<i4")])
+SCORE16_DTYPE = np.dtype([("score", "<i2"), ("qle", "<i2"), ("tle", "<i2"), ("gtle", "<i2"), ("gscore", "<i2"), ("max_off", "<i2"),
+                          ("reserved", "<i2", (2,))])
+BSW_PAIR_RAW = 1
+BSW_PACKED_MAX_QLEN = 824
+
+
+class BswPackedBatch(C.Structure):
+    _fields_ = [
+        ("n_pairs", C.c_int64), ("desc", C.c_void_p),
+        ("q2", C.c_void_p), ("q2_words", C.c_int64), ("r2", C.c_void_p), ("r2_words", C.c_int64),
+        ("raw_q", C.c_void_p), ("raw_q_bytes", C.c_int64), ("raw_r", C.c_void_p), ("raw_r_bytes", C.c_int64),
+        ("ordered", C.c_int32), ("reserved", C.c_int32 * 3),
+    ]
+
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t)
+RELEASE_FN = C.CFUNCTYPE(None, C.c_void_p)
+
+# every symbol include/bsw.h declares: (name, restype, argtypes); HOST_ABI = the subset libbsw_host.so exports too
 _P = C.c_void_p
+_PB = C.POINTER(BswPackedBatch)
+HOST_ABI_NAMES = {"bsw_bucket_order", "bsw_partition", "bsw_gen_named_config", "bsw_gen_bounds", "bsw_gen_pairs",
+                  "bsw_count_pairs_file", "bsw_read_pairs_file", "bsw_write_pairs_file", "bsw_batch_from_pairs",
+                  "bsw_batch_from_file", "bsw_batch_to_pairs", "bsw_batch_release", "bsw_batch_gen"}
 ABI = [
+    ("bsw_batch_from_pairs", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P, _PB]),
+    ("bsw_batch_from_file", C.c_int, [C.c_char_p, C.c_int64, C.c_int32, _P, _P, _PB]),
+    ("bsw_batch_to_pairs", C.c_int, [_PB, _P, _P, C.c_int64, _P, C.c_int64]),
+    ("bsw_batch_release", None, [_PB, _P]),
+    ("bsw_batch_gen", C.c_int, [C.POINTER(BswGenConfig), C.c_int64, C.c_int64, C.c_int32, _P, _P, _PB]),
+    ("bsw_extend_packed", C.c_int, [_P, _PB, C.c_int32, _P]),
+    ("bsw_extend_packed16", C.c_int, [_P, _PB, C.c_int32, _P]),
     ("bsw_create", _P, [C.POINTER(BswParams), C.POINTER(C.c_int)]),
     ("bsw_destroy", None, [_P]),
     ("bsw_last_error", C.c_char_p, [_P]),
@@ -137,6 +169,28 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         fn.argtypes = argtypes
     if path is None:
         _lib = lib
+    return lib
+
+
+_host_lib = None
+HOST_LIB_PATH = PKG_DIR / "lib" / "libbsw_host.so"
+
+
+def load_host_library() -> C.CDLL:
+    """libbsw_host.so: generator, text format, packed-batch builders, bucketing -- no CUDA code, maps no CUDA
+    library.  For tools that must stay off the GPU stack (bench.py --impl reference)."""
+    global _host_lib
+    if _host_lib is not None:
+        return _host_lib
+    if not HOST_LIB_PATH.exists():
+        raise RuntimeError(f"{HOST_LIB_PATH} not found: build it with `python -m genomicsbench_b200.build`")
+    lib = C.CDLL(str(HOST_LIB_PATH))
+    for name, restype, argtypes in ABI:
+        if name in HOST_ABI_NAMES:
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+    _host_lib = lib
     return lib
 
 

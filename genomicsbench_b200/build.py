@@ -21,9 +21,15 @@ STAMP = LIB_DIR / ".build_stamp"
 SOURCES = [
     "bsw_gen.cpp",
     "bsw_host.cpp",
+    "bsw_pack.cpp",
     "bsw_engine.cu",
     "bsw_shim.cpp",
 ]
+# libbsw_host.so: the host-only part of the ABI (generator, text format, packed-batch builders, bucketing /
+# partition utilities) without any CUDA code, for tools that must not map the CUDA library -- bench.py's
+# reference arm generates its inputs through it
+HOST_LIB_PATH = LIB_DIR / "libbsw_host.so"
+HOST_SOURCES = ["bsw_gen.cpp", "bsw_host.cpp", "bsw_pack.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -57,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile the library if sources changed; returns the path of the .so."""
     LIB_DIR.mkdir(exist_ok=True)
     fp = _fingerprint()
-    if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text() == fp:
+    if not force and LIB_PATH.exists() and HOST_LIB_PATH.exists() and STAMP.exists() and STAMP.read_text() == fp:
         return LIB_PATH
     # never try to rebuild on a box without nvcc sources context (e.g. GPU box has nvcc too,
     # but a prebuilt library with a stale stamp is still better than none)
@@ -74,6 +80,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed building libbsw_b200.so (see genomicsbench_b200/lib/build.log)")
     if verbose:
         print(log)
+    hcmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unused-function",
+            "-I", str(PKG_DIR.parent / "include"), "-o", str(HOST_LIB_PATH)] + [str(CSRC / s) for s in HOST_SOURCES]
+    res = subprocess.run(hcmd, capture_output=True, text=True, env=env)
+    with open(LIB_DIR / "build.log", "a") as f:
+        f.write(" ".join(hcmd) + "\n" + res.stdout + res.stderr)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building libbsw_host.so (see genomicsbench_b200/lib/build.log)")
     STAMP.write_text(fp)
     return LIB_PATH
 

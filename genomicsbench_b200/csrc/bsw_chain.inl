@@ -109,13 +109,13 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
     }
     const bsw_params& P = eng->p;
     std::vector<ChainRun> run((size_t)n_chains);
-    std::vector<int64_t> group_first((size_t)n_chains);         // first chain of the read a chain belongs to
+    std::vector<int64_t> groups;                                // first chain of every read (chains of a read are adjacent)
     int64_t n_seeds_total = 0;
     for (int64_t c = 0; c < n_chains; ++c) {
         const bsw_chain& ch = chains[c];
         out_count[c] = 0;
         if (ch.n_seeds < 0 || ch.l_query < 1 || ch.rmax1 < ch.rmax0 || ch.seed_first < 0) { eng->err = "bsw_extend_chains: malformed chain"; return BSW_ERR_PARAM; }
-        group_first[(size_t)c] = (c > 0 && ch.same_read) ? group_first[(size_t)c - 1] : c;
+        if (!(c > 0 && ch.same_read)) groups.push_back(c);
         if (ch.same_read && (c == 0 || chains[c - 1].l_query != ch.l_query || chains[c - 1].query_off != ch.query_off)) {
             eng->err = "bsw_extend_chains: same_read set on a chain whose predecessor is another read";
             return BSW_ERR_PARAM;
@@ -148,7 +148,6 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
     if (!eng->cbufs) eng->cbufs = new ChainBufs();
     ChainBufs& CB = *static_cast<ChainBufs*>(eng->cbufs);
     std::vector<int32_t> band, prev, pick;
-    std::vector<uint8_t> done_before((size_t)n_chains, 0);      // chain had no seed left when the round began
     auto add_stats = [&]() {
         const bsw_stats& s = eng->stats;
         total.pairs += s.pairs; total.cells_nominal += s.cells_nominal; total.cells_effective += s.cells_effective;
@@ -163,26 +162,27 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
     auto lap = [&](int k) { const double t = now_ms(); tl[k] += t - t_mark; t_mark = t; };
     for (;;) {
         ++rounds;
-        // ---- next surviving seed of every chain (containment test, bwamem.c:667-700) ------------
+        // ---- next surviving seed of every read (containment test, bwamem.c:667-700) -------------
+        // The chains of a read run one after the other (mem_align1_core pushes their regions into one vector,
+        // bwamem.c:1105-1112): per read, the first chain that still has seeds is searched; if the search only
+        // skips contained seeds and drains the chain, the read's next chain is searched in the same round, so
+        // a round without a candidate means every chain of the batch is done (the result never depends on
+        // which other reads share the batch).
         cand.clear();
         pick.assign((size_t)n_chains, -1);
-        for (int64_t c = 0; c < n_chains; ++c) done_before[(size_t)c] = run[(size_t)c].k < 0 ? 1 : 0;
-        eng->pool->for_range(n_chains, 512, [&](int64_t cb, int64_t ce, int) {
-        for (int64_t c = cb; c < ce; ++c) {
+        eng->pool->for_range((int64_t)groups.size(), 256, [&](int64_t gb, int64_t ge, int) {
+        for (int64_t gi = gb; gi < ge; ++gi) {
+        const int64_t g0 = groups[(size_t)gi], g1 = gi + 1 < (int64_t)groups.size() ? groups[(size_t)gi + 1] : n_chains;
+        for (int64_t c = g0; c < g1; ++c) {
             const bsw_chain& ch = chains[c];
             ChainRun& R = run[(size_t)c];
+            if (R.k < 0) continue;                                              // done: the read's next chain acts
             const bsw_seed* S = seeds + ch.seed_first;
-            // the chains of a read run one after the other: this chain acts once its predecessors are done
-            // (a predecessor that finishes in this very search leaves k < 0 only after its own loop, so the
-            // chain waits for the next round -- chains of a group may sit in different pool ranges)
-            bool blocked = false;
-            for (int64_t g = group_first[(size_t)c]; g < c; ++g) blocked = blocked || done_before[(size_t)g] == 0;
-            if (blocked) continue;
             // regions the containment test looks at: those of the read's earlier chains, then this chain's
             int n_av = 0;
-            for (int64_t g = group_first[(size_t)c]; g <= c; ++g) n_av += out_count[g];
+            for (int64_t g = g0; g <= c; ++g) n_av += out_count[g];
             auto reg_at = [&](int i) -> const bsw_alnreg& {
-                for (int64_t g = group_first[(size_t)c];; ++g) {
+                for (int64_t g = g0;; ++g) {
                     if (i < out_count[g]) return out[chains[g].seed_first + i];
                     i -= out_count[g];
                 }
@@ -217,6 +217,8 @@ int bsw_extend_chains(bsw_engine* eng, const bsw_chain* chains, int64_t n_chains
                 pick[(size_t)c] = (int)(uint32_t)R.srt[k];
                 break;
             }
+            if (pick[(size_t)c] >= 0) break;                                    // the read's later chains wait for this one
+        }
         }
         });
         for (int64_t c = 0; c < n_chains; ++c) {

@@ -126,6 +126,14 @@ struct Slot {
     // chunk state
     int64_t a = 0; int n = 0;             // pairs [a, a + n) of the batch
     bool direct = false;
+    bool packed = false;                  // packed route (bsw_extend_packed): desc holds bsw_pair_desc records
+    bool use16 = true;                    // this chunk's short pairs run the packed 16-bit kernel
+    const uint8_t* q2src = nullptr;       // packed route: device copy of the chunk's 2-bit words (query / reference) ...
+    const uint8_t* r2src = nullptr;
+    const uint32_t* dp_q = nullptr;       // 2-bit words the DP kernels read (the packed copies, or q2src / r2src in place)
+    const uint32_t* dp_t = nullptr;
+    unsigned int q_lo = 0, r_lo = 0;      // ... and the batch word offset of its first word
+    Buf<uint8_t> outbuf;                  // packed route: OutScore records on their way out
     bool tiny = false;                    // latency route: every pair goes to the warp-per-pair kernel (run_pipeline)
     bool seq_on_device = false;           // both sequence buffers are device copies with >= 64 bytes of slack behind them
     const uint8_t* qbase = nullptr;       // device-visible address of descriptor offset 0 (query / reference)
@@ -151,6 +159,17 @@ struct DevCtx {
     unsigned long long* d_cells = nullptr;
     unsigned long long* h_cells = nullptr;
     bool attr_set = false;
+    // packed route: buffers of the batch that stay resident for the whole call (RAW sequences; every 2-bit word
+    // when the batch is not ordered) and the event that marks their arrival
+    Buf<uint8_t> rawq, rawr, allq, allr;
+    cudaEvent_t ev_res{};
+};
+
+// What a call processes: the reference's layout (SeqPair records + one byte per base, results in place) or a
+// packed batch (include/bsw.h: bsw_packed_batch) with a separate result array.
+struct Job {
+    SeqPair* pairs = nullptr; const uint8_t* seq_ref = nullptr; const uint8_t* seq_qer = nullptr;
+    const bsw_packed_batch* pb = nullptr; void* out = nullptr; bool out16 = false;
 };
 
 } // namespace
@@ -176,11 +195,19 @@ struct bsw_engine {
 
 namespace {
 
+// A call on an engine with several devices runs one host thread per device (run_sharded): each thread collects its
+// statistics and its error text in its own Shard and points these at them; everywhere else they stay null and the
+// engine's own members are used.
+thread_local bsw_stats* t_stats = nullptr;
+thread_local std::string* t_err = nullptr;
+inline bsw_stats& stats_of(bsw_engine* eng) { return t_stats ? *t_stats : eng->stats; }
+inline std::string& err_of(bsw_engine* eng) { return t_err ? *t_err : eng->err; }
+
 #define CUDA_TRY(call)                                                                          \
     do {                                                                                        \
         cudaError_t e_ = (call);                                                                \
         if (e_ != cudaSuccess) {                                                                \
-            eng->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            err_of(eng) = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
             return BSW_ERR_CUDA;                                                                \
         }                                                                                       \
     } while (0)
@@ -358,7 +385,7 @@ int slot_create(bsw_engine* eng, DevCtx& c, Slot& s)
     if (c.svc_sms > 0) {
         CUstream cu = nullptr;
         if (green_api().stream_create(&cu, c.g_svc, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) {
-            eng->err = "cuGreenCtxStreamCreate failed";
+            err_of(eng) = "cuGreenCtxStreamCreate failed";
             return BSW_ERR_CUDA;
         }
         s.st_svc = (cudaStream_t)cu;
@@ -385,7 +412,7 @@ void slot_destroy(Slot& s)
     for (cudaEvent_t e : s.ev_tl) if (e) cudaEventDestroy(e);
     release(s.raw_pairs); release(s.desc); release(s.meta); release(s.res); release(s.perm); release(s.rank);
     release(s.bins); release(s.nlist); release(s.llist); release(s.qpk); release(s.tpk); release(s.scratch);
-    release(s.qraw); release(s.rraw);
+    release(s.qraw); release(s.rraw); release(s.outbuf);
     if (s.d_info) cudaFree(s.d_info);
     if (s.h_info) cudaFreeHost(s.h_info);
     if (s.d_queue) cudaFree(s.d_queue);
@@ -431,8 +458,8 @@ int direct_begin(bsw_engine* eng, DevCtx& c, Slot& s, const SeqPair* pairs, cons
     bsw_info_publish<<<1, PREP_BLOCK, 0, s.st>>>(s.d_info, s.h_info_dev);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s.ev_info, s.st));
-    eng->stats.h2d_bytes += (int64_t)bytes;
-    eng->stats.kernel_launches += 4;
+    stats_of(eng).h2d_bytes += (int64_t)bytes;
+    stats_of(eng).kernel_launches += 4;
 
     // Speculative sequence copy.  The byte range the chunk's sequences span is only known after the
     // scan, and waiting for it would leave the copy engine idle for a host round trip per chunk.
@@ -461,7 +488,7 @@ int direct_begin(bsw_engine* eng, DevCtx& c, Slot& s, const SeqPair* pairs, cons
         if (int rc = ensure(eng, *sd.buf, (size_t)(sd.hi - lo_al) + 64)) return rc;
         CUDA_TRY(cudaMemcpyAsync(sd.buf->d, sd.host + lo_al, (size_t)(sd.hi - lo_al), cudaMemcpyHostToDevice, c.h2d));
         s.spec[k] = true; s.spec_lo[k] = lo_al; s.spec_hi[k] = sd.hi;
-        eng->stats.h2d_bytes += sd.hi - lo_al;
+        stats_of(eng).h2d_bytes += sd.hi - lo_al;
     }
     CUDA_TRY(cudaEventRecord(s.ev_seqd, c.h2d));
     return BSW_OK;
@@ -495,17 +522,108 @@ int direct_sequences(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8
             if (int rc = ensure(eng, *sd.buf, bytes + 64)) return rc;
             CUDA_TRY(cudaMemcpyAsync(sd.buf->d, sd.host + lo_al, bytes, cudaMemcpyHostToDevice, s.st));
             *sd.out = sd.buf->d + (sd.base0 - lo_al);
-            eng->stats.h2d_bytes += (int64_t)bytes;
+            stats_of(eng).h2d_bytes += (int64_t)bytes;
         } else {
             void* dp = nullptr;
             CUDA_TRY(cudaHostGetDevicePointer(&dp, const_cast<uint8_t*>(sd.host), 0));
             *sd.out = static_cast<const uint8_t*>(dp) + sd.base0;
             s.seq_on_device = false;                                        // host memory read in place: it may end with the last base
-            eng->stats.h2d_bytes += (int64_t)sd.bases;
+            stats_of(eng).h2d_bytes += (int64_t)sd.bases;
         }
     }
     // (the chunk stream never overtakes its own speculative copies, used or not: the buffers are its own)
     CUDA_TRY(cudaStreamWaitEvent(s.st, s.ev_seqd, 0));
+    if (g_timeline) CUDA_TRY(cudaEventRecord(s.ev_seq, s.st));
+    return BSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage A, packed route: descriptors + the chunk's 2-bit words DMA'd as the loader packed them, scan
+// ------------------------------------------------------------------------------------------
+inline unsigned int words_of(int len) { return (unsigned int)(len + 15) >> 4; }
+
+// buffers of a packed batch that every chunk of the call addresses absolutely: the RAW sequences, and all 2-bit
+// words when the batch does not promise ascending offsets
+int packed_resident(bsw_engine* eng, DevCtx& c, const bsw_packed_batch& B)
+{
+    CUDA_TRY(cudaSetDevice(c.dev));
+    if (B.raw_q_bytes > 0 || B.raw_r_bytes > 0) {
+        if (int rc = ensure(eng, c.rawq, (size_t)B.raw_q_bytes + 64)) return rc;
+        if (int rc = ensure(eng, c.rawr, (size_t)B.raw_r_bytes + 64)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c.rawq.d, B.raw_q, (size_t)B.raw_q_bytes, cudaMemcpyHostToDevice, c.h2d));
+        CUDA_TRY(cudaMemcpyAsync(c.rawr.d, B.raw_r, (size_t)B.raw_r_bytes, cudaMemcpyHostToDevice, c.h2d));
+        stats_of(eng).h2d_bytes += B.raw_q_bytes + B.raw_r_bytes;
+    }
+    if (!B.ordered) {
+        if (int rc = ensure(eng, c.allq, (size_t)B.q2_words * 4 + 64)) return rc;
+        if (int rc = ensure(eng, c.allr, (size_t)B.r2_words * 4 + 64)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c.allq.d, B.q2, (size_t)B.q2_words * 4, cudaMemcpyHostToDevice, c.h2d));
+        CUDA_TRY(cudaMemcpyAsync(c.allr.d, B.r2, (size_t)B.r2_words * 4, cudaMemcpyHostToDevice, c.h2d));
+        stats_of(eng).h2d_bytes += (B.q2_words + B.r2_words) * 4;
+    }
+    CUDA_TRY(cudaEventRecord(c.ev_res, c.h2d));
+    return BSW_OK;
+}
+
+int packed_begin(bsw_engine* eng, DevCtx& c, Slot& s, const bsw_packed_batch& B)
+{
+    const bsw_pair_desc* D = B.desc + s.a;
+    if (int rc = ensure(eng, s.desc, (size_t)s.n)) return rc;
+    if (int rc = ensure(eng, s.bins, BINS_WORDS)) return rc;
+    bsw_info_init<<<1, PREP_BLOCK, 0, s.st>>>(s.d_info);
+    bsw_zero_words<<<64, PREP_BLOCK, 0, s.st>>>(reinterpret_cast<uint4*>(s.bins.d), (int)(BINS_WORDS / 4));
+    s.bins_zeroed = true;
+    CUDA_TRY(cudaMemcpyAsync(s.desc.d, D, sizeof(bsw_pair_desc) * (size_t)s.n, cudaMemcpyHostToDevice, c.h2d));
+    CUDA_TRY(cudaEventRecord(s.ev_rec, c.h2d));
+    CUDA_TRY(cudaStreamWaitEvent(s.st, s.ev_rec, 0));
+    stats_of(eng).h2d_bytes += (int64_t)sizeof(bsw_pair_desc) * s.n;
+    PackedRange R{};
+    R.rawq = (unsigned int)B.raw_q_bytes; R.rawr = (unsigned int)B.raw_r_bytes;
+    if (!B.ordered) {
+        R.qlo = 0; R.qhi = (unsigned int)B.q2_words; R.rlo = 0; R.rhi = (unsigned int)B.r2_words;
+        s.q2src = c.allq.d; s.r2src = c.allr.d;
+    } else {
+        // ascending offsets: the chunk's words are the range from its first to its last 2-bit pair
+        int f = 0, l = s.n - 1;
+        while (f < s.n && (D[f].flags & BSW_PAIR_RAW)) ++f;
+        while (l > f && (D[l].flags & BSW_PAIR_RAW)) --l;
+        if (f < s.n) {
+            R.qlo = D[f].q_off; R.qhi = D[l].q_off + words_of(D[l].len2);
+            R.rlo = D[f].r_off; R.rhi = D[l].r_off + words_of(D[l].len1);
+            if (R.qhi < R.qlo || R.rhi < R.rlo || (int64_t)R.qhi > B.q2_words || (int64_t)R.rhi > B.r2_words) {
+                err_of(eng) = "bsw_extend_packed: batch.ordered is set but the offsets do not ascend inside the buffers";
+                return BSW_ERR_PARAM;
+            }
+        }
+        const size_t qb = (size_t)(R.qhi - R.qlo) * 4, rb = (size_t)(R.rhi - R.rlo) * 4;
+        if (int rc = ensure(eng, s.qraw, qb + 64)) return rc;
+        if (int rc = ensure(eng, s.rraw, rb + 64)) return rc;
+        if (qb) CUDA_TRY(cudaMemcpyAsync(s.qraw.d, B.q2 + R.qlo, qb, cudaMemcpyHostToDevice, c.h2d));
+        if (rb) CUDA_TRY(cudaMemcpyAsync(s.rraw.d, B.r2 + R.rlo, rb, cudaMemcpyHostToDevice, c.h2d));
+        s.q2src = s.qraw.d; s.r2src = s.rraw.d;
+        stats_of(eng).h2d_bytes += (int64_t)(qb + rb);
+    }
+    s.q_lo = R.qlo; s.r_lo = R.rlo;
+    CUDA_TRY(cudaEventRecord(s.ev_seqd, c.h2d));
+    bsw_scan_packed<<<grid_for(c, s.n, 8 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.desc.d, s.n, R, eng->p.match, eng->short_max,
+                                                                               eng->use16 ? 1 : 0, s.d_info);
+    bsw_info_publish<<<1, PREP_BLOCK, 0, s.st>>>(s.d_info, s.h_info_dev);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s.ev_info, s.st));
+    stats_of(eng).kernel_launches += 4;
+    return BSW_OK;
+}
+
+// stage B, packed route: the summary is on the host; the byte kernels read the resident RAW sequences
+int packed_info(bsw_engine* eng, DevCtx& c, Slot& s)
+{
+    CUDA_TRY(cudaEventSynchronize(s.ev_info));
+    s.info = *s.h_info;
+    if (s.info.bad) return BSW_ERR_DOMAIN;
+    s.qbase = c.rawq.d; s.rbase = c.rawr.d;
+    s.seq_on_device = true;
+    CUDA_TRY(cudaStreamWaitEvent(s.st, s.ev_seqd, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s.st, c.ev_res, 0));
     if (g_timeline) CUDA_TRY(cudaEventRecord(s.ev_seq, s.st));
     return BSW_OK;
 }
@@ -558,7 +676,7 @@ int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t
     if (I.bad) return BSW_ERR_DOMAIN;
     for (int b = 0; b < nblk; ++b) { qsum[(size_t)b + 1] += qsum[(size_t)b]; rsum[(size_t)b + 1] += rsum[(size_t)b]; }
     const uint64_t qtot = qsum[(size_t)nblk], rtot = rsum[(size_t)nblk];
-    if (qtot > 0x3fffffffull || rtot > 0x3fffffffull) { eng->err = "chunk too large for 32-bit byte offsets"; return BSW_ERR_PARAM; }
+    if (qtot > 0x3fffffffull || rtot > 0x3fffffffull) { err_of(eng) = "chunk too large for 32-bit byte offsets"; return BSW_ERR_PARAM; }
     if (int rc = ensure(eng, s.desc, (size_t)n, true)) return rc;
     if (int rc = ensure(eng, s.qraw, (size_t)qtot + 64, true)) return rc;
     if (int rc = ensure(eng, s.rraw, (size_t)rtot + 64, true)) return rc;
@@ -580,16 +698,16 @@ int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t
         }
     });
     memset(s.qraw.h + qtot, 0, 64); memset(s.rraw.h + rtot, 0, 64);
-    eng->stats.ms_pack += now_ms() - t0;
+    stats_of(eng).ms_pack += now_ms() - t0;
     // H2D
     bsw_info_init<<<1, PREP_BLOCK, 0, s.st>>>(s.d_info);
-    eng->stats.kernel_launches++;
+    stats_of(eng).kernel_launches++;
     CUDA_TRY(cudaMemcpyAsync(s.desc.d, s.desc.h, sizeof(int4) * (size_t)n, cudaMemcpyHostToDevice, s.st));
     CUDA_TRY(cudaMemcpyAsync(s.qraw.d, s.qraw.h, (size_t)qtot + 64, cudaMemcpyHostToDevice, s.st));
     CUDA_TRY(cudaMemcpyAsync(s.rraw.d, s.rraw.h, (size_t)rtot + 64, cudaMemcpyHostToDevice, s.st));
     s.qbase = s.qraw.d; s.rbase = s.rraw.d;
     s.seq_on_device = true;
-    eng->stats.h2d_bytes += (int64_t)(sizeof(int4) * (size_t)n + qtot + rtot + 128);
+    stats_of(eng).h2d_bytes += (int64_t)(sizeof(int4) * (size_t)n + qtot + rtot + 128);
     return BSW_OK;
 }
 
@@ -606,6 +724,9 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
     // whose rows live in shared memory; a pair then takes ~0.1 ms instead of ~0.35 ms.
     if (s.tiny) I.n_short = 0;
     s.n_sorted = I.n_short;
+    // (packed route: 2-bit pairs outside the 16-bit kernel's score domain cannot fall back to the byte kernel --
+    // the chunk then runs the 32-bit kernel as a whole)
+    s.use16 = eng->use16 && !(s.packed && I.n_wide > 0);
     const size_t qwords = (size_t)(I.qbases / 16) + (size_t)I.n_short + 8;
     const size_t twords = (size_t)(I.tbases / 16) + (size_t)I.n_short + 8;
     if (int rc = ensure(eng, s.meta, (size_t)n)) return rc;
@@ -634,25 +755,40 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
         unsigned int* ticket = totals + SCAN_MAX_TILES;
         if (!s.bins_zeroed) {                                                // (direct route: cleared at open())
             bsw_zero_words<<<64, PREP_BLOCK, 0, s.st>>>(reinterpret_cast<uint4*>(s.bins.d), (int)(BINS_WORDS / 4));
-            eng->stats.kernel_launches++;
+            stats_of(eng).kernel_launches++;
         }
         s.bins_zeroed = false;
         TL_MARK(0);
         bsw_bucket_count<<<grid_for(c, n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.desc.d, n, K, s.bins.d, s.rank.d, s.llist.d, s.d_info);
-        eng->stats.kernel_launches++;
+        stats_of(eng).kernel_launches++;
         TL_MARK(1);
         if (I.n_short > 0) {
             bsw_bucket_scan<<<ntiles, PREP_BLOCK, 0, s.st>>>(s.bins.d, nbins, totals, ticket);
             TL_MARK(2);
-            bsw_bucket_scatter<<<grid_for(c, n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d);
-            TL_MARK(3);
-            // 2-bit packing in processing order
-            bsw_pack_pairs<<<grid_for(c, I.n_short, PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.desc.d, s.perm.d, I.n_short, s.qbase, s.rbase,
-                                                                          s.meta.d, s.qpk.d, s.tpk.d, s.nlist.d, s.d_info,
-                                                                          eng->use16 ? eng->p.match : 0,
-                                                                          s.seq_on_device ? 1 : 0);
+            static const bool gather = getenv("BSW_PACKED_GATHER") && atoi(getenv("BSW_PACKED_GATHER")) != 0;   // A/B: re-lay the words in processing order
+            if (s.packed && !gather) {
+                // packed route: the DP kernels read the 2-bit words where the host's DMA left them
+                bsw_bucket_scatter<true><<<grid_for(c, n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(
+                    s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d, s.meta.d, s.nlist.d, s.d_info, s.q_lo, s.r_lo);
+                TL_MARK(3);
+                s.dp_q = reinterpret_cast<const uint32_t*>(s.q2src); s.dp_t = reinterpret_cast<const uint32_t*>(s.r2src);
+                stats_of(eng).kernel_launches += 2;
+            } else {
+                bsw_bucket_scatter<false><<<grid_for(c, n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d);
+                TL_MARK(3);
+                // 2-bit packing in processing order
+                if (s.packed)
+                    bsw_pack_pairs<true><<<grid_for(c, I.n_short, PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(
+                        s.desc.d, s.perm.d, I.n_short, s.q2src, s.r2src, s.meta.d, s.qpk.d, s.tpk.d, s.nlist.d, s.d_info, 0, 1,
+                        s.q_lo, s.r_lo);
+                else
+                    bsw_pack_pairs<false><<<grid_for(c, I.n_short, PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(
+                        s.desc.d, s.perm.d, I.n_short, s.qbase, s.rbase, s.meta.d, s.qpk.d, s.tpk.d, s.nlist.d, s.d_info,
+                        s.use16 ? eng->p.match : 0, s.seq_on_device ? 1 : 0);
+                s.dp_q = s.qpk.d; s.dp_t = s.tpk.d;
+                stats_of(eng).kernel_launches += 3;
+            }
             TL_MARK(4);
-            eng->stats.kernel_launches += 3;
             // launch plan: the processing order ascends in len2, so the shared-memory classes are
             // prefix ranges of it, read off the len2 histogram
             static const bool circ_ok = !(getenv("BSW_CIRC") && atoi(getenv("BSW_CIRC")) == 0);   // BSW_CIRC=0: rows always hold the whole query
@@ -660,10 +796,10 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
             for (int l = I.mn[0]; l <= std::min(I.mx[0], eng->short_max); ++l) {
                 const int cnt = (int)I.hist[l];
                 if (!cnt) continue;
-                int qs = stride_for(l, eng->use16);
+                int qs = stride_for(l, s.use16);
                 int wc = 0;
                 const int plane = qs;
-                if (eng->use16 && circ_ok && eng->kp.w <= 4096 && (k16::circ_cols(eng->kp.w) + 4) * 10 <= qs * 7) {
+                if (s.use16 && circ_ok && eng->kp.w <= 4096 && (k16::circ_cols(eng->kp.w) + 4) * 10 <= qs * 7) {
                     // the band is much narrower than the query: circular rows of the band's width (bsw_kernel16.cuh);
                     // every longer class then shares one row stride and merges into one launch.  Only where the
                     // rows shrink by 30 % or more: the wrap costs ~6 registers and a few instructions per block,
@@ -682,7 +818,7 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
                 }
                 pos += cnt;
             }
-            if (eng->use16) for (Launch& L : s.plan) L.block = short16_block(L.qstride, L.plane, L.wcols != 0);
+            if (s.use16) for (Launch& L : s.plan) L.block = short16_block(L.qstride, L.plane, L.wcols != 0);
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -693,7 +829,7 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
     s.fork_recorded = true;
     bsw_info_publish<<<1, PREP_BLOCK, 0, s.st>>>(s.d_info, s.h_info_dev);
     CUDA_TRY(cudaGetLastError());
-    eng->stats.kernel_launches++;
+    stats_of(eng).kernel_launches++;
     CUDA_TRY(cudaEventRecord(s.ev_lists, s.st));
     return BSW_OK;
 }
@@ -714,11 +850,11 @@ int launch_dp(bsw_engine* eng, DevCtx& c, Slot& s, bool partitioned = false)
         const Launch& L = s.plan[(size_t)k];
         cudaStream_t st = cs[li % NSTREAMS];
         const int grid = (L.count + L.block - 1) / L.block;
-        if (eng->use16) {
+        if (s.use16) {
             const bool sg = eng->kp.oe_del == eng->kp.oe_ins;
             const size_t smem = k16::smem_bytes(L.block, L.qstride, L.plane);
 #define BSW_LAUNCH16(B, SG, CIRC)                                                                                     \
-            bsw_short16_kernel<B, SG, CIRC><<<grid, B, smem, st>>>(s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first,   \
+            bsw_short16_kernel<B, SG, CIRC><<<grid, B, smem, st>>>(s.meta.d, s.perm.d, s.dp_q, s.dp_t, s.res.d, L.first,     \
                                                                    L.count, L.qstride, eng->kp, c.d_cells, L.wcols)
             const int variant = (L.block == 32 ? 4 : 0) | (sg ? 2 : 0) | (L.wcols ? 1 : 0);
             switch (variant) {
@@ -734,9 +870,9 @@ int launch_dp(bsw_engine* eng, DevCtx& c, Slot& s, bool partitioned = false)
 #undef BSW_LAUNCH16
         } else {
             bsw_short_kernel<SHORT_BLOCK, false><<<grid, SHORT_BLOCK, short_smem_bytes(L.qstride), st>>>(
-                s.meta.d, s.perm.d, s.qpk.d, s.tpk.d, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
+                s.meta.d, s.perm.d, s.dp_q, s.dp_t, s.res.d, L.first, L.count, L.qstride, eng->kp, c.d_cells);
         }
-        eng->stats.kernel_launches++;
+        stats_of(eng).kernel_launches++;
     }
     CUDA_TRY(cudaGetLastError());
     for (int k = 0; k < used; ++k) {
@@ -755,7 +891,7 @@ int launch_bytes(bsw_engine* eng, DevCtx& c, Slot& s)
         bsw_short_kernel<SHORT_BLOCK, true><<<grid, SHORT_BLOCK, short_smem_bytes(qstride), s.st>>>(
             s.desc.d, s.nlist.d, reinterpret_cast<const uint32_t*>(s.qbase), reinterpret_cast<const uint32_t*>(s.rbase),
             s.res.d, 0, (int)s.n_nlist, qstride, eng->kp, c.d_cells);
-        eng->stats.kernel_launches++;
+        stats_of(eng).kernel_launches++;
     }
     if (s.n_llist > 0) {
         s.long_stride = (s.info.qmax_all + 12) & ~3;
@@ -775,26 +911,40 @@ int launch_bytes(bsw_engine* eng, DevCtx& c, Slot& s)
                 s.desc.d, s.llist.d, s.qbase, s.rbase, s.res.d, (int)s.n_llist, eng->kp, s.scratch.d, s.long_stride,
                 s.d_queue, c.d_cells);
         }
-        eng->stats.kernel_launches++;
+        stats_of(eng).kernel_launches++;
     }
     CUDA_TRY(cudaGetLastError());
     return BSW_OK;
 }
 
 // results of a chunk leave the device: straight into the caller's records (direct) or D2H
-int output_chunk(bsw_engine* eng, DevCtx& c, Slot& s, SeqPair* pairs)
+int output_chunk(bsw_engine* eng, DevCtx& c, Slot& s, const Job& job)
 {
-    if (s.direct) {
+    SeqPair* const pairs = job.pairs;
+    if (s.packed) {
+        // the six result fields alone: 16 bytes per pair as the kernels leave them, or OutScore records (24 bytes)
+        if (job.out16) {
+            CUDA_TRY(cudaMemcpyAsync(static_cast<bsw_score16*>(job.out) + s.a, s.res.d, sizeof(int4) * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
+            stats_of(eng).d2h_bytes += (int64_t)sizeof(int4) * s.n;
+        } else {
+            if (int rc = ensure(eng, s.outbuf, sizeof(OutScore) * (size_t)s.n)) return rc;
+            bsw_out_scores<<<grid_for(c, s.n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.res.d, s.n, reinterpret_cast<int2*>(s.outbuf.d));
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(static_cast<OutScore*>(job.out) + s.a, s.outbuf.d, sizeof(OutScore) * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
+            stats_of(eng).kernel_launches++;
+            stats_of(eng).d2h_bytes += (int64_t)sizeof(OutScore) * s.n;
+        }
+    } else if (s.direct) {
         // results go into the device copy of the records, which then returns by one DMA (the
         // input fields come back as they left; per-field writes over PCIe would be 4-byte TLPs)
         bsw_writeback<<<grid_for(c, s.n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.res.d, s.n, reinterpret_cast<SeqPair*>(s.raw_pairs.d));
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(pairs + s.a, s.raw_pairs.d, (size_t)s.n * sizeof(SeqPair), cudaMemcpyDeviceToHost, s.st));
-        eng->stats.kernel_launches++;
-        eng->stats.d2h_bytes += (int64_t)s.n * (int64_t)sizeof(SeqPair);
+        stats_of(eng).kernel_launches++;
+        stats_of(eng).d2h_bytes += (int64_t)s.n * (int64_t)sizeof(SeqPair);
     } else {
         CUDA_TRY(cudaMemcpyAsync(s.res.h, s.res.d, sizeof(int4) * (size_t)s.n, cudaMemcpyDeviceToHost, s.st));
-        eng->stats.d2h_bytes += (int64_t)sizeof(int4) * s.n;
+        stats_of(eng).d2h_bytes += (int64_t)sizeof(int4) * s.n;
     }
     CUDA_TRY(cudaEventRecord(s.ev_out, s.st));
     return BSW_OK;
@@ -817,7 +967,7 @@ void unpack_chunk(bsw_engine* eng, Slot& s, SeqPair* pairs)
     eng->pool->for_range(s.n, 8192, [&](int64_t b, int64_t e, int) {
         for (int64_t k = b; k < e; ++k) write_result(P[k], r[k]);
     });
-    eng->stats.ms_scatter += now_ms() - t0;
+    stats_of(eng).ms_scatter += now_ms() - t0;
 }
 
 // after ev_lists: the pack kernel's counters are on the host
@@ -848,12 +998,18 @@ struct ChunkRef { int dev; int slot; };
 
 // Runs the chunks of the batch through the pipeline.  keep == true: stop before the DP launches
 // and keep every chunk resident in its own slot (bsw_stage).
-int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer,
-                 int64_t n, int64_t chunk_pairs, bool keep)
+//
+// The call's pairs [a0, a0 + n) run on the devices [dev_lo, dev_lo + ndev) of the engine, chunks dealt round-robin
+// (run_sharded gives every device its own contiguous, cost-balanced range and its own host thread; bsw_stage deals
+// one range over all devices).
+int run_pipeline(bsw_engine* eng, const Job& job, int dev_lo, int ndev, int64_t a0, int64_t n, int64_t chunk_pairs, bool keep)
 {
-    bsw_stats& S = eng->stats;
-    const int ndev = (int)eng->devs.size();
-    const bool direct = is_pinned(pairs) && is_pinned(seq_ref) && is_pinned(seq_qer);
+    bsw_stats& S = stats_of(eng);
+    SeqPair* const pairs = job.pairs;
+    const uint8_t* const seq_ref = job.seq_ref;
+    const uint8_t* const seq_qer = job.seq_qer;
+    const bool packed = job.pb != nullptr;
+    const bool direct = packed || (is_pinned(pairs) && is_pinned(seq_ref) && is_pinned(seq_qer));
     // PCIe-bound or compute-bound?  A sample of the records gives DP time (nominal cells at the
     // resident kernel rate) against transfer time (record + sequence bytes at PCIe rate) per pair.
     // PCIe-bound batches run partitioned: chunk streams on the service SMs, DP on the rest.
@@ -861,15 +1017,21 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
     if (!keep && n >= 4 * CHUNK_MIN) {
         double cells = 0, bytes = 0;
         const int64_t step = std::max<int64_t>(1, n / 509);
-        for (int64_t i = 0; i < n; i += step) {
-            cells += (double)pairs[i].len1 * (double)pairs[i].len2;
-            bytes += (double)sizeof(SeqPair) + (double)pairs[i].len1 + (double)pairs[i].len2;
+        for (int64_t i = a0; i < a0 + n; i += step) {
+            if (packed) {
+                const bsw_pair_desc& d = job.pb->desc[i];
+                cells += (double)d.len1 * (double)d.len2;
+                bytes += (double)sizeof(bsw_pair_desc) + ((d.flags & BSW_PAIR_RAW) ? (double)d.len1 + d.len2 : 0.25 * ((double)d.len1 + d.len2));
+            } else {
+                cells += (double)pairs[i].len1 * (double)pairs[i].len2;
+                bytes += (double)sizeof(SeqPair) + (double)pairs[i].len1 + (double)pairs[i].len2;
+            }
         }
         pcie_bound = partitioned = cells / 2.0e9 < 0.7 * (bytes / 50e6);
-        for (DevCtx& c : eng->devs) partitioned = partitioned && c.svc_sms > 0;
+        for (int d = dev_lo; d < dev_lo + ndev; ++d) partitioned = partitioned && eng->devs[(size_t)d].svc_sms > 0;
     }
-    eng->stats.partitioned = partitioned ? 1 : 0;
-    const bool tiny = !keep && eng->p.tiny_batch > 0 && n <= eng->p.tiny_batch;
+    S.partitioned = partitioned ? 1 : 0;
+    const bool tiny = !keep && !packed && eng->p.tiny_batch > 0 && n <= eng->p.tiny_batch;
     // chunk boundaries: a small first chunk (the first DP starts after a short H2D), full-size
     // chunks, then -- where transfers or the host bound the batch -- a geometric ramp-down so that the
     // work left after the last H2D (its DP and its D2H) is small.  PCIe-bound batches use smaller full-size chunks, sized so that the DP of one
@@ -884,9 +1046,11 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
     // (a compute-bound batch on pinned buffers has all its data on the device long before the DP is done:
     // small last chunks only add launches with few blocks -- scripts/chunk_probe.py: large mix 23.1 -> 21.9 ms)
     const bool rampdown = env_rampdown >= 0 ? env_rampdown != 0 : (small_chunks || !direct);
-    std::vector<int64_t> cut{0};
+    std::vector<int64_t> cut{a0};
     static const int64_t env_first = getenv("BSW_FIRST_CHUNK") ? atoll(getenv("BSW_FIRST_CHUNK")) : 0;
-    int64_t ramp = keep ? big : (env_first > 0 && !small_chunks ? env_first : CHUNK_MIN);
+    // (packed route, compute-bound: the whole batch arrives in a fraction of its DP time, and 64 k pairs -- half of what
+    // the SMs hold at once -- start the DP 0.15 ms earlier than they cost in launch tails: 3.07 -> 2.93 ms per 1 M short pairs)
+    int64_t ramp = keep ? big : (env_first > 0 && !small_chunks ? env_first : (packed && !small_chunks ? 2 * CHUNK_MIN : CHUNK_MIN));
     for (int64_t rem = n; rem > 0;) {
         int64_t sz;
         if (ramp < big && rem > 4 * ramp) { sz = ramp; ramp = small_chunks ? big : ramp * 2; }
@@ -900,19 +1064,20 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
     std::vector<ChunkRef> refs((size_t)nchunks);
     const double tl_host0 = now_ms();
     std::vector<std::string> tl_lines;
-    eng->staged_chunks.clear();
-    for (DevCtx& c : eng->devs) {
+    if (keep) eng->staged_chunks.clear();
+    for (int d = dev_lo; d < dev_lo + ndev; ++d) {
+        DevCtx& c = eng->devs[(size_t)d];
         CUDA_TRY(cudaSetDevice(c.dev));
         if (int rc = set_kernel_attrs(eng, c)) return rc;
-        CUDA_TRY(cudaMemsetAsync(c.d_cells, 0, sizeof(unsigned long long), c.cs[0]));
-        CUDA_TRY(cudaStreamSynchronize(c.cs[0]));
+        if (packed) if (int rc = packed_resident(eng, c, *job.pb)) return rc;
     }
+    DevCtx& tl_dev = eng->devs[(size_t)dev_lo];                   // BSW_TIMELINE: the device whose events are printed
     auto slot_of = [&](int64_t k) -> Slot& { return eng->devs[(size_t)refs[(size_t)k].dev].slots[(size_t)refs[(size_t)k].slot]; };
     auto dev_of = [&](int64_t k) -> DevCtx& { return eng->devs[(size_t)refs[(size_t)k].dev]; };
 
     // open: bind chunk k to its device and slot; on the direct route start its records DMA + scan
     auto open = [&](int64_t k) -> int {
-        const int d = (int)(k % ndev);
+        const int d = dev_lo + (int)(k % ndev);
         const int sl = keep ? (int)(k / ndev) : (int)((k / ndev) % NSLOTS);
         refs[(size_t)k] = ChunkRef{d, sl};
         DevCtx& c = eng->devs[(size_t)d];
@@ -922,10 +1087,12 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
         Slot& s = *sp;
         s.a = cut[(size_t)k]; s.n = (int)(cut[(size_t)k + 1] - cut[(size_t)k]);
         s.direct = direct;
+        s.packed = packed;
         s.tiny = tiny;
         s.st = partitioned ? s.st_svc : s.st_plain;
-        if (g_timeline) { if (k == 0) CUDA_TRY(cudaEventRecord(eng->devs[0].ev_t0, s.st)); s.host_t[0] = now_ms() - tl_host0; }
+        if (g_timeline) { if (k == 0) CUDA_TRY(cudaEventRecord(tl_dev.ev_t0, s.st)); s.host_t[0] = now_ms() - tl_host0; }
         CUDA_TRY(cudaEventRecord(s.ev_k0, s.st));
+        if (packed) return packed_begin(eng, c, s, *job.pb);
         if (direct) return direct_begin(eng, c, s, pairs, seq_ref, seq_qer);
         return BSW_OK;
     };
@@ -941,7 +1108,7 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
         S.n_short += s.n_sorted - (int)s.n_nlist; S.n_long += (int)s.n_llist;
         if (int rc = launch_bytes(eng, c, s)) return rc;
         CUDA_TRY(cudaEventRecord(s.ev_k1, s.st));
-        const int rc = output_chunk(eng, c, s, pairs);
+        const int rc = output_chunk(eng, c, s, job);
         if (g_timeline) s.host_t[4] = now_ms() - tl_host0;
         return rc;
     };
@@ -958,7 +1125,7 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
             float t[7] = {};
             cudaEvent_t evs[7] = {s.ev_k0, s.ev_info, s.ev_seq, s.ev_fork, s.ev_dp, s.ev_k1, s.ev_out};
             for (int e = 0; e < 7; ++e)
-                if (cudaEventElapsedTime(&t[e], eng->devs[0].ev_t0, evs[e]) != cudaSuccess) { t[e] = -1; cudaGetLastError(); }
+                if (cudaEventElapsedTime(&t[e], tl_dev.ev_t0, evs[e]) != cudaSuccess) { t[e] = -1; cudaGetLastError(); }
             snprintf(line, sizeof(line),
                      "chunk %2d n=%7d | dev: open %6.3f rec+scan %6.3f seq %6.3f prep %6.3f dp %6.3f bytes %6.3f out %6.3f"
                      " | host: open %6.3f info %6.3f launched %6.3f dp-seen %6.3f out-enq %6.3f retired %6.3f",
@@ -967,7 +1134,7 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
             tl_lines.emplace_back(line);
             float p[5] = {};
             for (int e = 0; e < 5; ++e)
-                if (cudaEventElapsedTime(&p[e], eng->devs[0].ev_t0, s.ev_tl[e]) != cudaSuccess) { p[e] = -1; cudaGetLastError(); }
+                if (cudaEventElapsedTime(&p[e], tl_dev.ev_t0, s.ev_tl[e]) != cudaSuccess) { p[e] = -1; cudaGetLastError(); }
             snprintf(line, sizeof(line), "          prep detail: zero %6.3f count %6.3f scan %6.3f scatter %6.3f pack %6.3f fork %6.3f",
                      p[0], p[1], p[2], p[3], p[4], t[3]);
             tl_lines.emplace_back(line);
@@ -994,8 +1161,9 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
         if (k < nchunks) {
             DevCtx& c = dev_of(k); Slot& s = slot_of(k);
             CUDA_TRY(cudaSetDevice(c.dev));
-            int rc = direct ? direct_sequences(eng, s, pairs, seq_ref, seq_qer) : staged_prepare(eng, s, pairs, seq_ref, seq_qer);
-            if (rc) { if (rc == BSW_ERR_DOMAIN) eng->err = kDomainMsg; return rc; }
+            int rc = packed ? packed_info(eng, c, s)
+                   : direct ? direct_sequences(eng, s, pairs, seq_ref, seq_qer) : staged_prepare(eng, s, pairs, seq_ref, seq_qer);
+            if (rc) { if (rc == BSW_ERR_DOMAIN) err_of(eng) = kDomainMsg; return rc; }
             S.cells_nominal += (int64_t)s.info.nominal;
             if ((rc = device_prepare(eng, c, s))) return rc;
             if (g_timeline) s.host_t[1] = now_ms() - tl_host0;      // (after the wait for the summary + planning)
@@ -1031,6 +1199,86 @@ int run_pipeline(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const 
         }
     }
     return BSW_OK;
+}
+
+int zero_cells(bsw_engine* eng)
+{
+    for (DevCtx& c : eng->devs) {
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaMemsetAsync(c.d_cells, 0, sizeof(unsigned long long), c.cs[0]));
+        CUDA_TRY(cudaStreamSynchronize(c.cs[0]));
+    }
+    return BSW_OK;
+}
+
+// Estimated DP cost of a pair: rows x min(columns, band) + a fixed per-pair part
+inline double pair_cost(int len1, int len2, int w)
+{
+    return (double)len1 * (double)std::min(len2, 2 * w + 1) + 64.0;
+}
+
+// The multi-GPU partitioner on the hot path (replaces the OpenMP batch loop, main_banded.cpp:279-291): the call's
+// pairs are cut, in input order, into one contiguous range per device with equal estimated DP cost
+// (sum of len1 * min(len2, 2w + 1), read off a sample of the records), each range runs through the chunk pipeline of
+// its own device on its own host thread, and every chunk's results land at its pairs' input positions.  Contiguous
+// ranges keep the host side free of any gather / scatter pass and every copy a plain DMA; the length bucketing
+// happens per chunk on the device.  BSW_MULTI=deal in the environment restores the single-thread round-robin
+// dealing of chunks over the devices (kept for A/B measurements, scripts/multi_probe.py).
+int run_sharded(bsw_engine* eng, const Job& job, int64_t n, int64_t chunk_pairs)
+{
+    const int ndev = (int)eng->devs.size();
+    if (int rc = zero_cells(eng)) return rc;
+    static const bool deal = getenv("BSW_MULTI") && std::string(getenv("BSW_MULTI")) == "deal";
+    if (ndev == 1 || deal) return run_pipeline(eng, job, 0, ndev, 0, n, chunk_pairs, false);
+    if (n < (int64_t)ndev * CHUNK_MIN) return run_pipeline(eng, job, 0, 1, 0, n, chunk_pairs, false);   // too small to split
+    // cost curve from a sample (every step-th pair), cut at equal cost
+    const int64_t step = std::max<int64_t>(1, n / 8192);
+    const int64_t ns = (n + step - 1) / step;
+    std::vector<double> cum((size_t)ns + 1, 0.0);
+    for (int64_t k = 0; k < ns; ++k) {
+        const int64_t i = k * step;
+        int l1, l2;
+        if (job.pb) { l1 = job.pb->desc[i].len1; l2 = job.pb->desc[i].len2; }
+        else { l1 = job.pairs[i].len1; l2 = job.pairs[i].len2; }
+        l1 = std::min(std::max(l1, 1), 32767); l2 = std::min(std::max(l2, 1), 32767);
+        cum[(size_t)k + 1] = cum[(size_t)k] + pair_cost(l1, l2, eng->w);
+    }
+    std::vector<int64_t> begin((size_t)ndev + 1, 0);
+    begin[(size_t)ndev] = n;
+    for (int g = 1; g < ndev; ++g) {
+        const double target = cum[(size_t)ns] * (double)g / (double)ndev;
+        const int64_t k = std::lower_bound(cum.begin(), cum.end(), target) - cum.begin();
+        begin[(size_t)g] = std::min(n, std::max(begin[(size_t)g - 1], (k * step) & ~(int64_t)63));
+    }
+    struct Shard { bsw_stats stats; std::string err; int rc = BSW_OK; };
+    std::vector<Shard> shards((size_t)ndev);
+    auto work = [&](int g) {
+        Shard& sh = shards[(size_t)g];
+        memset(&sh.stats, 0, sizeof(sh.stats));
+        t_stats = &sh.stats; t_err = &sh.err;
+        const int64_t a = begin[(size_t)g], m = begin[(size_t)g + 1] - a;
+        if (m > 0) sh.rc = run_pipeline(eng, job, g, 1, a, m, chunk_pairs, false);
+        if (sh.rc != BSW_OK) { cudaSetDevice(eng->devs[(size_t)g].dev); cudaDeviceSynchronize(); }
+        t_stats = nullptr; t_err = nullptr;
+    };
+    std::vector<std::thread> threads;
+    for (int g = 1; g < ndev; ++g) threads.emplace_back(work, g);
+    work(0);
+    for (std::thread& t : threads) t.join();
+    bsw_stats& S = eng->stats;
+    int rc = BSW_OK;
+    double ms_kernel = 0;
+    for (const Shard& sh : shards) {
+        if (sh.rc != BSW_OK && rc == BSW_OK) { rc = sh.rc; eng->err = sh.err; }
+        S.cells_nominal += sh.stats.cells_nominal; S.kernel_launches += sh.stats.kernel_launches;
+        S.h2d_bytes += sh.stats.h2d_bytes; S.d2h_bytes += sh.stats.d2h_bytes;
+        S.ms_pack += sh.stats.ms_pack; S.ms_scatter += sh.stats.ms_scatter;
+        S.n_short += sh.stats.n_short; S.n_long += sh.stats.n_long;
+        S.partitioned |= sh.stats.partitioned;
+        ms_kernel = std::max(ms_kernel, sh.stats.ms_kernel);      // the devices run side by side
+    }
+    S.ms_kernel += ms_kernel;
+    return rc;
 }
 
 int collect_cells(bsw_engine* eng)
@@ -1139,6 +1387,8 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
         }
         if (ok) setup_partitions(c);
         ok = ok && cudaEventCreate(&c.ev_t0) == cudaSuccess && cudaEventCreate(&c.ev_t1) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&c.ev_res, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventRecord(c.ev_res, c.h2d) == cudaSuccess;
         ok = ok && cudaMalloc((void**)&c.d_cells, sizeof(unsigned long long)) == cudaSuccess;
         ok = ok && cudaHostAlloc((void**)&c.h_cells, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
         if (!ok) {
@@ -1173,6 +1423,8 @@ void bsw_destroy(bsw_engine* eng)
         if (c.g_dp) green_api().destroy(c.g_dp);
         if (c.ev_t0) cudaEventDestroy(c.ev_t0);
         if (c.ev_t1) cudaEventDestroy(c.ev_t1);
+        if (c.ev_res) cudaEventDestroy(c.ev_res);
+        release(c.rawq); release(c.rawr); release(c.allq); release(c.allr);
         if (c.d_cells) cudaFree(c.d_cells);
         if (c.h_cells) cudaFreeHost(c.h_cells);
     }
@@ -1196,11 +1448,66 @@ int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const ui
     const double t_begin = now_ms();
     if (int rc = begin_batch(eng, pairs, seq_ref, seq_qer, n, w)) return rc;
     if (n == 0) return BSW_OK;
-    const int rc = run_pipeline(eng, pairs, seq_ref, seq_qer, n, CHUNK_EXTEND, false);
+    Job job;
+    job.pairs = pairs; job.seq_ref = seq_ref; job.seq_qer = seq_qer;
+    const int rc = run_sharded(eng, job, n, CHUNK_EXTEND);
     if (rc != BSW_OK) { quiesce(eng); return rc; }
     if (int rc2 = collect_cells(eng)) return rc2;
     eng->stats.ms_total = now_ms() - t_begin;
     return BSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the hot path for a loader that emits the packed layout: 2 bits per base + 16-byte descriptors in,
+// the six result fields out
+// ------------------------------------------------------------------------------------------
+static int extend_packed(bsw_engine* eng, const bsw_packed_batch* b, int32_t w, void* out, bool out16)
+{
+    if (!eng) return BSW_ERR_PARAM;
+    const double t_begin = now_ms();
+    eng->err.clear();
+    eng->staged = false; eng->ran = false;
+    if (!b || b->n_pairs < 0 || w < 0 || (b->n_pairs > 0 && (!b->desc || !out)) ||
+        b->q2_words < 0 || b->r2_words < 0 || b->raw_q_bytes < 0 || b->raw_r_bytes < 0 ||
+        (b->q2_words > 0 && !b->q2) || (b->r2_words > 0 && !b->r2) || (b->raw_q_bytes > 0 && !b->raw_q) ||
+        (b->raw_r_bytes > 0 && !b->raw_r)) {
+        eng->err = "bsw_extend_packed: bad arguments";
+        return BSW_ERR_PARAM;
+    }
+    if (b->n_pairs > 0x7fffffff || b->q2_words > 0xffffffffll || b->r2_words > 0xffffffffll ||
+        b->raw_q_bytes > 0x7fffffffll || b->raw_r_bytes > 0x7fffffffll) {
+        eng->err = "bsw_extend_packed: batch too large (2^31-1 pairs, 2^32-1 words, 2^31-1 RAW bytes per side)";
+        return BSW_ERR_PARAM;
+    }
+    bsw_stats& S = eng->stats;
+    memset(&S, 0, sizeof(S));
+    S.pairs = b->n_pairs;
+    eng->n = b->n_pairs; eng->w = w; eng->kp.w = w;
+    if (b->n_pairs == 0) return BSW_OK;
+    Job job;
+    job.pb = b; job.out = out; job.out16 = out16;
+    const int rc = run_sharded(eng, job, b->n_pairs, CHUNK_EXTEND);
+    if (rc != BSW_OK) {
+        if (rc == BSW_ERR_DOMAIN)
+            eng->err = "bsw_extend_packed: descriptor outside the domain: need 1<=len1,len2<=32767, h0>=1, h0+len2*match<=32767, "
+                       "offsets inside the batch's buffers, and queries the engine routes to the byte-reading kernels "
+                       "(longer than BSW_PACKED_MAX_QLEN or bsw_params.long_min_qlen) stored RAW";
+        quiesce(eng);
+        return rc;
+    }
+    if (int rc2 = collect_cells(eng)) return rc2;
+    eng->stats.ms_total = now_ms() - t_begin;
+    return BSW_OK;
+}
+
+int bsw_extend_packed(bsw_engine* eng, const bsw_packed_batch* batch, int32_t w, OutScore* out)
+{
+    return extend_packed(eng, batch, w, out, false);
+}
+
+int bsw_extend_packed16(bsw_engine* eng, const bsw_packed_batch* batch, int32_t w, bsw_score16* out)
+{
+    return extend_packed(eng, batch, w, out, true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1266,7 +1573,11 @@ int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, con
     if (int rc = begin_batch(eng, pairs, seq_ref, seq_qer, n, w)) return rc;
     eng->staged_chunks.clear();
     if (n > 0) {
-        const int rc = run_pipeline(eng, const_cast<SeqPair*>(pairs), seq_ref, seq_qer, n, CHUNK_STAGE, true);
+        if (int rc = zero_cells(eng)) return rc;
+        Job job;
+        job.pairs = const_cast<SeqPair*>(pairs); job.seq_ref = seq_ref; job.seq_qer = seq_qer;
+        static const int64_t env_stage = getenv("BSW_STAGE_CHUNK") ? atoll(getenv("BSW_STAGE_CHUNK")) : 0;     // experiments
+        const int rc = run_pipeline(eng, job, 0, (int)eng->devs.size(), 0, n, env_stage > 0 ? env_stage : CHUNK_STAGE, true);
         if (rc != BSW_OK) { quiesce(eng); return rc; }
     }
     eng->staged = true;
@@ -1324,7 +1635,9 @@ int bsw_fetch(bsw_engine* eng, SeqPair* pairs, int64_t n)
         CUDA_TRY(cudaSetDevice(c.dev));
         s.direct = pinned_out && s.direct;           // the record DMA needs the chunk's device copy
         if (!s.direct) if (int rc = ensure(eng, s.res, (size_t)s.n, true)) return rc;
-        if (int rc = output_chunk(eng, c, s, pairs)) return rc;
+        Job job;
+        job.pairs = pairs;
+        if (int rc = output_chunk(eng, c, s, job)) return rc;
     }
     for (auto& ds : eng->staged_chunks) {
         DevCtx& c = eng->devs[(size_t)ds.first]; Slot& s = c.slots[(size_t)ds.second];

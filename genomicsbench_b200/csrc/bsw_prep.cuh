@@ -42,6 +42,8 @@ struct ChunkInfo {
     unsigned int qcursor, tcursor;                   // packed words handed out
     int qmax_n;                                      // longest query among the N pairs
     int qmax_all;                                    // longest query of the chunk
+    int n_wide;                                      // packed route: 2-bit pairs outside the 16-bit kernel's score domain
+    int pad_[3];
     unsigned int hist[LEN_HIST];                     // pairs per len2
 };
 static_assert(sizeof(ChunkInfo) % 16 == 0, "bsw_info_publish copies 16-byte words");
@@ -159,6 +161,70 @@ bsw_scan_pairs(const SeqPair* __restrict__ pairs, int n, long long base0_r, long
     }
 }
 
+// Packed route (bsw_extend_packed): the chunk's descriptors arrive in the host format of include/bsw.h
+// (bsw_pair_desc = {q_off, r_off, len2 | len1 << 16, h0 | flags << 16} read as one int4), offsets absolute in the
+// batch's buffers.  Validates them against the word ranges [qlo, qhi) / [rlo, rhi) that were copied for this chunk
+// (RAW pairs: against the byte sizes of the raw buffers, resident as a whole) and builds the same summary as
+// bsw_scan_pairs.  qbases / tbases count 16 bases per packed word (they size the gathered word arrays).
+struct PackedRange {
+    unsigned int qlo, qhi, rlo, rhi;          // words
+    unsigned int rawq, rawr;                  // bytes
+};
+
+__global__ void __launch_bounds__(PREP_BLOCK)
+bsw_scan_packed(const int4* __restrict__ desc, int n, const __grid_constant__ PackedRange R, int match, int short_max,
+                int packed16, ChunkInfo* __restrict__ info)
+{
+    __shared__ unsigned int s_hist[LEN_HIST];
+    for (int k = threadIdx.x; k < LEN_HIST; k += blockDim.x) s_hist[k] = 0;
+    __syncthreads();
+    unsigned long long nominal = 0, qb = 0, tb = 0;
+    int mn0 = 0x7fffffff, mn1 = 0x7fffffff, mn2 = 0x7fffffff, mx0 = 0, mx1 = 0, mx2 = 0, bad = 0, nshort = 0, qall = 0, nwide = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 d = desc[i];
+        const int len2 = d.z & 0xffff, len1 = (d.z >> 16) & 0xffff, h0 = d.w & 0xffff;
+        const bool raw = ((d.w >> 16) & BSW_PAIR_RAW) != 0;
+        const unsigned int qo = (unsigned int)d.x, ro = (unsigned int)d.y;
+        bool ok = len1 >= 1 && len1 <= 32767 && len2 >= 1 && len2 <= 32767 && h0 >= 1 && h0 + len2 * match <= 32767;
+        if (raw) ok = ok && (unsigned long long)qo + len2 <= R.rawq && (unsigned long long)ro + len1 <= R.rawr;
+        else ok = ok && len2 <= short_max && qo >= R.qlo && (unsigned long long)qo + ((len2 + 15) >> 4) <= R.qhi &&
+                  ro >= R.rlo && (unsigned long long)ro + ((len1 + 15) >> 4) <= R.rhi;
+        if (!ok) { bad = 1; continue; }
+        nominal += (unsigned long long)len1 * (unsigned long long)len2;
+        atomicAdd(&s_hist[min(len2, LEN_HIST - 1)], 1u);
+        qall = max(qall, len2);
+        if (!raw) { qb += (unsigned)((len2 + 15) >> 4) * 16u; tb += (unsigned)((len1 + 15) >> 4) * 16u; }
+        if (len2 <= short_max) {
+            ++nshort;
+            mn0 = min(mn0, len2); mx0 = max(mx0, len2);
+            mn1 = min(mn1, h0);   mx1 = max(mx1, h0);
+            mn2 = min(mn2, len1); mx2 = max(mx2, len1);
+            if (!raw && packed16 && !k16::eligible(match, len2, h0)) ++nwide;
+        }
+    }
+    const unsigned FULL = 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nominal += __shfl_xor_sync(FULL, nominal, o); qb += __shfl_xor_sync(FULL, qb, o); tb += __shfl_xor_sync(FULL, tb, o);
+    }
+    mn0 = __reduce_min_sync(FULL, mn0); mn1 = __reduce_min_sync(FULL, mn1); mn2 = __reduce_min_sync(FULL, mn2);
+    mx0 = __reduce_max_sync(FULL, mx0); mx1 = __reduce_max_sync(FULL, mx1); mx2 = __reduce_max_sync(FULL, mx2);
+    bad = __reduce_max_sync(FULL, bad); nshort = __reduce_add_sync(FULL, nshort); qall = __reduce_max_sync(FULL, qall);
+    nwide = __reduce_add_sync(FULL, nwide);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&info->nominal, nominal); atomicAdd(&info->qbases, qb); atomicAdd(&info->tbases, tb);
+        atomicMin(&info->mn[0], mn0); atomicMin(&info->mn[1], mn1); atomicMin(&info->mn[2], mn2);
+        atomicMax(&info->mx[0], mx0); atomicMax(&info->mx[1], mx1); atomicMax(&info->mx[2], mx2);
+        if (bad) atomicAdd(&info->bad, 1);
+        if (nshort) atomicAdd(&info->n_short, nshort);
+        if (nwide) atomicAdd(&info->n_wide, nwide);
+        atomicMax(&info->qmax_all, qall);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < LEN_HIST; k += blockDim.x)
+        if (s_hist[k]) atomicAdd(&info->hist[k], s_hist[k]);
+}
+
 // 16 base codes (one per byte) at any alignment -> one 2-bit word.  *bad collects codes > 3.
 // `room` = bytes of the sequence from src on: the word-wise path may touch up to 3 bytes past its
 // 16 and is only taken when they still belong to the sequence (the buffer may be host memory
@@ -205,11 +271,16 @@ __device__ __forceinline__ uint32_t bsw_pack16(const uint8_t* src, int nb, int r
 // found by binary search), so loads stay coalesced for short and long sequences alike.  The output
 // range is reserved once per block tile (two atomics on the chunk's cursors per block).
 // meta[s] (processing order) gets word offsets; desc[i] (input order) keeps byte offsets.
+// SRC2BIT (packed route): the sources are the chunk's 2-bit words as the host packed them (qraw / rraw point at the
+// chunk's first word, word_lo = that word's offset in the batch); words are copied instead of packed, and RAW pairs
+// (bsw_pair_desc.flags, desc.w >> 16) contribute no words and are listed for the byte kernel like pairs with N.
+template <bool SRC2BIT>
 __global__ void __launch_bounds__(PREP_BLOCK)
 bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm, int n_sorted,
                const uint8_t* __restrict__ qraw, const uint8_t* __restrict__ rraw, int4* __restrict__ meta,
                uint32_t* __restrict__ qpk, uint32_t* __restrict__ tpk,
-               uint32_t* __restrict__ nlist, ChunkInfo* __restrict__ info, int packed16_match, int overread)
+               uint32_t* __restrict__ nlist, ChunkInfo* __restrict__ info, int packed16_match, int overread,
+               unsigned int q_word_lo = 0, unsigned int r_word_lo = 0)
 {
     constexpr int NW = PREP_BLOCK / 32;
     __shared__ uint32_t s_pre[NW][2][33];
@@ -228,8 +299,9 @@ bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm,
             len2 = d.z & 0xffff; len1 = (d.z >> 16) & 0xffff;
         }
         s_desc[wib][lane] = d;
-        const uint32_t nq = (uint32_t)(len2 + 15) >> 4;
-        const uint32_t nt = (uint32_t)(len1 + 15) >> 4;
+        const bool is_raw = SRC2BIT && ((d.w >> 16) & BSW_PAIR_RAW) != 0;
+        const uint32_t nq = is_raw ? 0u : (uint32_t)(len2 + 15) >> 4;
+        const uint32_t nt = is_raw ? 0u : (uint32_t)(len1 + 15) >> 4;
         uint32_t pq = nq, pt = nt;                  // inclusive warp scans
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -263,23 +335,31 @@ bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm,
                 for (int step = 16; step > 0; step >>= 1)
                     if (pre[lo + step] <= wv) lo += step;
                 const int4 dd = s_desc[wib][lo];
-                const int len = kind ? (dd.z >> 16) & 0xffff : dd.z & 0xffff;
                 const uint32_t wi = wv - pre[lo];
-                const uint8_t* src = (kind ? rraw + dd.y : qraw + dd.x) + 16 * (int)wi;
-                uint32_t bad = 0;
-                const int room = len - 16 * (int)wi;
-                const uint32_t word = bsw_pack16(src, min(16, room), room, bad, overread != 0);
-                (kind ? tpk + bt : qpk + bq)[wv] = word;
-                if (bad) atomicOr(&s_bad[wib][lo], 1u);
+                if (SRC2BIT) {
+                    const uint32_t* srcw = kind ? reinterpret_cast<const uint32_t*>(rraw) + ((uint32_t)dd.y - r_word_lo)
+                                                : reinterpret_cast<const uint32_t*>(qraw) + ((uint32_t)dd.x - q_word_lo);
+                    (kind ? tpk + bt : qpk + bq)[wv] = __ldg(srcw + wi);
+                } else {
+                    const int len = kind ? (dd.z >> 16) & 0xffff : dd.z & 0xffff;
+                    const uint8_t* src = (kind ? rraw + dd.y : qraw + dd.x) + 16 * (int)wi;
+                    uint32_t bad = 0;
+                    const int room = len - 16 * (int)wi;
+                    const uint32_t word = bsw_pack16(src, min(16, room), room, bad, overread != 0);
+                    (kind ? tpk + bt : qpk + bq)[wv] = word;
+                    if (bad) atomicOr(&s_bad[wib][lo], 1u);
+                }
             }
         }
         __syncwarp();
         if (s < n_sorted) {
             // pairs for the 32-bit byte kernel: those that contain N and, when the packed 16-bit kernel
             // runs the rest (packed16_match = its match score), those outside its score domain
-            const bool has_n = s_bad[wib][lane] != 0 ||
-                               (packed16_match > 0 && !k16::eligible(packed16_match, len2, d.w & 0xffff));
-            meta[s] = make_int4((int)(bq + pq - nq), (int)(bt + pt - nt), d.z, d.w | (has_n ? BSW_META_NFLAG : 0));
+            // (packed route: a chunk with 2-bit pairs outside that domain runs the 32-bit kernel as a whole)
+            const bool has_n = SRC2BIT ? is_raw
+                                       : s_bad[wib][lane] != 0 ||
+                                         (packed16_match > 0 && !k16::eligible(packed16_match, len2, d.w & 0xffff));
+            meta[s] = make_int4((int)(bq + pq - nq), (int)(bt + pt - nt), d.z, (d.w & 0xffff) | (has_n ? BSW_META_NFLAG : 0));
             if (has_n) { nlist[atomicAdd(&info->n_nlist, 1u)] = (uint32_t)pi; atomicMax(&info->qmax_n, len2); }
         }
         __syncthreads();                            // s_tot / s_base / s_desc are reused by the next tile
@@ -396,16 +476,29 @@ bsw_bucket_scan(uint32_t* __restrict__ bins, int nbins, uint32_t* __restrict__ t
     }
 }
 
+// PACKED (packed route): the sequences stay where the host packed them -- the DP kernels read them in place -- so
+// the scatter also writes the processing-order descriptor meta[pos] = {query word, reference word (relative to the
+// chunk's first word), len2 | len1 << 16, h0}; RAW pairs get BSW_META_NFLAG and are listed for the byte kernel.
+template <bool PACKED>
 __global__ void __launch_bounds__(PREP_BLOCK)
 bsw_bucket_scatter(const int4* __restrict__ desc, int n, const __grid_constant__ BucketKey K,
                    const uint32_t* __restrict__ bins, const uint32_t* __restrict__ totals,
-                   const uint32_t* __restrict__ rank, uint32_t* __restrict__ perm)
+                   const uint32_t* __restrict__ rank, uint32_t* __restrict__ perm,
+                   int4* __restrict__ meta = nullptr, uint32_t* __restrict__ nlist = nullptr,
+                   ChunkInfo* __restrict__ info = nullptr, unsigned int q_word_lo = 0, unsigned int r_word_lo = 0)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int4 d = desc[i];
         if ((d.z & 0xffff) > K.short_max) continue;
         const uint32_t b = bsw_bucket_of(K, d);
-        perm[bins[b] + totals[b / SCAN_TILE] + rank[i]] = (uint32_t)i;
+        const uint32_t pos = bins[b] + totals[b / SCAN_TILE] + rank[i];
+        perm[pos] = (uint32_t)i;
+        if (PACKED) {
+            const bool raw = ((d.w >> 16) & BSW_PAIR_RAW) != 0;
+            meta[pos] = make_int4((int)((uint32_t)d.x - q_word_lo), (int)((uint32_t)d.y - r_word_lo), d.z,
+                                  (d.w & 0xffff) | (raw ? BSW_META_NFLAG : 0));
+            if (raw) { nlist[atomicAdd(&info->n_nlist, 1u)] = (uint32_t)i; atomicMax(&info->qmax_n, d.z & 0xffff); }
+        }
     }
 }
 
@@ -423,6 +516,19 @@ bsw_writeback(const int4* __restrict__ res, int n, SeqPair* __restrict__ pairs)
         out[3] = (int)(short)(v.x >> 16);           // qle
         out[4] = (int)(short)(v.z & 0xffff);        // gscore
         out[5] = (int)(short)(v.z >> 16);           // max_off
+    }
+}
+
+// packed route: res[i] -> OutScore[i] (bandedSWA.h:103-107: score tle gtle qle gscore max_off), 24 bytes per pair
+__global__ void __launch_bounds__(PREP_BLOCK)
+bsw_out_scores(const int4* __restrict__ res, int n, int2* __restrict__ out)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 v = res[i];
+        int2* o = out + 3 * (size_t)i;
+        o[0] = make_int2((int)(short)(v.x & 0xffff), (int)(short)(v.y & 0xffff));     // score, tle
+        o[1] = make_int2((int)(short)(v.y >> 16), (int)(short)(v.x >> 16));           // gtle, qle
+        o[2] = make_int2((int)(short)(v.z & 0xffff), (int)(short)(v.z >> 16));        // gscore, max_off
     }
 }
 

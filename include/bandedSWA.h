@@ -51,10 +51,7 @@
 #define max_(x, y) ((x)>(y)?(x):(y))
 #endif
 
-typedef struct dnaOutScore {
-    int32_t score, tle, gtle, qle;
-    int32_t gscore, max_off;
-} OutScore;
+/* OutScore (bandedSWA.h:103-107) comes with bsw.h: bsw_extend_packed returns it */
 
 typedef struct {
     int32_t h, e;

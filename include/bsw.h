@@ -119,6 +119,75 @@ void        bsw_default_params(bsw_params* p);       /* bwa defaults: main_bande
 int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref,
                const uint8_t* seq_qer, int64_t n_pairs, int32_t w);
 
+/* ---- the packed host format ---------------------------------------------------
+ * The reference keeps file parsing outside its timed region (main_banded.cpp:262-270 loadPairs, :306 readTim) and
+ * layout conversion inside it (the AoS->SoA transposes of bandedSWA.cpp:1266-1326).  A loader that emits THIS layout
+ * instead of SeqPair[] + one byte per base lets the engine DMA 2 bits per base and 16 bytes per descriptor
+ * (~50 B/pair for 16-96 bp reads instead of 194) and return 24 bytes per pair (OutScore, the reference's own result
+ * type, bandedSWA.h:103-107) instead of the whole 72-byte record.
+ *   packed pair   bases 0-3, 16 per 32-bit word, base k of a sequence at bits [2k, 2k+2) of word k/16, every
+ *                 sequence starts on a word; q_off / r_off = first word in q2 / r2
+ *   RAW pair      (BSW_PAIR_RAW) one base code per byte (0-3, 4 = N) in raw_q / raw_r, q_off / r_off = first byte;
+ *                 the builders use it for pairs that contain N and for queries longer than
+ *                 BSW_PACKED_MAX_QLEN (the thread-per-pair kernel's limit)
+ * `ordered` = 1 promises that offsets never decrease with the pair index (in q2, r2, and among the RAW pairs in
+ * raw_q, raw_r) -- what the builders below emit; the engine then streams the buffers chunk by chunk.  Otherwise
+ * all four buffers are copied before the first chunk runs. */
+#define BSW_PACKED_MAX_QLEN 824
+enum { BSW_PAIR_RAW = 1 };
+typedef struct bsw_pair_desc {        /* 16 bytes */
+    uint32_t q_off, r_off;
+    uint16_t len2, len1;              /* query / reference (target) length, 1..32767     */
+    uint16_t h0;                      /* seed score, >= 1                                 */
+    uint16_t flags;                   /* BSW_PAIR_RAW                                     */
+} bsw_pair_desc;
+typedef struct bsw_packed_batch {
+    int64_t n_pairs;
+    bsw_pair_desc* desc;
+    uint32_t* q2; int64_t q2_words;
+    uint32_t* r2; int64_t r2_words;
+    uint8_t* raw_q; int64_t raw_q_bytes;
+    uint8_t* raw_r; int64_t raw_r_bytes;
+    int32_t ordered;
+    int32_t reserved[3];
+} bsw_packed_batch;
+#ifndef BSW_OUTSCORE_DEFINED
+#define BSW_OUTSCORE_DEFINED
+typedef struct dnaOutScore {          /* bandedSWA.h:103-107 */
+    int32_t score, tle, gtle, qle;
+    int32_t gscore, max_off;
+} OutScore;
+#endif
+typedef struct bsw_score16 {          /* the same six values in 16 bytes (all fit int16: bandedSWA.h:84) */
+    int16_t score, qle, tle, gtle, gscore, max_off, reserved[2];
+} bsw_score16;
+
+/* Builders (host only; no CUDA call).  alloc / release = the allocator of the batch's five buffers: pass
+ * bsw_host_alloc / bsw_host_free for page-locked memory (what the engine DMAs without staging), NULL / NULL for
+ * malloc / free.  raw_min_qlen: queries of at least this length are stored RAW (0 = BSW_PACKED_MAX_QLEN + 1).
+ *   bsw_batch_from_pairs   from the reference's layout (SeqPair[] + byte buffers): the packing loader
+ *   bsw_batch_from_file    from the 3-line text format of main_banded.cpp:131-185
+ *   bsw_batch_gen          the synthetic generator of SURVEY 8(d), straight into the packed layout
+ *   bsw_batch_to_pairs     the inverse (tests, tools): pairs[] with idr / idq laid out consecutively, bytes in
+ *                          ref / qer (capacities in bytes; BSW_ERR_NOMEM if too small)
+ *   bsw_batch_release      frees the five buffers with `release` (NULL = free) and clears the struct */
+typedef void* (*bsw_alloc_fn)(size_t bytes);
+typedef void  (*bsw_release_fn)(void* p);
+int  bsw_batch_from_pairs(const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer, int64_t n_pairs,
+                          int32_t raw_min_qlen, bsw_alloc_fn alloc, bsw_release_fn release, bsw_packed_batch* out);
+int  bsw_batch_from_file(const char* path, int64_t max_pairs, int32_t raw_min_qlen, bsw_alloc_fn alloc,
+                         bsw_release_fn release, bsw_packed_batch* out);
+int  bsw_batch_to_pairs(const bsw_packed_batch* batch, SeqPair* pairs, uint8_t* seq_ref, int64_t ref_cap,
+                        uint8_t* seq_qer, int64_t qer_cap);
+void bsw_batch_release(bsw_packed_batch* batch, bsw_release_fn release);
+
+/* replaces: getScores16 (bandedSWA.cpp:1124-1148) for a loader that emits the packed layout.  out[i] receives the
+ * six result fields of pair i (input order).  Same kernels, same results as bsw_extend on the unpacked pairs.
+ * Page-locked batch buffers and out (bsw_host_alloc) are DMA'd in place; pageable ones work, slower.
+ * bsw_extend_packed16: the same call returning 16 bytes per pair. */
+int bsw_extend_packed(bsw_engine* eng, const bsw_packed_batch* batch, int32_t w, OutScore* out);
+int bsw_extend_packed16(bsw_engine* eng, const bsw_packed_batch* batch, int32_t w, bsw_score16* out);
+
 /* ---- (f.1) band-doubling retry of the aligner ------------------------------
  * replaces: the MAX_BAND_TRY loops around ksw_extend2 in mem_chain2aln,
  * tools/bwa/bwamem.c:630,723-753 (left extension) and :770-800 (right extension):
@@ -256,6 +325,10 @@ int     bsw_gen_bounds(const bsw_gen_config* cfg, int64_t* ref_bytes, int64_t* q
 int     bsw_gen_pairs(const bsw_gen_config* cfg, int64_t first_pair, int64_t n,
                       SeqPair* pairs, uint8_t* seq_ref, uint8_t* seq_qer,
                       int64_t* ref_used, int64_t* qer_used);
+
+/* The same stream, straight into the packed layout (see bsw_batch_from_pairs for alloc / release). */
+int     bsw_batch_gen(const bsw_gen_config* cfg, int64_t first_pair, int64_t n, int32_t raw_min_qlen,
+                      bsw_alloc_fn alloc, bsw_release_fn release, bsw_packed_batch* out);
 
 /* ---- dataset I/O: the 3-line text format of main_banded.cpp:131-185 --------- */
 int64_t bsw_count_pairs_file(const char* path);

@@ -79,8 +79,8 @@ def test_header_compiles_as_c_and_layouts_match_the_mirrors(lib, tmp_path):
     sizes / offsets the C compiler sees with the numpy and ctypes mirrors the tests and the Python class use."""
     import shutil
     import subprocess
-    from genomicsbench_b200._lib import (ALNREG_DTYPE, CHAIN_DTYPE, SEED_DTYPE, BswChainOpt, BswGenConfig, BswParams,
-                                         BswStats)
+    from genomicsbench_b200._lib import (ALNREG_DTYPE, CHAIN_DTYPE, OUTSCORE_DTYPE, PAIR_DESC_DTYPE, SCORE16_DTYPE, SEED_DTYPE,
+                                         BswChainOpt, BswGenConfig, BswPackedBatch, BswParams, BswStats)
     cc = shutil.which("gcc") or shutil.which("cc")
     if not cc:
         pytest.skip("no C compiler")
@@ -98,6 +98,9 @@ int main(void) {
     S(bsw_chain); O(bsw_chain, l_query); O(bsw_chain, rmax0); O(bsw_chain, ref_off); O(bsw_chain, same_read);
     S(bsw_alnreg); O(bsw_alnreg, qb); O(bsw_alnreg, truesc); O(bsw_alnreg, seedlen0);
     S(bsw_chain_opt);
+    S(bsw_pair_desc); O(bsw_pair_desc, len2); O(bsw_pair_desc, h0); O(bsw_pair_desc, flags);
+    S(bsw_packed_batch); O(bsw_packed_batch, q2_words); O(bsw_packed_batch, raw_r_bytes); O(bsw_packed_batch, ordered);
+    S(OutScore); O(OutScore, qle); S(bsw_score16); O(bsw_score16, max_off);
     return 0;
 }
 ''')
@@ -113,7 +116,12 @@ int main(void) {
     assert got["bsw_stats.kernel_launches"] == BswStats.kernel_launches.offset
     assert got["bsw_stats.partitioned"] == BswStats.partitioned.offset
     assert got["bsw_gen_config"] == C.sizeof(BswGenConfig) and got["bsw_chain_opt"] == C.sizeof(BswChainOpt)
-    for name, dt, fields in (("bsw_seed", SEED_DTYPE, ("qbeg", "score")),
+    assert got["bsw_packed_batch"] == C.sizeof(BswPackedBatch)
+    for f in ("q2_words", "raw_r_bytes", "ordered"):
+        assert got[f"bsw_packed_batch.{f}"] == getattr(BswPackedBatch, f).offset
+    for name, dt, fields in (("bsw_pair_desc", PAIR_DESC_DTYPE, ("len2", "h0", "flags")), ("OutScore", OUTSCORE_DTYPE, ("qle",)),
+                             ("bsw_score16", SCORE16_DTYPE, ("max_off",)),
+                             ("bsw_seed", SEED_DTYPE, ("qbeg", "score")),
                              ("bsw_chain", CHAIN_DTYPE, ("l_query", "rmax0", "ref_off", "same_read")),
                              ("bsw_alnreg", ALNREG_DTYPE, ("qb", "truesc", "seedlen0"))):
         assert got[name] == dt.itemsize, name

@@ -136,3 +136,30 @@ def test_extend_chains_vector_zdrop_equals_scalar_for_unit_extension(lib):
         # empty batch
         r, n = eng.extend_chains(chains[:0], seeds[:0], query, ref, c["w"], c["clip5"], c["clip3"], 2)
         assert len(r) == 0 and len(n) == 0
+
+
+@pytest.mark.gpu
+def test_extend_chains_result_independent_of_batch_composition(lib):
+    """Every multi-chain read of chain_multi submitted ALONE gives the golden regions: a chain that waits for
+    its read's earlier chains must still run when those only skip contained seeds and no other read of the
+    batch keeps the round loop alive (mem_chain2aln always processes every chain, bwamem.c:1105-1112)."""
+    c = load_chain_case("chain_multi")
+    read = c["chain_read"]
+    reg_first = np.concatenate([[0], np.cumsum(c["reg_n"])])
+    with lib.Engine(end_bonus=c["clip5"], zdrop_mode=lib.BSW_ZDROP_SCALAR, **c["P"]) as eng:
+        chains, seeds, query, ref = _build_batch(lib, eng, c)
+        starts = [k for k in range(len(read)) if k == 0 or read[k] != read[k - 1]]
+        n_multi = 0
+        for gi, k0 in enumerate(starts):
+            k1 = starts[gi + 1] if gi + 1 < len(starts) else len(read)
+            if k1 - k0 < 2:
+                continue
+            n_multi += 1
+            regs, count = eng.extend_chains(chains[k0:k1], seeds, query, ref, c["w"], c["clip5"], c["clip3"], 2)
+            assert np.array_equal(count, c["reg_n"][k0:k1]), f"read {read[k0]}: counts {count} want {c['reg_n'][k0:k1]}"
+            for j, k in enumerate(range(k0, k1)):
+                first = int(chains[k]["seed_first"])
+                got = regs[first: first + int(count[j])]
+                gm = np.stack([got[f] for f in lib.ALNREG_FIELDS], axis=1).astype(np.int64).reshape(-1, len(lib.ALNREG_FIELDS))
+                assert np.array_equal(gm, c["regs"][reg_first[k]: reg_first[k + 1]]), f"read {read[k0]} chain {k}"
+        assert n_multi > 100
