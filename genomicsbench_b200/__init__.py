@@ -24,7 +24,7 @@ from ._lib import (ABI, ALNREG_DTYPE, ALNREG_FIELDS, BSW_PACKED_MAX_QLEN, BSW_PA
 
 __all__ = [
     "BandedPairWiseSW", "Engine", "BswError", "SEQPAIR_DTYPE", "RESULT_FIELDS", "default_params",
-    "gen_named_config", "gen_pairs", "bucket_order", "partition", "read_pairs_file",
+    "gen_named_config", "gen_pairs", "bucket_order", "partition", "split_by_cost", "read_pairs_file",
     "write_pairs_file", "load_library", "NAMED_CONFIGS", "pinned_empty", "pinned_copy",
     "SEED_DTYPE", "CHAIN_DTYPE", "ALNREG_DTYPE", "ALNREG_FIELDS", "PackedBatch", "PAIR_DESC_DTYPE", "OUTSCORE_DTYPE",
     "SCORE16_DTYPE", "BSW_PAIR_RAW", "BSW_PACKED_MAX_QLEN", "load_host_library",
@@ -423,6 +423,17 @@ def partition(pairs: np.ndarray, w: int, n_shards: int):
     if rc:
         raise BswError(rc, "partition")
     return order, begin
+
+
+def split_by_cost(pairs: np.ndarray, w: int, n_shards: int) -> np.ndarray:
+    """Contiguous cut of the input order into n_shards ranges of equal estimated DP cost (bsw_split_by_cost)."""
+    if pairs.dtype != SEQPAIR_DTYPE or not pairs.flags.c_contiguous:
+        raise TypeError("pairs must be a C-contiguous array of SEQPAIR_DTYPE")
+    begin = np.zeros(n_shards + 1, dtype=np.int64)
+    rc = load_library().bsw_split_by_cost(ptr(pairs), len(pairs), w, n_shards, ptr(begin))
+    if rc:
+        raise BswError(rc, "split_by_cost")
+    return begin
 
 
 def read_pairs_file(path: str, max_pairs: Optional[int] = None):

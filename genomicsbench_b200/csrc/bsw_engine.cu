@@ -1229,8 +1229,10 @@ int run_sharded(bsw_engine* eng, const Job& job, int64_t n, int64_t chunk_pairs)
     const int ndev = (int)eng->devs.size();
     if (int rc = zero_cells(eng)) return rc;
     static const bool deal = getenv("BSW_MULTI") && std::string(getenv("BSW_MULTI")) == "deal";
+    eng->stats.shards = 1;
     if (ndev == 1 || deal) return run_pipeline(eng, job, 0, ndev, 0, n, chunk_pairs, false);
     if (n < (int64_t)ndev * CHUNK_MIN) return run_pipeline(eng, job, 0, 1, 0, n, chunk_pairs, false);   // too small to split
+    eng->stats.shards = ndev;
     // cost curve from a sample (every step-th pair), cut at equal cost
     const int64_t step = std::max<int64_t>(1, n / 8192);
     const int64_t ns = (n + step - 1) / step;

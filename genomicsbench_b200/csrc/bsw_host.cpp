@@ -168,6 +168,25 @@ int bsw_bucket_order(const SeqPair* pairs, int64_t n, int64_t* order)
     return BSW_OK;
 }
 
+// Contiguous cost-balanced cut of the input order (exact: every record is read; the engine's own cut inside
+// bsw_extend reads a sample).  shard_begin has n_shards + 1 entries.
+int bsw_split_by_cost(const SeqPair* pairs, int64_t n, int32_t w, int32_t n_shards, int64_t* shard_begin)
+{
+    if (n < 0 || n_shards < 1 || !shard_begin || w < 0 || (n > 0 && !pairs)) return BSW_ERR_PARAM;
+    std::vector<int64_t> cum((size_t)n + 1, 0);
+    for (int64_t k = 0; k < n; ++k) {
+        if (pairs[k].len1 < 1 || pairs[k].len2 < 1 || pairs[k].len1 > 32767 || pairs[k].len2 > 32767) return BSW_ERR_DOMAIN;
+        cum[(size_t)k + 1] = cum[(size_t)k] + pair_cost(pairs[k].len1, pairs[k].len2, w);
+    }
+    shard_begin[0] = 0; shard_begin[n_shards] = n;
+    for (int g = 1; g < n_shards; ++g) {
+        const int64_t target = cum[(size_t)n] / n_shards * g;
+        const int64_t k = std::lower_bound(cum.begin(), cum.end(), target) - cum.begin();
+        shard_begin[g] = std::max(shard_begin[g - 1], std::min(n, k));
+    }
+    return BSW_OK;
+}
+
 int bsw_partition(const SeqPair* pairs, int64_t n, int32_t w, int32_t n_shards,
                   int64_t* order, int64_t* shard_begin)
 {

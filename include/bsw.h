@@ -99,7 +99,8 @@ typedef struct bsw_stats {
     int32_t kernel_launches;     /* kernels launched by the last call (prep + DP + write-back) */
     int32_t n_short, n_long;     /* pairs routed to the thread-per-pair / warp-per-pair kernel */
     int32_t partitioned;         /* 1: the call ran with the SMs split into a service and a DP partition (PCIe-bound batch) */
-    int32_t reserved[4];
+    int32_t shards;              /* device ranges the call was cut into (multi-GPU partitioner): 1, or the engine's device count */
+    int32_t reserved[3];
 } bsw_stats;
 
 typedef struct bsw_engine bsw_engine;
@@ -291,9 +292,15 @@ int bsw_get_stats(const bsw_engine* eng, bsw_stats* out);
 
 /* ---- a6 / (e): length bucketing and the multi-GPU partitioner --------------
  * replaces: sortPairsLen / sortPairsId (bandedSWA.cpp:368-420) and the OpenMP
- * batch loop (main_banded.cpp:279-291).  order[] receives the processing order
- * (indices into pairs[]), sorted by (len2, len1, h0); shard_begin[0..n_shards]
- * receives cut points into order[] that balance sum len1*min(len2, 2w+1). */
+ * batch loop (main_banded.cpp:279-291).
+ * Inside bsw_extend / bsw_extend_packed an engine with several devices cuts the call's pairs, in input order, into one
+ * contiguous range per device with equal estimated DP cost sum len1*min(len2, 2w+1) (bsw_split_by_cost is that cut,
+ * exposed for callers that shard across processes), runs every range on its own host thread through its device's
+ * chunk pipeline (length bucketing per chunk, on the device), and every result lands at its pair's input position.
+ * bsw_bucket_order / bsw_partition are the host-side utilities for callers that want the global processing order:
+ * order[] receives indices into pairs[] sorted by (len2, h0, len1); shard_begin[0..n_shards] receives cut points
+ * into order[] that balance the same cost. */
+int bsw_split_by_cost(const SeqPair* pairs, int64_t n_pairs, int32_t w, int32_t n_shards, int64_t* shard_begin);
 int bsw_bucket_order(const SeqPair* pairs, int64_t n_pairs, int64_t* order);
 int bsw_partition(const SeqPair* pairs, int64_t n_pairs, int32_t w, int32_t n_shards,
                   int64_t* order, int64_t* shard_begin);

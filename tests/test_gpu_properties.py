@@ -215,9 +215,10 @@ def test_sparse_sequence_buffers_are_read_in_place(lib, oracle):
 
 @pytest.mark.parametrize("devices", [[0, 0], [0, 1], [0, 1, 0]])
 def test_engine_deals_chunks_over_its_devices(lib, devices):
-    """One engine driving several devices (bsw_params.devices): chunks are dealt round-robin, every
-    chunk is bucketed and computed on its own device, results land in input order.  [0, 0] runs
-    the multi-device plumbing on a single GPU; [0, 1] needs two."""
+    """One engine driving several devices (bsw_params.devices): the call is cut into one contiguous cost-balanced
+    range per device, every range runs on its own host thread through its device's chunk pipeline, results land
+    in input order (bsw_stage still deals chunks round-robin).  [0, 0] runs the multi-device plumbing -- two device
+    contexts, two host threads -- on a single GPU; [0, 1] needs two."""
     import torch
     if max(devices) >= torch.cuda.device_count():
         pytest.skip("needs more GPUs")
@@ -232,9 +233,64 @@ def test_engine_deals_chunks_over_its_devices(lib, devices):
         eng.extend(b, ref, qer, 100)                                 # staged route
         assert np.array_equal(results_matrix(b), results_matrix(a))
         assert eng.stats()["cells_effective"] == cells
+        assert eng.stats()["shards"] == len(devices)
         pp, pr, pq = lib.pinned_copy(pairs), lib.pinned_copy(ref), lib.pinned_copy(qer)
         eng.extend(pp, pr, pq, 100)                                  # direct route
         assert np.array_equal(results_matrix(pp), results_matrix(a))
         c = pairs.copy()
         eng.stage(c, ref, qer, 100); eng.run_staged(); eng.fetch(c)
         assert np.array_equal(results_matrix(c), results_matrix(a))
+
+
+@pytest.mark.parametrize("devices", [[0, 0], [0, 1], [0, 1, 2, 3]])
+def test_partitioner_on_the_hot_path(lib, devices):
+    """The in-call multi-GPU partitioner (replaces main_banded.cpp:279-291) on a batch whose cost is NOT uniform in
+    input order -- short pairs first, long pairs last: the cut balances sum len1*min(len2, 2w+1), not the pair count;
+    all three routes (pageable, page-locked, packed) return the single-device results in input order, and a batch
+    too small to split runs on one device."""
+    import torch
+    if max(devices) >= torch.cuda.device_count():
+        pytest.skip("needs more GPUs")
+    ca, cb = lib.gen_named_config("short8"), lib.gen_named_config("long16")
+    pa, ra, qa = lib.gen_pairs(ca, 0, 600_000)
+    pb, rb, qb = lib.gen_pairs(cb, 0, 150_000)
+    pb["idr"] += len(ra); pb["idq"] += len(qa)
+    pairs = np.zeros(len(pa) + len(pb), dtype=lib.SEQPAIR_DTYPE)     # (np.concatenate would drop the record's padding)
+    pairs[:len(pa)] = pa; pairs[len(pa):] = pb
+    ref = np.concatenate([ra, rb]); qer = np.concatenate([qa, qb])
+    pairs["id"] = np.arange(len(pairs))
+    g = len(devices)
+    cut = lib.split_by_cost(pairs, 100, g)
+    assert cut[0] == 0 and cut[-1] == len(pairs) and np.all(np.diff(cut) > 0)
+    cost = pairs["len1"].astype(np.int64) * np.minimum(pairs["len2"], 201) + 64
+    shares = np.add.reduceat(cost, cut[:-1]) / cost.sum()
+    assert np.all(np.abs(shares - 1.0 / g) < 0.02), shares
+    assert cut[1] > len(pairs) // g                                  # more (cheap) pairs in the first range than an equal count
+    with lib.Engine() as one:
+        a = pairs.copy()
+        one.extend(a, ref, qer, 100)
+        cells = one.stats()["cells_effective"]
+    with lib.Engine(devices=devices) as eng:
+        b = pairs.copy()
+        eng.extend(b, ref, qer, 100)
+        st = eng.stats()
+        assert np.array_equal(results_matrix(b), results_matrix(a))
+        assert st["cells_effective"] == cells and st["shards"] == g
+        pp, pr, pq = lib.pinned_copy(pairs), lib.pinned_copy(ref), lib.pinned_copy(qer)
+        eng.extend(pp, pr, pq, 100)
+        assert np.array_equal(results_matrix(pp), results_matrix(a)) and eng.stats()["shards"] == g
+        batch = lib.PackedBatch.from_pairs(pairs, ref, qer, pinned=True)
+        out = eng.extend_packed(batch, 100)
+        assert eng.stats()["shards"] == g and eng.stats()["cells_effective"] == cells
+        for f in lib.RESULT_FIELDS:
+            assert np.array_equal(out[f], a[f]), f
+        small = pairs[:3000].copy()
+        eng.extend(small, ref, qer, 100)
+        assert eng.stats()["shards"] == 1 and np.array_equal(results_matrix(small), results_matrix(a[:3000]))
+        bad = pairs.copy()
+        bad["len2"][700_000] = 0                                     # a domain error inside one device's range fails the call
+        with pytest.raises(lib.BswError) as ei:
+            eng.extend(bad, ref, qer, 100)
+        assert ei.value.code == -2
+        eng.extend(b, ref, qer, 100)                                 # and the engine keeps working
+        assert np.array_equal(results_matrix(b), results_matrix(a))
