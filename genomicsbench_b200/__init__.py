@@ -95,6 +95,24 @@ class Engine:
         _check_arrays(pairs, seq_ref, seq_qer)
         self._rc(self._lib.bsw_extend(self._h, ptr(pairs), ptr(seq_ref), ptr(seq_qer), len(pairs), w))
 
+    def extend_async(self, pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray, w: int) -> int:
+        """bsw_extend_async: queues the call, returns its ticket (the arrays must stay alive until wait())."""
+        _check_arrays(pairs, seq_ref, seq_qer)
+        t = C.c_int64(0)
+        self._rc(self._lib.bsw_extend_async(self._h, ptr(pairs), ptr(seq_ref), ptr(seq_qer), len(pairs), w, C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket: int) -> int:
+        """bsw_wait: blocks until the ticket's results are in its records; returns the call's share of effective cells."""
+        cells = C.c_int64(0)
+        self._rc(self._lib.bsw_wait(self._h, ticket, C.byref(cells)))
+        return int(cells.value)
+
+    def async_stats(self) -> tuple:
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._rc(self._lib.bsw_async_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def extend_retry(self, pairs: np.ndarray, seq_ref: np.ndarray, seq_qer: np.ndarray, w: int,
                      max_try: int = 2, prev_score: Optional[np.ndarray] = None) -> np.ndarray:
         """Band-doubling retry of the aligner (tools/bwa/bwamem.c:630,723-753,770-800; MAX_BAND_TRY = 2).

@@ -30,6 +30,8 @@
 #include <memory>
 #include <deque>
 #include <climits>
+#include <thread>
+#include <condition_variable>
 #include <type_traits>
 #include <cuda.h>                         // types only: the driver entry points are fetched through the runtime
 
@@ -191,6 +193,8 @@ struct bsw_engine {
     void* gbufs = nullptr;                // device buffers of bsw_global (GlobalBufs, bsw_global.inl)
     bool global_attr_set = false;
     void* cbufs = nullptr;                // page-locked staging of bsw_extend_chains (ChainBufs, bsw_chain.inl)
+    void* aq = nullptr;                   // queue + worker of bsw_extend_async (AsyncQueue, bsw_async.inl)
+    std::once_flag aq_once;
 };
 
 namespace {
@@ -741,13 +745,29 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
     {
         BucketKey K;
         K.mn2 = I.n_short ? I.mn[0] : 0; K.mnh = I.n_short ? I.mn[1] : 0; K.mn1 = I.n_short ? I.mn[2] : 0;
-        const int b_l2 = I.n_short ? bits_for((uint32_t)(I.mx[0] - I.mn[0])) : 0;
-        K.b_h0 = I.n_short ? bits_for((uint32_t)(I.mx[1] - I.mn[1])) : 0;
-        K.b_l1 = I.n_short ? bits_for((uint32_t)(I.mx[2] - I.mn[2])) : 0;
+        const int b_l2 = I.n_short ? bits_for((uint32_t)(I.mx[0] - I.mn[0])) : 0;        // <= 10: never shortened
+        const int w_h0 = I.n_short ? bits_for((uint32_t)(I.mx[1] - I.mn[1])) : 0;
+        const int w_l1 = I.n_short ? bits_for((uint32_t)(I.mx[2] - I.mn[2])) : 0;
+        // key = len2 | h0 | len1 cut to the bin table's BUCKET_BITS.  BSW_KEY_MODE (experiments): 0 = drop the low bits
+        // of the last field only (h0 exact, len1 coarse), 1 = len2 | len1 | h0 the same way, 2 = len2 | len1 | h0 with
+        // the dropped bits shared between both fields
+        // (measured, r02j_keymode.log: the orders differ by <= 2 %; 2 is never behind: short8 2.205 -> 2.167 ms, sweep w = 500 22.00 -> 21.58 ms)
+        static const int key_mode = getenv("BSW_KEY_MODE") ? atoi(getenv("BSW_KEY_MODE")) : 2;
+        const int room = std::max(0, BUCKET_BITS - b_l2);
+        K.l1_first = key_mode != 0;
+        if (key_mode == 2) {
+            int k_l1 = std::min(w_l1, (room * 3 + 4) / 5), k_h0 = std::min(w_h0, room - k_l1);
+            k_l1 = std::min(w_l1, room - k_h0);
+            K.b_l1 = k_l1; K.b_h0 = k_h0;
+        } else if (key_mode == 1) {
+            K.b_l1 = std::min(w_l1, room); K.b_h0 = std::min(w_h0, room - K.b_l1);
+        } else {
+            K.b_h0 = std::min(w_h0, room); K.b_l1 = std::min(w_l1, room - K.b_h0);
+        }
+        K.s_h0 = w_h0 - K.b_h0; K.s_l1 = w_l1 - K.b_l1;
         const int total = b_l2 + K.b_h0 + K.b_l1;
-        K.drop = std::max(0, total - BUCKET_BITS);          // only ever eats h0 / len1 bits: b_l2 <= 10
         K.short_max = s.tiny ? 0 : eng->short_max;
-        const int nbins = 1 << (total - K.drop);
+        const int nbins = 1 << total;
         const int ntiles = (nbins + SCAN_TILE - 1) / SCAN_TILE;           // <= 256
         const size_t nb_pad = (size_t)ntiles * SCAN_TILE;                  // whole tiles, so the scan needs no edge cases
         if (int rc = ensure(eng, s.bins, BINS_WORDS)) return rc;            // bins, tile totals, ticket counter
@@ -1338,7 +1358,10 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
     // H2D stream): with the default of 8 connections, streams share queues and a prep kernel of one
     // chunk waits behind another chunk's result copy.  Only effective if this is the process's
     // first CUDA call; a caller that initialises CUDA earlier exports the variable itself.
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    // (set once per process: engines may be created from concurrent threads -- the C++ class creates its engine
+    // lazily inside the driver's OpenMP region -- and setenv is not thread-safe)
+    static std::once_flag env_once;
+    std::call_once(env_once, [] { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); });
     int ndev_avail = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev_avail);
     if (ce != cudaSuccess || ndev_avail < 1)
@@ -1362,7 +1385,7 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
     if (params->n_devices == 0) { int cur = 0; cudaGetDevice(&cur); ids.push_back(cur); }
     else for (int i = 0; i < params->n_devices; ++i) ids.push_back(params->devices[i]);
     for (int id : ids)
-        if (id < 0 || id >= ndev_avail) { delete eng; return fail(BSW_ERR_PARAM, "device ordinal out of range"); }
+        if (id < 0 || id >= ndev_avail) { bsw_destroy(eng); return fail(BSW_ERR_PARAM, "device ordinal out of range"); }
     eng->devs.resize(ids.size());
     for (size_t i = 0; i < ids.size(); ++i) {
         DevCtx& c = eng->devs[i];
@@ -1371,7 +1394,7 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
         cudaDeviceProp prop{};
         ok = ok && cudaGetDeviceProperties(&prop, c.dev) == cudaSuccess;
         if (ok && prop.major != 10) {
-            delete eng;
+            bsw_destroy(eng);                                  // releases the streams / events of the devices set up so far
             return fail(BSW_ERR_CUDA, std::string("device ") + prop.name +
                                       " is not sm_100: this library carries sm_100a code only");
         }
@@ -1405,10 +1428,12 @@ bsw_engine* bsw_create(const bsw_params* params, int* err)
 
 static void bsw_global_release(bsw_engine* eng);      // bsw_global.inl
 static void bsw_chain_release(bsw_engine* eng);       // bsw_chain.inl
+static void bsw_async_release(bsw_engine* eng);       // bsw_async.inl
 
 void bsw_destroy(bsw_engine* eng)
 {
     if (!eng) return;
+    bsw_async_release(eng);
     bsw_global_release(eng);
     bsw_chain_release(eng);
     for (DevCtx& c : eng->devs) {
@@ -1562,6 +1587,7 @@ int bsw_extend_retry(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, co
 
 #include "bsw_chain.inl"
 #include "bsw_global.inl"
+#include "bsw_async.inl"
 
 // ------------------------------------------------------------------------------------------
 // resident form: stage (host -> HBM, packed + bucketed), run (DP kernels only, repeatable),

@@ -369,16 +369,18 @@ bsw_pack_pairs(const int4* __restrict__ desc, const uint32_t* __restrict__ perm,
 // ---- bucketing: counting sort by the compressed key (len2 | h0 | len1) >> drop --------------
 struct BucketKey {
     int mn2, mnh, mn1;        // minima of len2, h0, len1
-    int b_h0, b_l1;           // bit widths of the h0 and len1 fields
-    int drop;                 // low bits dropped so that the key fits the bin table
+    int b_h0, b_l1;           // bit widths of the h0 and len1 fields (after their shifts)
+    int s_h0, s_l1;           // low bits dropped from h0 - mnh / len1 - mn1 so that the key fits the bin table
+    int l1_first;             // field order below len2: 1 = len1 then h0, 0 = h0 then len1
     int short_max;
 };
 
 __device__ __forceinline__ uint32_t bsw_bucket_of(const BucketKey& K, const int4 d)
 {
     const uint32_t len2 = d.z & 0xffff, len1 = (d.z >> 16) & 0xffff, h0 = d.w & 0xffff;
-    const uint32_t key = ((len2 - K.mn2) << (K.b_h0 + K.b_l1)) | ((h0 - K.mnh) << K.b_l1) | (len1 - K.mn1);
-    return key >> K.drop;
+    const uint32_t a = (h0 - K.mnh) >> K.s_h0, b = (len1 - K.mn1) >> K.s_l1;
+    const uint32_t low = K.l1_first ? (b << K.b_h0) | a : (a << K.b_l1) | b;
+    return ((len2 - K.mn2) << (K.b_h0 + K.b_l1)) | low;
 }
 
 // rank[i] = arrival order of pair i inside its bin; bins[] accumulates the bin sizes; pairs whose

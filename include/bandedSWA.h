@@ -16,6 +16,8 @@
  *     (reference: bandedSWA.cpp:1171-1177, :414);
  *   - getScores8 and getScores16 route to the same engine (kernel choice is by query
  *     length, not by score width) and return identical results inside the 8-bit envelope;
+ *   - BSW_SHIM_COALESCE=<pairs> in the environment coalesces calls of at most that many pairs from all instances
+ *     and threads into shared batches (bsw_extend_async; off by default, see csrc/bsw_shim.cpp);
  *   - there is no CPU path: every method runs on the GPU and aborts, like the reference's
  *     exit(EXIT_FAILURE) (bandedSWA.cpp:94-99), if the device or the library fails.
  */
@@ -108,6 +110,7 @@ private:
     BandedPairWiseSW(const BandedPairWiseSW&);
     BandedPairWiseSW& operator=(const BandedPairWiseSW&);
     bsw_engine* engine(int zdrop_mode);
+    bsw_params checked_params(int zdrop_mode);
     void run(int zdrop_mode, SeqPair*, const uint8_t*, const uint8_t*, int64_t, int32_t);
 
     bsw_params params_;

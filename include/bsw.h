@@ -189,6 +189,20 @@ void bsw_batch_release(bsw_packed_batch* batch, bsw_release_fn release);
 int bsw_extend_packed(bsw_engine* eng, const bsw_packed_batch* batch, int32_t w, OutScore* out);
 int bsw_extend_packed16(bsw_engine* eng, const bsw_packed_batch* batch, int32_t w, bsw_score16* out);
 
+/* ---- asynchronous submit + call coalescing -----------------------
+ * replaces: the OpenMP loop of 512-pair getScores16 calls, main_banded.cpp:279-291 with scripts/run-cpu.sh:30.
+ * bsw_extend_async queues the call and returns a ticket at once; a worker thread of the engine runs everything that is
+ * queued at that moment -- calls of any threads, over any buffers, with the same w -- as ONE batch and writes every
+ * call's six result fields into its own records; bsw_wait blocks until the ticket's results are there and returns
+ * that call's status (cells_effective, optional: the call's share of the batch's effective DP cells).  Thread-safe:
+ * any thread may submit and wait.  The buffers must stay valid until bsw_wait returns; every ticket must be waited for
+ * exactly once.  The queue runs on a private child engine, so synchronous calls on `eng` may go on meanwhile.
+ * bsw_async_stats: calls submitted / batches run so far (calls / batches = the coalescing factor). */
+int bsw_extend_async(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer, int64_t n_pairs,
+                     int32_t w, int64_t* ticket);
+int bsw_wait(bsw_engine* eng, int64_t ticket, int64_t* cells_effective);
+int bsw_async_stats(const bsw_engine* eng, int64_t* calls, int64_t* batches);
+
 /* ---- (f.1) band-doubling retry of the aligner ------------------------------
  * replaces: the MAX_BAND_TRY loops around ksw_extend2 in mem_chain2aln,
  * tools/bwa/bwamem.c:630,723-753 (left extension) and :770-800 (right extension):

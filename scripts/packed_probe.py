@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--w", type=int, default=100)
     ap.add_argument("--only-packed", action="store_true")
     ap.add_argument("--only-resident", action="store_true")
+    ap.add_argument("--long", action="store_true", help="route every pair to the warp-per-pair kernel")
     args = ap.parse_args()
     res = {}
     for name in args.workloads:
@@ -50,7 +51,7 @@ def main():
         out = gb.pinned_empty(n, gb.OUTSCORE_DTYPE)
         out16 = gb.pinned_empty(n, gb.SCORE16_DTYPE)
         if args.only_resident:
-            with gb.Engine() as eng:
+            with gb.Engine(**(dict(long_min_qlen=1) if args.long else {})) as eng:
                 eng.stage(pairs, ref, qer, args.w)
                 ks = []
                 for _ in range(args.steps + 3):

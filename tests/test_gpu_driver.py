@@ -49,12 +49,15 @@ def _build_check():
     return subprocess.run(cmd).returncode == 0
 
 
+@pytest.mark.parametrize("coalesce", [0, 8192])
 @pytest.mark.parametrize("case", ["small_151bp", "short8", "with_N", "gap_e2_e3_z20", "large_mix"])
-def test_cxx_dropin_class_results(lib, tmp_path, case):
+def test_cxx_dropin_class_results(lib, tmp_path, case, coalesce):
     """BandedPairWiseSW of include/bandedSWA.h called from C++ (tests/cxx/dropin_check.cpp): getScores16, getScores8
     and the -t 4 -b 512 shape (instances created lazily inside the OpenMP region) give the golden getScores16
     fields; scalarBandedSWAWrapper and scalarBandedSWA (scalar z-drop rule, `mat` consulted for the ambiguity score)
-    give the golden scalarBandedSWA fields."""
+    give the golden scalarBandedSWA fields.  coalesce = BSW_SHIM_COALESCE: small calls of all instances through the
+    shared coalescing queue (bsw_extend_async) or every instance on its own engine (the default)."""
+    import os
     if not _build_check():
         pytest.skip("no C++ compiler for tests/cxx/dropin_check.cpp")
     pairs, ref, qer, w, P, expect, scalar = load_golden(case)
@@ -65,7 +68,8 @@ def test_cxx_dropin_class_results(lib, tmp_path, case):
                             P["match"], P["mismatch"], P["ambig"]))
         f.write(struct.pack("<2q", len(ref), len(qer)))
         f.write(pairs.tobytes()); f.write(ref.tobytes()); f.write(qer.tobytes())
-    res = subprocess.run([str(CHECK), str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+    res = subprocess.run([str(CHECK), str(inp), str(outp)], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, BSW_SHIM_COALESCE=str(coalesce)))
     assert res.returncode == 0, res.stderr
     out = np.fromfile(outp, dtype=np.int32).reshape(5, n, 6)
     in8 = (pairs["len1"] < 128) & (pairs["len2"] < 128) & (pairs["h0"] + pairs["len2"] * P["match"] <= 127)
