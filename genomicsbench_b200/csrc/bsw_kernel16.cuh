@@ -580,25 +580,33 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
             int jj;
             if (zb) jj = fb + lobit(zb);
             else {
-                jj = fb + 8;
-                while (jj < end) {
-                    const uint32_t ha = K16_HADDR(jj);
-                    if (lds16(ha) | lds16(ha + 8)) break;
-                    ++jj;
+                // the first block holds no live column: look for the first one a whole block at a time (two 128-bit
+                // loads and one non-zero map per 8 columns; on divergent pairs this search runs more than once per
+                // row, for one or two lanes of the warp at a time, and a column-by-column loop of dependent 16-bit
+                // loads cost 6 % of the kernel, profiles/r02k_sass_sweep_w100_launch0.txt)
+                jj = end;
+                for (int jb = fb + 8; jb < end; jb += 8) {
+                    const uint32_t ba = eh_sa + 4u * K16_MODW(jb);
+                    const uint4 b0 = lds128(ba), b1 = lds128(ba + 16);
+                    uint32_t zm;
+                    K16_ZMAP(b0.x | b0.z, b0.y | b0.w, b1.x | b1.z, b1.y | b1.w, zm)
+                    if (zm) { jj = jb + lobit(zm); break; }
                 }
-                jj = jj < end ? jj : end;
+                jj = jj < end ? jj : end;              // (columns from end on may hold stale non-zero cells)
             }
             beg = jj;
             const uint32_t ze = beg > lb ? zl & (0xffu << (beg - lb)) : zl;
             if (ze) jj = lb + hibit(ze);
             else {
-                jj = lb - 1;
-                while (jj >= beg) {
-                    const uint32_t ha = K16_HADDR(jj);
-                    if (lds16(ha) | lds16(ha + 8)) break;
-                    --jj;
+                jj = beg - 1;
+                for (int jb = lb - 8; jb + 7 >= beg; jb -= 8) {
+                    const uint32_t ba = eh_sa + 4u * K16_MODW(jb);
+                    const uint4 b0 = lds128(ba), b1 = lds128(ba + 16);
+                    uint32_t zm;
+                    K16_ZMAP(b0.x | b0.z, b0.y | b0.w, b1.x | b1.z, b1.y | b1.w, zm)
+                    if (jb < beg) zm &= 0xffu << (beg - jb);
+                    if (zm) { jj = jb + hibit(zm); break; }
                 }
-                jj = jj >= beg - 1 ? jj : beg - 1;
             }
             end = jj + 2 < qlen ? jj + 2 : qlen;
         }

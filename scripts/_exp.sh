@@ -1,10 +1,8 @@
 cd $GRAFT_REPO_ROOT
-echo "small short: $(python scripts/packed_probe.py small --only-resident --steps 10 2>&1 | tail -1)"
-echo "small long:  $(python scripts/packed_probe.py small --only-resident --steps 10 --long 2>&1 | tail -1)"
-for n in 2000 5000 20000 40000; do
-echo "small n=$n short: $(python scripts/packed_probe.py small --n $n --only-resident --steps 10 2>&1 | tail -1)"
-echo "small n=$n long:  $(python scripts/packed_probe.py small --n $n --only-resident --steps 10 --long 2>&1 | tail -1)"
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_properties.py -x -q 2>&1 | tail -3
+for wl in short8 large sweep long16; do
+  echo "$wl w=100: $(python scripts/packed_probe.py $wl --only-resident --steps 5 2>&1 | tail -1)"
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:bsw_short16 -c 1 -f -o /tmp/prof python scripts/resident_run.py sweep_w100_z100 0 1 > /dev/null 2>&1
-python scripts/ncu_summary.py /tmp/prof.ncu-rep 0 --sass > gpurun_out/r02k_sass_sweep_w100_launch0.txt 2>&1
-wc -l gpurun_out/r02k_sass_sweep_w100_launch0.txt
+echo "sweep w=500: $(python scripts/packed_probe.py sweep --only-resident --steps 5 --w 500 2>&1 | tail -1)"
+echo "sweep w=32: $(python scripts/packed_probe.py sweep --only-resident --steps 5 --w 32 2>&1 | tail -1)"
+echo "small: $(python scripts/packed_probe.py small --only-resident --steps 5 2>&1 | tail -1)"
