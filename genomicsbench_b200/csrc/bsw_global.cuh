@@ -182,4 +182,28 @@ bsw_cigar_compact(const GlobalDesc* __restrict__ desc, int n, const uint32_t* __
     for (int k = 0; k < m; ++k) dst[k] = src[k];
 }
 
+// out_off[0 .. n] = exclusive prefix sum of n_cigar[0 .. n) (input order): one block, every thread sums a contiguous
+// slice, the slice totals are scanned in shared memory.  Keeps the chunk on the device between the alignment kernel
+// and the compaction (no host round trip for the offsets).
+__global__ void __launch_bounds__(1024)
+bsw_cigar_offsets(const int32_t* __restrict__ n_cigar, int n, long long* __restrict__ out_off)
+{
+    __shared__ long long s_tot[1024];
+    const int per = (n + 1023) / 1024;
+    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    long long sum = 0;
+    for (int k = lo; k < hi; ++k) sum += n_cigar[k];
+    s_tot[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const long long v = threadIdx.x >= o ? s_tot[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_tot[threadIdx.x] += v;
+        __syncthreads();
+    }
+    long long run = s_tot[threadIdx.x] - sum;
+    for (int k = lo; k < hi; ++k) { out_off[k] = run; run += n_cigar[k]; }
+    if (threadIdx.x == 1023) out_off[n] = s_tot[1023];
+}
+
 } // namespace bsw

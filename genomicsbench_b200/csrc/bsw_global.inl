@@ -5,14 +5,44 @@
 // buffer one after the other (cigar_off[]).
 namespace {
 
-struct GlobalBufs {                      // grow-only device buffers of bsw_global, owned by the engine
+// One chunk in flight: grow-only device buffers with page-locked twins for everything that crosses PCIe.  Two of
+// them alternate (owned by the engine), so that the host prepares chunk k + 1 -- gather, work order -- while the
+// device runs chunk k and chunk k - 1 drains.
+struct GlobalSlot {
     Buf<uint8_t> q, r, z;
     Buf<GlobalDesc> desc;
     Buf<int2> eh;
     Buf<uint32_t> cig, packed;
     Buf<int32_t> score, ncig;
     Buf<long long> off;
+    cudaStream_t st{};
+    cudaEvent_t e0{}, e1{};
+    int64_t first = 0, m = 0;            // alignments [first, first + m) of the call
+    long long cap_words = 0;             // upper bound of the chunk's packed operations
+    long long cells = 0;
 };
+
+struct GlobalBufs {
+    GlobalSlot slot[2];
+    std::vector<GlobalDesc> hd;
+    std::vector<uint64_t> key, tmp;
+};
+
+// stable LSD radix sort on bits 20 .. 51 of the keys (two 16-bit digits: target length, band): the chunk's work order
+void radix_sort_work(std::vector<uint64_t>& a, std::vector<uint64_t>& tmp)
+{
+    tmp.resize(a.size());
+    std::vector<uint32_t> cnt(65536);
+    for (int pass = 0; pass < 2; ++pass) {
+        const int sh = 20 + 16 * pass;
+        std::fill(cnt.begin(), cnt.end(), 0u);
+        for (uint64_t v : a) ++cnt[(v >> sh) & 0xffff];
+        uint32_t run = 0;
+        for (uint32_t& c : cnt) { const uint32_t t = c; c = run; run += t; }
+        for (uint64_t v : a) tmp[cnt[(v >> sh) & 0xffff]++] = v;
+        a.swap(tmp);
+    }
+}
 
 } // namespace
 
@@ -21,8 +51,13 @@ static void bsw_global_release(bsw_engine* eng)
     if (!eng->gbufs) return;
     GlobalBufs* B = static_cast<GlobalBufs*>(eng->gbufs);
     if (!eng->devs.empty()) cudaSetDevice(eng->devs[0].dev);
-    release(B->q); release(B->r); release(B->z); release(B->desc); release(B->eh); release(B->cig);
-    release(B->packed); release(B->score); release(B->ncig); release(B->off);
+    for (GlobalSlot& S : B->slot) {
+        release(S.q); release(S.r); release(S.z); release(S.desc); release(S.eh); release(S.cig);
+        release(S.packed); release(S.score); release(S.ncig); release(S.off);
+        if (S.st) cudaStreamDestroy(S.st);
+        if (S.e0) cudaEventDestroy(S.e0);
+        if (S.e1) cudaEventDestroy(S.e1);
+    }
     delete B;
     eng->gbufs = nullptr;
 }
@@ -43,38 +78,46 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
     if (cigar_off) cigar_off[0] = 0;
     if (n == 0) return BSW_OK;
     const double t_begin = now_ms();
-    for (int64_t i = 0; i < n; ++i) {
-        const SeqPair& sp = pairs[i];
-        const long long dl = (long long)sp.len1 - (long long)sp.len2;
-        if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.idr < 0 || sp.idq < 0 || w[i] < 0 ||
-            w[i] > 32767 || (dl < 0 ? -dl : dl) > w[i]) {
-            eng->err = "bsw_global: need 1 <= len1, len2 <= 32767, offsets >= 0 and |len1 - len2| <= w <= 32767 "
-                       "(outside the band the reference's backtrack leaves its matrix, ksw.c:593-595)";
-            return BSW_ERR_DOMAIN;
+    std::atomic<int> bad{0};
+    eng->pool->for_range(n, 16384, [&](int64_t b, int64_t e, int) {
+        for (int64_t i = b; i < e; ++i) {
+            const SeqPair& sp = pairs[i];
+            const long long dl = (long long)sp.len1 - (long long)sp.len2;
+            if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.idr < 0 || sp.idq < 0 || w[i] < 0 ||
+                w[i] > 32767 || (dl < 0 ? -dl : dl) > w[i]) bad.store(1, std::memory_order_relaxed);
         }
+    });
+    if (bad.load()) {
+        eng->err = "bsw_global: need 1 <= len1, len2 <= 32767, offsets >= 0 and |len1 - len2| <= w <= 32767 "
+                   "(outside the band the reference's backtrack leaves its matrix, ksw.c:593-595)";
+        return BSW_ERR_DOMAIN;
     }
     DevCtx& c = eng->devs[0];
     CUDA_TRY(cudaSetDevice(c.dev));
     if (!eng->gbufs) eng->gbufs = new GlobalBufs();
     GlobalBufs& B = *static_cast<GlobalBufs*>(eng->gbufs);
-    cudaStream_t st = c.cs[0];
+    for (GlobalSlot& G : B.slot)
+        if (!G.st) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&G.st, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreate(&G.e0));
+            CUDA_TRY(cudaEventCreate(&G.e1));
+        }
     GlobalParams GP{eng->p.o_del, eng->p.e_del, eng->p.o_ins, eng->p.e_ins, eng->p.match, -eng->p.mismatch, eng->p.ambig};
-    std::vector<GlobalDesc> hd;
-    std::vector<uint64_t> order;
-    std::vector<long long> hoff;
-    std::vector<int32_t> hn;
-    const long long Z_CAP = 3ll << 30, C_CAP = 1ll << 28, EH_CAP = 1ll << 27;      // bytes / words / cells per chunk
-    int64_t done = 0;
-    long long out_pos = 0;
-    while (done < n) {
-        // chunk: as many alignments as fit the direction-matrix, operation-list and row-scratch budgets
+    const long long Z_CAP = 3ll << 29, C_CAP = 1ll << 27, EH_CAP = 1ll << 26;      // bytes / words / cells per chunk
+    const int64_t M_CAP = 65536;                                                    // alignments per chunk
+    std::vector<GlobalDesc>& hd = B.hd;
+
+    // host part of a chunk: descriptors, gather into page-locked staging, work order; then everything the device
+    // does with it, enqueued on the slot's stream (nothing here waits for the device)
+    auto launch = [&](GlobalSlot& G, int64_t first) -> int {
+        const double t_host0 = now_ms();
         hd.clear();
         long long zb = 0, cw = 0, qb = 0, rb = 0;
         int qmax = 0, wmax = 0;
         int64_t m = 0;
-        while (done + m < n && m < 131072) {
-            const SeqPair& sp = pairs[done + m];
-            const int wv = w[done + m];
+        while (first + m < n && m < M_CAP) {
+            const SeqPair& sp = pairs[first + m];
+            const int wv = w[first + m];
             const long long n_col = sp.len2 < 2 * wv + 1 ? sp.len2 : 2 * wv + 1;
             const long long zi = ((n_col + 7) & ~7ll) * sp.len1, ci = (long long)sp.len1 + sp.len2;   // row pitch of bsw_global_kernel
             const int qm = std::max(qmax, sp.len2);
@@ -86,95 +129,128 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
             zb += zi; cw += ci; qb += sp.len2; rb += sp.len1; qmax = qm; wmax = std::max(wmax, wv);
             ++m;
         }
-        if (int rc = ensure(eng, B.q, (size_t)qb + 16, true)) return rc;      // pinned staging twins: the H2D copies run at link speed
-        if (int rc = ensure(eng, B.r, (size_t)rb + 16, true)) return rc;
-        if (int rc = ensure(eng, B.desc, (size_t)m, true)) return rc;
-        uint8_t* const hq = B.q.h; uint8_t* const hr = B.r.h;
+        G.first = first; G.m = m; G.cap_words = cw;
+        if (int rc = ensure(eng, G.q, (size_t)qb + 16, true)) return rc;      // pinned staging twins: the copies run at link speed
+        if (int rc = ensure(eng, G.r, (size_t)rb + 16, true)) return rc;
+        if (int rc = ensure(eng, G.desc, (size_t)m, true)) return rc;
+        uint8_t* const hq = G.q.h; uint8_t* const hr = G.r.h;
         std::vector<long long> cells_part((size_t)eng->pool->size(), 0);
         eng->pool->for_range(m, 1024, [&](int64_t b, int64_t e, int tid) {
             long long cells = 0;
             for (int64_t k = b; k < e; ++k) {
-                const SeqPair& sp = pairs[done + k];
+                const SeqPair& sp = pairs[first + k];
                 const GlobalDesc& d = hd[(size_t)k];
                 memcpy(hq + d.qoff, seq_qer + sp.idq, (size_t)sp.len2);
                 memcpy(hr + d.roff, seq_ref + sp.idr, (size_t)sp.len1);
-                for (int i = 0; i < d.tlen; ++i) {                   // DP cells inside the band
-                    const int beg = i > d.w ? i - d.w : 0, end = i + d.w + 1 < d.qlen ? i + d.w + 1 : d.qlen;
-                    if (end > beg) cells += end - beg;
-                }
+                // DP cells inside the band: sum over rows i < tlen of min(i + w + 1, qlen) - max(i - w, 0), in closed
+                // form (|tlen - qlen| <= w keeps every row's window non-empty)
+                const long long T = d.tlen, Q = d.qlen, W = d.w;
+                const long long a = std::min(T, std::max(0ll, Q - W - 1));           // rows whose window ends before qlen
+                const long long kb = std::max(0ll, T - W - 1);                        // rows whose window starts after 0
+                cells += a * (a - 1) / 2 + a * (W + 1) + (T - a) * Q - kb * (kb + 1) / 2;
             }
             cells_part[(size_t)tid] += cells;
         });
-        for (long long v : cells_part) S.cells_effective += v;
-        // threads run in order of decreasing target length: the lanes of a warp then finish together and
-        // the longest alignments start first (idx keeps the input position for the outputs)
-        // (band width first: the column loop's trip count is what the lanes of a warp share row by row)
-        order.resize((size_t)m);
+        G.cells = 0;
+        for (long long v : cells_part) G.cells += v;
+        // threads run in order of decreasing band width, then target length: the column loop's trip count is what
+        // the lanes of a warp share row by row, and the longest alignments start first (idx keeps the input position)
+        B.key.resize((size_t)m);
         for (int64_t k = 0; k < m; ++k) {
             const GlobalDesc& d = hd[(size_t)k];
             const uint64_t band = (uint64_t)(d.qlen < 2 * d.w + 1 ? d.qlen : 2 * d.w + 1);
-            order[(size_t)k] = ~((band << 16 | (uint64_t)d.tlen) << 20) & ~0xfffffull | (uint64_t)k;   // descending work, then input order
+            B.key[(size_t)k] = (~((band << 16 | (uint64_t)d.tlen) << 20) & 0xfffffffffff00000ull) | (uint64_t)k;
         }
-        std::sort(order.begin(), order.end());
-        for (int64_t k = 0; k < m; ++k) B.desc.h[k] = hd[(size_t)(order[(size_t)k] & 0xfffff)];
+        radix_sort_work(B.key, B.tmp);
+        for (int64_t k = 0; k < m; ++k) G.desc.h[k] = hd[(size_t)(B.key[(size_t)k] & 0xfffff)];
         const int threads = (int)m, stride = ((threads + 31) / 32) * 32;
-        if (int rc = ensure(eng, B.z, (size_t)zb + 16)) return rc;
-        if (int rc = ensure(eng, B.cig, (size_t)cw + 16)) return rc;
+        if (int rc = ensure(eng, G.z, (size_t)zb + 16)) return rc;
+        if (int rc = ensure(eng, G.cig, (size_t)cw + 16)) return rc;
+        if (int rc = ensure(eng, G.packed, (size_t)cw + 16, true)) return rc;
         const int W = std::max(2 * wmax + 2, 16);                    // live columns of a row (bsw_global.cuh; >= 16: its 8-column blocks wrap once)
         const int qstride = 4 * (((qmax + 3) / 4) | 1);               // query bytes per thread in shared memory
         const size_t smem = (size_t)W * GLOBAL_BLOCK * sizeof(int2) + (size_t)qstride * GLOBAL_BLOCK;
         const bool use_smem = smem <= 200 * 1024;
-        if (!use_smem) if (int rc = ensure(eng, B.eh, (size_t)(qmax + 1) * (size_t)stride)) return rc;
-        if (int rc = ensure(eng, B.score, (size_t)m)) return rc;
-        if (int rc = ensure(eng, B.ncig, (size_t)m)) return rc;
-        if (int rc = ensure(eng, B.off, (size_t)m + 1)) return rc;
-        CUDA_TRY(cudaMemcpyAsync(B.desc.d, B.desc.h, sizeof(GlobalDesc) * (size_t)m, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(B.q.d, hq, (size_t)qb, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(B.r.d, hr, (size_t)rb, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaEventRecord(c.ev_t0, st));
+        if (!use_smem) if (int rc = ensure(eng, G.eh, (size_t)(qmax + 1) * (size_t)stride)) return rc;
+        if (int rc = ensure(eng, G.score, (size_t)m, true)) return rc;
+        if (int rc = ensure(eng, G.ncig, (size_t)m, true)) return rc;
+        if (int rc = ensure(eng, G.off, (size_t)m + 1, true)) return rc;
+        cudaStream_t st = G.st;
+        CUDA_TRY(cudaMemcpyAsync(G.desc.d, G.desc.h, sizeof(GlobalDesc) * (size_t)m, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(G.q.d, hq, (size_t)qb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(G.r.d, hr, (size_t)rb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(G.e0, st));
         const int gblocks = (threads + GLOBAL_BLOCK - 1) / GLOBAL_BLOCK;
         if (use_smem) {
             if (!eng->global_attr_set) {
                 CUDA_TRY(cudaFuncSetAttribute(bsw_global_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 eng->global_attr_set = true;
             }
-            bsw_global_kernel<true><<<gblocks, GLOBAL_BLOCK, smem, st>>>(B.desc.d, threads, B.q.d, B.r.d, nullptr, 0, W, qstride, B.z.d,
-                                                                         B.cig.d, B.score.d, B.ncig.d, GP);
+            bsw_global_kernel<true><<<gblocks, GLOBAL_BLOCK, smem, st>>>(G.desc.d, threads, G.q.d, G.r.d, nullptr, 0, W, qstride, G.z.d,
+                                                                         G.cig.d, G.score.d, G.ncig.d, GP);
         } else {
-            bsw_global_kernel<false><<<gblocks, GLOBAL_BLOCK, 0, st>>>(B.desc.d, threads, B.q.d, B.r.d, B.eh.d, stride, 0, 0, B.z.d,
-                                                                       B.cig.d, B.score.d, B.ncig.d, GP);
+            bsw_global_kernel<false><<<gblocks, GLOBAL_BLOCK, 0, st>>>(G.desc.d, threads, G.q.d, G.r.d, G.eh.d, stride, 0, 0, G.z.d,
+                                                                       G.cig.d, G.score.d, G.ncig.d, GP);
         }
+        CUDA_TRY(cudaEventRecord(G.e1, st));
+        // offsets of the packed operation lists (device scan), compaction, and the way out -- the packed lists are
+        // copied as far as the chunk's upper bound allows without knowing their total: first the scalars, and after
+        // the host has seen the total, exactly that many operations
+        bsw_cigar_offsets<<<1, 1024, 0, st>>>(G.ncig.d, threads, G.off.d);
+        bsw_cigar_compact<<<(threads + 127) / 128, 128, 0, st>>>(G.desc.d, threads, G.cig.d, G.ncig.d, G.off.d, G.packed.d);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(c.ev_t1, st));
-        CUDA_TRY(cudaMemcpyAsync(score + done, B.score.d, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(n_cigar + done, B.ncig.d, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, c.ev_t0, c.ev_t1) == cudaSuccess) S.ms_kernel += (double)ms;
-        // pack the operation lists behind those of the earlier chunks
-        hoff.resize((size_t)m + 1);
-        long long run = 0;
-        for (int64_t k = 0; k < m; ++k) { hoff[(size_t)k] = run; run += n_cigar[done + k]; cigar_off[done + k + 1] = out_pos + run; }
-        hoff[(size_t)m] = run;
+        CUDA_TRY(cudaMemcpyAsync(G.score.h, G.score.d, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(G.ncig.h, G.ncig.d, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(G.off.h, G.off.d, sizeof(long long) * ((size_t)m + 1), cudaMemcpyDeviceToHost, st));
+        S.kernel_launches += 3;
+        S.h2d_bytes += (int64_t)(sizeof(GlobalDesc) * (size_t)m + (size_t)qb + (size_t)rb);
+        S.ms_pack += now_ms() - t_host0;                 // host: descriptors, gather, work order, enqueue
+        return BSW_OK;
+    };
+    long long out_pos = 0;
+    // results of a chunk into the caller's arrays (behind those of the earlier chunks)
+    auto finish = [&](GlobalSlot& G) -> int {
+        const double t_w0 = now_ms();
+        CUDA_TRY(cudaStreamSynchronize(G.st));
+        const double t_w1 = now_ms();
+        S.ms_d2h += t_w1 - t_w0;                         // host waiting for the device
+        const int64_t m = G.m, first = G.first;
+        const long long run = G.off.h[m];
         if (out_pos + run > cigar_cap) {
             eng->err = "bsw_global: cigar buffer too small (len1 + len2 entries per alignment always suffice)";
             return BSW_ERR_PARAM;
         }
-        if (run > 0) {
-            if (int rc = ensure(eng, B.packed, (size_t)run)) return rc;
-            CUDA_TRY(cudaMemcpyAsync(B.off.d, hoff.data(), sizeof(long long) * ((size_t)m + 1), cudaMemcpyHostToDevice, st));
-            bsw_cigar_compact<<<(threads + 127) / 128, 128, 0, st>>>(B.desc.d, threads, B.cig.d, B.ncig.d, B.off.d, B.packed.d);
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemcpyAsync(cigar + out_pos, B.packed.d, sizeof(uint32_t) * (size_t)run, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-        }
-        S.kernel_launches += 2;
-        S.h2d_bytes += (int64_t)(sizeof(GlobalDesc) * (size_t)m + (size_t)qb + (size_t)rb);
-        S.d2h_bytes += (int64_t)(8 * m + 4 * run);
-
-        for (int64_t k = 0; k < m; ++k) S.cells_nominal += (int64_t)pairs[done + k].len1 * pairs[done + k].len2;
+        if (run > 0) CUDA_TRY(cudaMemcpyAsync(G.packed.h, G.packed.d, sizeof(uint32_t) * (size_t)run, cudaMemcpyDeviceToHost, G.st));
+        memcpy(score + first, G.score.h, sizeof(int32_t) * (size_t)m);
+        memcpy(n_cigar + first, G.ncig.h, sizeof(int32_t) * (size_t)m);
+        for (int64_t k = 0; k < m; ++k) cigar_off[first + k + 1] = out_pos + G.off.h[k + 1];
+        for (int64_t k = 0; k < m; ++k) S.cells_nominal += (int64_t)pairs[first + k].len1 * pairs[first + k].len2;
+        CUDA_TRY(cudaStreamSynchronize(G.st));
+        if (run > 0) memcpy(cigar + out_pos, G.packed.h, sizeof(uint32_t) * (size_t)run);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, G.e0, G.e1) == cudaSuccess) S.ms_kernel += (double)ms;
+        S.cells_effective += G.cells;
+        S.d2h_bytes += (int64_t)(16 * m + 4 * run);
         out_pos += run;
-        done += m;
+        S.ms_scatter += now_ms() - t_w1;                 // host: results into the caller's arrays (incl. the wait for the packed lists)
+        return BSW_OK;
+    };
+    int64_t next = 0;
+    int cur = 0;
+    bool pending[2] = {false, false};
+    while (next < n) {
+        GlobalSlot& G = B.slot[cur];
+        if (pending[cur]) { if (int rc = finish(G)) { cudaDeviceSynchronize(); return rc; } pending[cur] = false; }
+        if (int rc = launch(G, next)) { cudaDeviceSynchronize(); return rc; }
+        pending[cur] = true;
+        next += G.m;
+        cur ^= 1;
+    }
+    // drain in submission order: the slot that was launched first is the one `cur` points at now
+    for (int k = 0; k < 2; ++k) {
+        GlobalSlot& G = B.slot[cur];
+        if (pending[cur]) { if (int rc = finish(G)) { cudaDeviceSynchronize(); return rc; } pending[cur] = false; }
+        cur ^= 1;
     }
     S.ms_total = now_ms() - t_begin;
     return BSW_OK;

@@ -27,6 +27,7 @@ assert np.array_equal(score, np.tile(z["score"], tiles)) and np.array_equal(ciga
 line = {"metric": "global_alignments_per_sec", "alignments": int(len(big)), "seconds": best, "value": len(big) / best,
         "band_cells": int(st["cells_effective"]), "gcups_band": st["cells_effective"] / best / 1e9,
         "kernel_ms": st["ms_kernel"], "gcups_band_kernel_only": st["cells_effective"] / (st["ms_kernel"] * 1e-3) / 1e9,
+        "host_ms": {"prepare_and_enqueue": st["ms_pack"], "wait_for_device": st["ms_d2h"], "results_out": st["ms_scatter"], "call_total": st["ms_total"]},
         "cigar_ops": int(len(cigar)), "gpu_launches": int(st["kernel_launches"]), "buffers": "pageable numpy arrays"}
 if KswReference.available():
     K = KswReference(); P = make_params(**c["P"])
