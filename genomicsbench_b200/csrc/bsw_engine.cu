@@ -172,7 +172,9 @@ struct DevCtx {
 struct Job {
     SeqPair* pairs = nullptr; const uint8_t* seq_ref = nullptr; const uint8_t* seq_qer = nullptr;
     const bsw_packed_batch* pb = nullptr; void* out = nullptr; bool out16 = false;
+    bool force_staged = false;            // page-locked buffers, but sequences spread over more than the direct route's 2^30-byte reach
 };
+constexpr int BSW_RETRY_STAGED = -100;    // internal: the direct route met such a chunk; the call is run again on the staged route
 
 } // namespace
 
@@ -505,6 +507,7 @@ int direct_sequences(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8
     CUDA_TRY(cudaEventSynchronize(s.ev_info));
     s.info = *s.h_info;
     if (s.info.bad) return BSW_ERR_DOMAIN;
+    if (s.info.far) return BSW_RETRY_STAGED;
     const long long base0_r = pairs[s.a].idr, base0_q = pairs[s.a].idq;
     struct Side { const uint8_t* host; long long base0; unsigned long long mn, mx, bases; Buf<uint8_t>* buf; const uint8_t** out; };
     Side sides[2] = {{seq_qer, base0_q, s.info.min_q, s.info.max_q, s.info.qbases, &s.qraw, &s.qbase},
@@ -653,7 +656,7 @@ int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t
         const int lo = (int)b * BLK, hi = std::min(n, lo + BLK);
         for (int k = lo; k < hi; ++k) {
             const SeqPair& sp = P[k];
-            if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.h0 < 1 ||
+            if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.h0 < 0 ||
                 (int64_t)sp.h0 + (int64_t)sp.len2 * match > 32767 || sp.idr < 0 || sp.idq < 0) { I.bad++; continue; }
             q += (uint64_t)sp.len2; r += (uint64_t)sp.len1;
             I.nominal += (unsigned long long)sp.len1 * (unsigned long long)sp.len2;
@@ -1011,7 +1014,7 @@ int begin_batch(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, c
 }
 
 const char* kDomainMsg =
-    "pair outside the domain: need 1<=len1,len2<=32767, h0>=1, h0+len2*match<=32767, offsets>=0 "
+    "pair outside the domain: need 1<=len1,len2<=32767, h0>=0, h0+len2*match<=32767, offsets>=0 "
     "(bandedSWA.h:84, SURVEY 8b); result fields of the batch are unspecified";
 
 struct ChunkRef { int dev; int slot; };
@@ -1029,7 +1032,7 @@ int run_pipeline(bsw_engine* eng, const Job& job, int dev_lo, int ndev, int64_t 
     const uint8_t* const seq_ref = job.seq_ref;
     const uint8_t* const seq_qer = job.seq_qer;
     const bool packed = job.pb != nullptr;
-    const bool direct = packed || (is_pinned(pairs) && is_pinned(seq_ref) && is_pinned(seq_qer));
+    const bool direct = packed || (!job.force_staged && is_pinned(pairs) && is_pinned(seq_ref) && is_pinned(seq_qer));
     // PCIe-bound or compute-bound?  A sample of the records gives DP time (nominal cells at the
     // resident kernel rate) against transfer time (record + sequence bytes at PCIe rate) per pair.
     // PCIe-bound batches run partitioned: chunk streams on the service SMs, DP on the rest.
@@ -1477,7 +1480,18 @@ int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const ui
     if (n == 0) return BSW_OK;
     Job job;
     job.pairs = pairs; job.seq_ref = seq_ref; job.seq_qer = seq_qer;
-    const int rc = run_sharded(eng, job, n, CHUNK_EXTEND);
+    int rc = run_sharded(eng, job, n, CHUNK_EXTEND);
+    if (rc == BSW_RETRY_STAGED) {
+        // page-locked buffers whose pairs address sequences 2^30 bytes or more apart inside one chunk (shuffled pair
+        // order over large buffers): the staged route gathers the bytes on the host and has no such limit
+        quiesce(eng);
+        bsw_stats& S = eng->stats;
+        memset(&S, 0, sizeof(S));
+        S.pairs = n;
+        eng->err.clear();
+        job.force_staged = true;
+        rc = run_sharded(eng, job, n, CHUNK_EXTEND);
+    }
     if (rc != BSW_OK) { quiesce(eng); return rc; }
     if (int rc2 = collect_cells(eng)) return rc2;
     eng->stats.ms_total = now_ms() - t_begin;
@@ -1516,7 +1530,7 @@ static int extend_packed(bsw_engine* eng, const bsw_packed_batch* b, int32_t w, 
     const int rc = run_sharded(eng, job, b->n_pairs, CHUNK_EXTEND);
     if (rc != BSW_OK) {
         if (rc == BSW_ERR_DOMAIN)
-            eng->err = "bsw_extend_packed: descriptor outside the domain: need 1<=len1,len2<=32767, h0>=1, h0+len2*match<=32767, "
+            eng->err = "bsw_extend_packed: descriptor outside the domain: need 1<=len1,len2<=32767, h0>=0, h0+len2*match<=32767, "
                        "offsets inside the batch's buffers, and queries the engine routes to the byte-reading kernels "
                        "(longer than BSW_PACKED_MAX_QLEN or bsw_params.long_min_qlen) stored RAW";
         quiesce(eng);
@@ -1605,7 +1619,13 @@ int bsw_stage(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, con
         Job job;
         job.pairs = const_cast<SeqPair*>(pairs); job.seq_ref = seq_ref; job.seq_qer = seq_qer;
         static const int64_t env_stage = getenv("BSW_STAGE_CHUNK") ? atoll(getenv("BSW_STAGE_CHUNK")) : 0;     // experiments
-        const int rc = run_pipeline(eng, job, 0, (int)eng->devs.size(), 0, n, env_stage > 0 ? env_stage : CHUNK_STAGE, true);
+        int rc = run_pipeline(eng, job, 0, (int)eng->devs.size(), 0, n, env_stage > 0 ? env_stage : CHUNK_STAGE, true);
+        if (rc == BSW_RETRY_STAGED) {
+            quiesce(eng);
+            job.force_staged = true;
+            eng->stats.cells_nominal = 0; eng->stats.h2d_bytes = 0; eng->stats.kernel_launches = 0;
+            rc = run_pipeline(eng, job, 0, (int)eng->devs.size(), 0, n, env_stage > 0 ? env_stage : CHUNK_STAGE, true);
+        }
         if (rc != BSW_OK) { quiesce(eng); return rc; }
     }
     eng->staged = true;

@@ -52,7 +52,7 @@ void build_sorted_batch(ThreadPool& pool, const SeqPair* pairs, int64_t n, int32
         Acc a = acc[t];
         for (int64_t k = b; k < e; ++k) {
             const SeqPair& sp = pairs[k];
-            if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.h0 < 1 ||
+            if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.h0 < 0 ||
                 (int64_t)sp.h0 + (int64_t)sp.len2 * match > 32767 || sp.idr < 0 || sp.idq < 0) { a.bad = 1; continue; }
             a.nominal += (int64_t)sp.len1 * sp.len2;
             out.in_len2[k] = (uint16_t)sp.len2; out.in_h0[k] = (uint16_t)sp.h0; out.in_len1[k] = (uint16_t)sp.len1;

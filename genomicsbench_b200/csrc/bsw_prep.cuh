@@ -43,7 +43,8 @@ struct ChunkInfo {
     int qmax_n;                                      // longest query among the N pairs
     int qmax_all;                                    // longest query of the chunk
     int n_wide;                                      // packed route: 2-bit pairs outside the 16-bit kernel's score domain
-    int pad_[3];
+    int far;                                         // direct route: valid pairs whose sequences lie 2^30 bytes or more from the chunk's first pair
+    int pad_[2];
     unsigned int hist[LEN_HIST];                     // pairs per len2
 };
 static_assert(sizeof(ChunkInfo) % 16 == 0, "bsw_info_publish copies 16-byte words");
@@ -97,7 +98,7 @@ bsw_scan_pairs(const SeqPair* __restrict__ pairs, int n, long long base0_r, long
     if (threadIdx.x < 9) s_i[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : 0;
     __syncthreads();
     unsigned long long min_r = ~0ull, max_r = 0, min_q = ~0ull, max_q = 0, nominal = 0, qb = 0, tb = 0;
-    int mn0 = 0x7fffffff, mn1 = 0x7fffffff, mn2 = 0x7fffffff, mx0 = 0, mx1 = 0, mx2 = 0, bad = 0, nshort = 0, qall = 0;
+    int mn0 = 0x7fffffff, mn1 = 0x7fffffff, mn2 = 0x7fffffff, mx0 = 0, mx1 = 0, mx2 = 0, bad = 0, nshort = 0, qall = 0, far = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         // 72-byte record: idr@0 idq@8 len1@24 len2@28 h0@32 (bandedSWA.h:91-100)
         const long long* p64 = reinterpret_cast<const long long*>(pairs + i);
@@ -105,10 +106,15 @@ bsw_scan_pairs(const SeqPair* __restrict__ pairs, int n, long long base0_r, long
         const long long idr = p64[0], idq = p64[1];
         const int len1 = p32[6], len2 = p32[7], h0 = p32[8];
         const long long dr = idr - base0_r, dq = idq - base0_q;
-        const bool ok = len1 >= 1 && len1 <= 32767 && len2 >= 1 && len2 <= 32767 && h0 >= 1 &&
-                        (long long)h0 + (long long)len2 * match <= 32767 && idr >= 0 && idq >= 0 &&
-                        dr > -(1ll << 30) && dr < (1ll << 30) && dq > -(1ll << 30) && dq < (1ll << 30);
-        if (!ok) { bad = 1; desc[i] = make_int4(0, 0, 1 | (1 << 16), 1); continue; }
+        const bool valid = len1 >= 1 && len1 <= 32767 && len2 >= 1 && len2 <= 32767 && h0 >= 0 &&
+                           (long long)h0 + (long long)len2 * match <= 32767 && idr >= 0 && idq >= 0;
+        const bool near = dr > -(1ll << 30) && dr < (1ll << 30) && dq > -(1ll << 30) && dq < (1ll << 30);
+        if (!valid || !near) {
+            // (a valid pair too far away for the 32-bit chunk-relative offsets: the call is re-run on the staged route)
+            if (valid) far = 1; else bad = 1;
+            desc[i] = make_int4(0, 0, 1 | (1 << 16), 1);
+            continue;
+        }
         desc[i] = make_int4((int)dq, (int)dr, len2 | (len1 << 16), h0);
         nominal += (unsigned long long)len1 * (unsigned long long)len2;
         const unsigned long long ur = (unsigned long long)(dr + (1ll << 30)), uq = (unsigned long long)(dq + (1ll << 30));
@@ -136,6 +142,8 @@ bsw_scan_pairs(const SeqPair* __restrict__ pairs, int n, long long base0_r, long
     mn0 = __reduce_min_sync(FULL, mn0); mn1 = __reduce_min_sync(FULL, mn1); mn2 = __reduce_min_sync(FULL, mn2);
     mx0 = __reduce_max_sync(FULL, mx0); mx1 = __reduce_max_sync(FULL, mx1); mx2 = __reduce_max_sync(FULL, mx2);
     bad = __reduce_max_sync(FULL, bad); nshort = __reduce_add_sync(FULL, nshort); qall = __reduce_max_sync(FULL, qall);
+    far = __reduce_max_sync(FULL, far);
+    if (far && (threadIdx.x & 31) == 0) atomicAdd(&info->far, 1);
     if ((threadIdx.x & 31) == 0) {
         atomicMin(&s_u64[0], min_r); atomicMax(&s_u64[1], max_r);
         atomicMin(&s_u64[2], min_q); atomicMax(&s_u64[3], max_q);
@@ -185,7 +193,7 @@ bsw_scan_packed(const int4* __restrict__ desc, int n, const __grid_constant__ Pa
         const int len2 = d.z & 0xffff, len1 = (d.z >> 16) & 0xffff, h0 = d.w & 0xffff;
         const bool raw = ((d.w >> 16) & BSW_PAIR_RAW) != 0;
         const unsigned int qo = (unsigned int)d.x, ro = (unsigned int)d.y;
-        bool ok = len1 >= 1 && len1 <= 32767 && len2 >= 1 && len2 <= 32767 && h0 >= 1 && h0 + len2 * match <= 32767;
+        bool ok = len1 >= 1 && len1 <= 32767 && len2 >= 1 && len2 <= 32767 && h0 >= 0 && h0 + len2 * match <= 32767;
         if (raw) ok = ok && (unsigned long long)qo + len2 <= R.rawq && (unsigned long long)ro + len1 <= R.rawr;
         else ok = ok && len2 <= short_max && qo >= R.qlo && (unsigned long long)qo + ((len2 + 15) >> 4) <= R.qhi &&
                   ro >= R.rlo && (unsigned long long)ro + ((len1 + 15) >> 4) <= R.rhi;

@@ -28,7 +28,7 @@ extern "C" {
 typedef struct dnaSeqPair {
     int64_t idr, idq, id;       /* byte offsets of ref / query in the sequence buffers; caller's id */
     int32_t len1, len2;         /* len1 = reference (target) length, len2 = query length          */
-    int32_t h0;                 /* seed score, > 0                                                 */
+    int32_t h0;                 /* seed score, >= 0                                                */
     int32_t seqid, regid;       /* untouched                                                       */
     int32_t score, tle, gtle, qle;  /* outputs                                                     */
     int32_t gscore, max_off;        /* outputs                                                     */
@@ -39,7 +39,7 @@ typedef struct dnaSeqPair {
 enum {
     BSW_OK            =  0,
     BSW_ERR_PARAM     = -1,   /* parameter outside the supported domain                 */
-    BSW_ERR_DOMAIN    = -2,   /* a pair violates 1<=len<=32767, h0>=1, scores<32768 ... */
+    BSW_ERR_DOMAIN    = -2,   /* a pair violates 1<=len<=32767, h0>=0, scores<32768 ... */
     BSW_ERR_CUDA      = -3,   /* CUDA runtime / no device / kernel image missing        */
     BSW_ERR_NOMEM     = -4,
     BSW_ERR_STATE     = -5,   /* call sequence error (e.g. run before stage)            */
@@ -139,7 +139,7 @@ enum { BSW_PAIR_RAW = 1 };
 typedef struct bsw_pair_desc {        /* 16 bytes */
     uint32_t q_off, r_off;
     uint16_t len2, len1;              /* query / reference (target) length, 1..32767     */
-    uint16_t h0;                      /* seed score, >= 1                                 */
+    uint16_t h0;                      /* seed score                                       */
     uint16_t flags;                   /* BSW_PAIR_RAW                                     */
 } bsw_pair_desc;
 typedef struct bsw_packed_batch {

@@ -117,7 +117,7 @@ def test_packed_errors_and_empty(lib):
             eng.extend_packed(b, w)
         assert ei.value.code in (-1, -2)
         b = lib.PackedBatch.from_pairs(pairs, ref, qer)
-        b.desc["h0"][9] = 0
+        b.desc["len1"][9] = 0
         with pytest.raises(lib.BswError) as ei:
             eng.extend_packed(b, w)
         assert ei.value.code == -2

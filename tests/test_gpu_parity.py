@@ -186,7 +186,7 @@ def test_edge_cases(lib, oracle):
         ro = qo = 0
         for k, (l1, l2) in enumerate(lens):
             pairs[k]["len1"], pairs[k]["len2"], pairs[k]["idr"], pairs[k]["idq"] = l1, l2, ro, qo
-            pairs[k]["h0"] = 1 if k % 3 == 0 else 40
+            pairs[k]["h0"] = (1 if k % 3 == 0 else 40) if k % 5 else 0          # h0 == 0 is in the domain (ksw_extend2 accepts it)
             m = min(l1, l2)                                # make them alignable
             qer[qo: qo + m] = ref[ro: ro + m]
             ro += l1; qo += l2
@@ -204,7 +204,7 @@ def test_domain_errors(lib):
         pairs = np.zeros(2, dtype=SEQPAIR_DTYPE)
         pairs["len1"], pairs["len2"], pairs["h0"] = 10, 10, 5
         buf = np.zeros(64, np.uint8)
-        for field, val in (("len1", 0), ("len2", 0), ("h0", 0), ("len2", 40000), ("h0", 32767)):
+        for field, val in (("len1", 0), ("len2", 0), ("h0", -1), ("len2", 40000), ("h0", 32767)):
             bad = pairs.copy()
             bad[field][1] = val
             with pytest.raises(lib.BswError) as ei:
@@ -213,7 +213,7 @@ def test_domain_errors(lib):
         # the same on page-locked buffers (direct route: the device-side scan finds it; the speculative
         # sequence copy must not act on a malformed first / last record)
         pbuf = lib.pinned_copy(np.zeros(1 << 16, np.uint8))
-        for field, val, at in (("len2", 40000, 0), ("len1", 0, 1), ("h0", 0, 1), ("len1", 50000, 1)):
+        for field, val, at in (("len2", 40000, 0), ("len1", 0, 1), ("h0", -3, 1), ("len1", 50000, 1)):
             bad = lib.pinned_copy(pairs)
             bad[field][at] = val
             with pytest.raises(lib.BswError) as ei:
@@ -224,3 +224,24 @@ def test_domain_errors(lib):
         assert ei.value.code == -5
         eng.extend(pairs, buf, buf, 100)                    # engine still usable afterwards
         assert (pairs["score"] >= 5).all()
+
+
+@pytest.mark.parametrize("kw", [{}, {"short_variant": 1}, {"long_min_qlen": 1}])
+def test_h0_zero_pairs(lib, oracle, kw):
+    """h0 == 0 next to ordinary pairs, on every kernel (packed 16-bit, 32-bit, warp-per-pair) and both routes."""
+    import genomicsbench_b200 as gb
+    cfg = gb.gen_named_config("large")
+    pairs, ref, qer = gb.gen_pairs(cfg, 31, 20000)
+    pairs["h0"][::3] = 0
+    for w in (5, 100, 400):
+        want = pairs.copy()
+        oracle.batch(make_params(), want, ref, qer, w)
+        with lib.Engine(**kw) as eng:
+            got = pairs.copy()
+            eng.extend(got, ref, qer, w)
+            assert np.array_equal(results_matrix(got), results_matrix(want)), (kw, w)
+            if not kw:
+                b = lib.PackedBatch.from_pairs(pairs, ref, qer)
+                out = eng.extend_packed(b, w)
+                for f in lib.RESULT_FIELDS:
+                    assert np.array_equal(out[f], want[f]), (f, w)

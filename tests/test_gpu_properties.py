@@ -294,3 +294,25 @@ def test_partitioner_on_the_hot_path(lib, devices):
         assert ei.value.code == -2
         eng.extend(b, ref, qer, 100)                                 # and the engine keeps working
         assert np.array_equal(results_matrix(b), results_matrix(a))
+
+
+def test_pinned_buffers_with_far_apart_sequences(lib, oracle):
+    """Page-locked buffers whose pairs, in one chunk, address sequences more than 2^30 bytes apart (shuffled pair order
+    over a large reference buffer): beyond the direct route's 32-bit chunk-relative offsets, so the call runs on the
+    staged route instead -- same results, no error (the pageable route always accepted such input)."""
+    cfg = lib.gen_named_config("small")
+    pairs, ref, qer = lib.gen_pairs(cfg, 0, 4000)
+    want = pairs.copy()
+    oracle.batch(make_params(), want, ref, qer, 100)
+    far = (1 << 30) + (1 << 27)
+    big = lib.pinned_empty(far + len(ref) + 64, np.uint8)
+    big[:len(ref)] = ref
+    big[far:far + len(ref)] = ref
+    pp, pq = lib.pinned_copy(pairs), lib.pinned_copy(qer)
+    pp["idr"][1::2] += far                                           # every other pair reads the far copy
+    with lib.Engine() as eng:
+        eng.extend(pp, big, pq, 100)
+        assert np.array_equal(results_matrix(pp), results_matrix(want))
+        eng.stage(pp, big, pq, 100); eng.run_staged()
+        c = pairs.copy(); eng.fetch(c)
+        assert np.array_equal(results_matrix(c), results_matrix(want))

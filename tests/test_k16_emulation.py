@@ -62,6 +62,7 @@ def test_emulated_sweep_matches_oracle(emu, oracle, config, w, zdrop, circ):
     from oracle.pyoracle import make_params
     cfg = gb.gen_named_config(config)
     pairs, ref, qer = gb.gen_pairs(cfg, 12345, 3000)
+    pairs["h0"][::11] = 0                            # h0 == 0 is in the domain
     want = pairs.copy()
     cells_o = oracle.batch(make_params(zdrop=zdrop), want, ref, qer, w)
     cells, skipped, ovf = run_emu(emu, dict(DEFAULT, zdrop=zdrop), pairs, ref, qer, w, circ=circ)

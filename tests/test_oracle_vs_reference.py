@@ -50,5 +50,24 @@ def test_oracle_equals_reference(oracle, reference, lib, idx):
     assert np.array_equal(results_matrix(c), results_matrix(d))
 
 
+@pytest.mark.parametrize("w", [5, 100, 400])
+def test_h0_zero_is_in_the_domain(oracle, reference, w):
+    """ksw_extend2 and getScores16 accept h0 == 0 (score 0, every end 0; gscore 0 / gtle 1 when the first row
+    reaches the query's end, else -1 / 0): the oracle agrees with the reference's vector and scalar code."""
+    cfg = gb.gen_named_config("large")
+    pairs, ref, qer = gb.gen_pairs(cfg, 31, 6000)
+    pairs["h0"][::3] = 0
+    pairs["h0"][1::7] = 1
+    a, b, c, d = pairs.copy(), pairs.copy(), pairs.copy(), pairs.copy()
+    oracle.batch(make_params(), a, ref, qer, w)
+    reference.getscores16(make_params(), b, ref, qer, w, batch=512, nthreads=2)
+    assert np.array_equal(results_matrix(a), results_matrix(b))
+    z = pairs["h0"] == 0
+    assert (a["score"][z] == 0).all() and (a["qle"][z] == 0).all() and (a["tle"][z] == 0).all()
+    oracle.batch(make_params(zdrop_mode=1), c, ref, qer, w)
+    reference.scalar(make_params(zdrop_mode=1), d, ref, qer, w)
+    assert np.array_equal(results_matrix(c), results_matrix(d))
+
+
 def test_reference_layout(reference):
     assert reference.lib.ref_sizeof_seqpair() == gb.SEQPAIR_DTYPE.itemsize == 72
