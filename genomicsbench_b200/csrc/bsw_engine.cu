@@ -195,6 +195,7 @@ struct bsw_engine {
     void* gbufs = nullptr;                // device buffers of bsw_global (GlobalBufs, bsw_global.inl)
     bool global_attr_set = false;
     void* cbufs = nullptr;                // page-locked staging of bsw_extend_chains (ChainBufs, bsw_chain.inl)
+    void* clanes = nullptr;               // child engines of bsw_extend_chains' lanes (ChainLanes, bsw_chain.inl)
     void* aq = nullptr;                   // queue + worker of bsw_extend_async (AsyncQueue, bsw_async.inl)
     std::once_flag aq_once;
 };
