@@ -645,8 +645,9 @@ int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t
     const SeqPair* P = pairs + s.a;
     const int n = s.n;
     const int match = eng->p.match, short_max = eng->short_max;
-    // pass 1: validate + byte totals per block of 4096 pairs
-    const int BLK = 4096;
+    // pass 1: validate + byte totals per block of pairs (4096, fewer for small chunks so that every pool thread gets
+    // a share: a 4096-pair call spent 0.18 of its 0.76 ms in a single-threaded gather)
+    const int BLK = std::max(256, std::min(4096, n / (2 * eng->pool->size())));
     const int nblk = (n + BLK - 1) / BLK;
     std::vector<uint64_t> qsum((size_t)nblk + 1, 0), rsum((size_t)nblk + 1, 0);
     std::vector<ChunkInfo> part((size_t)eng->pool->size());

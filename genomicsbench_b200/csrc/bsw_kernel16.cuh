@@ -310,11 +310,18 @@ BSW_HD bool eligible(int match, int qlen, int h0)
 // than the band then cost the band's shared memory, not the query's.
 template <bool SAMEGAP, bool CIRC = false>
 BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restrict__ qw,
-                       const uint32_t* __restrict__ tw, const uint32_t eh_sa, const uint32_t qp_sa,
+                       const uint32_t* __restrict__ tw, const uint32_t eh_sa_in, const uint32_t qp_sa,
                        const uint32_t qp_stride, const uint32_t tab_sa, PairState& st, long long& my_cells,
                        const uint32_t wcols = 0)
 {
     const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w & 0xffff;
+    // loop constants are pinned in registers through an opaque zero (see bsw_short_kernel): the row's address -- else
+    // the shared window's base is re-derived from special registers inside every row epilogue -- and the z-drop
+    // parameters, which the compiler otherwise re-loads from the constant bank in every row, a dependent stall each
+    // time (profiles/r02k_sass_sweep_w100_launch0.txt)
+    const uint32_t zero = (uint32_t)md.z >> 31;
+    const uint32_t eh_sa = eh_sa_in + zero;
+    const int zdrop_r = P.zdrop + (int)zero, zmode_r = P.zmode + (int)zero;
 
     // ---- first row (bandedSWA.cpp:155-157) and the query plane; the row is initialised up to the
     // end of the block that holds column qlen
@@ -352,8 +359,6 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
     st.max = h0; st.max_i = -1; st.max_j = -1; st.max_ie = -1; st.gscore = -1; st.max_off = 0;
     int beg = 0, end = qlen;
     uint32_t tword = 0;
-    // loop constants, pinned in registers through an opaque zero (see bsw_short_kernel)
-    const uint32_t zero = (uint32_t)md.z >> 31;
     const uint32_t noe_del2 = zero + pack2(-P.oe_del, -P.oe_del);
     const uint32_t noe_ins2 = zero + pack2(-P.oe_ins, -P.oe_ins);
     const uint32_t ne_del2 = zero + pack2(-P.e_del, -P.e_del);
@@ -550,7 +555,7 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
         }
         const int m = mkey >> 16;
         int mj = mkey & 0xffff;
-        if (m > st.max || (m != 0 && st.max - m > P.zdrop)) {
+        if (m > st.max || (m != 0 && st.max - m > zdrop_r)) {
             // (m == 0 ends the pair in bsw_row_update before mj is looked at -- and an empty window leaves
             // mkey = 0, whose "block" would lie in front of this thread's row: compute-sanitizer's racecheck
             // flagged those reads against the neighbouring thread's stores)
@@ -571,7 +576,20 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
             if (mj >= end) mask &= (1u << (end - (mj - 7))) - 1u;
             mj = mj - 7 + hibit(mask);
         }
-        if (bsw_row_update(P, st, i, m, mj)) break;
+        // row epilogue: global max / max_off / z-drop (bsw_row_update, on the register copies of the parameters)
+        if (m == 0) break;
+        if (m > st.max) {
+            st.max = m; st.max_i = i; st.max_j = mj;
+            int d = mj - i; d = d < 0 ? -d : d;
+            st.max_off = st.max_off > d ? st.max_off : d;
+        } else {
+            const int di = i - st.max_i, dj = mj - st.max_j;
+            bool stop;
+            if (zmode_r == 0) stop = st.max - m - (di > dj ? di - dj : dj - di) > zdrop_r;
+            else if (zdrop_r > 0) stop = di > dj ? st.max - m - (di - dj) * P.e_del > zdrop_r : st.max - m - (dj - di) * P.e_ins > zdrop_r;
+            else stop = false;
+            if (stop) break;
+        }
         // next row's window (bandedSWA.cpp:230-233): first non-zero column of [beg, end), then the
         // last non-zero column of [beg', end]
         if (end > beg) {
