@@ -322,6 +322,7 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
     const uint32_t zero = (uint32_t)md.z >> 31;
     const uint32_t eh_sa = eh_sa_in + zero;
     const int zdrop_r = P.zdrop + (int)zero, zmode_r = P.zmode + (int)zero;
+    const int e_del_r = P.e_del + (int)zero, h1_base = h0 - P.o_del + (int)zero;
 
     // ---- first row (bandedSWA.cpp:155-157) and the query plane; the row is initialised up to the
     // end of the block that holds column qlen
@@ -490,7 +491,7 @@ BSW_HD void pair_sweep(const KParams& P, const int4 md, const uint32_t* __restri
         end = end < i + w + 1 ? end : i + w + 1;
         end = end < qlen ? end : qlen;
         int h1 = 0;
-        if (beg == 0) { h1 = h0 - (P.o_del + P.e_del * (i + 1)); h1 = h1 > 0 ? h1 : 0; }
+        if (beg == 0) { h1 = h1_base - e_del_r * (i + 1); h1 = h1 > 0 ? h1 : 0; }
         if (CIRC) {
             // first-row values for the columns this row's last block may reach for the first time
             int need_hi = i + w + 1 < qlen ? i + w + 1 : qlen;
