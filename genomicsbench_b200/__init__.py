@@ -24,7 +24,7 @@ from ._lib import (ABI, ALNREG_DTYPE, ALNREG_FIELDS, BSW_PACKED_MAX_QLEN, BSW_PA
 
 __all__ = [
     "BandedPairWiseSW", "Engine", "BswError", "SEQPAIR_DTYPE", "RESULT_FIELDS", "default_params",
-    "gen_named_config", "gen_pairs", "bucket_order", "partition", "split_by_cost", "read_pairs_file",
+    "gen_named_config", "gen_pairs", "bucket_order", "split_by_cost", "read_pairs_file",
     "write_pairs_file", "load_library", "NAMED_CONFIGS", "pinned_empty", "pinned_copy",
     "SEED_DTYPE", "CHAIN_DTYPE", "ALNREG_DTYPE", "ALNREG_FIELDS", "PackedBatch", "PAIR_DESC_DTYPE", "OUTSCORE_DTYPE",
     "SCORE16_DTYPE", "BSW_PAIR_RAW", "BSW_PACKED_MAX_QLEN", "load_host_library",
@@ -432,15 +432,6 @@ def bucket_order(pairs: np.ndarray) -> np.ndarray:
     if rc:
         raise BswError(rc, "bucket_order")
     return order
-
-
-def partition(pairs: np.ndarray, w: int, n_shards: int):
-    order = np.empty(len(pairs), dtype=np.int64)
-    begin = np.zeros(n_shards + 1, dtype=np.int64)
-    rc = load_library().bsw_partition(ptr(pairs), len(pairs), w, n_shards, ptr(order), ptr(begin))
-    if rc:
-        raise BswError(rc, "partition")
-    return order, begin
 
 
 def split_by_cost(pairs: np.ndarray, w: int, n_shards: int) -> np.ndarray:

@@ -106,7 +106,7 @@ RELEASE_FN = C.CFUNCTYPE(None, C.c_void_p)
 # every symbol include/bsw.h declares: (name, restype, argtypes); HOST_ABI = the subset libbsw_host.so exports too
 _P = C.c_void_p
 _PB = C.POINTER(BswPackedBatch)
-HOST_ABI_NAMES = {"bsw_bucket_order", "bsw_partition", "bsw_split_by_cost", "bsw_gen_named_config", "bsw_gen_bounds", "bsw_gen_pairs",
+HOST_ABI_NAMES = {"bsw_bucket_order", "bsw_split_by_cost", "bsw_gen_named_config", "bsw_gen_bounds", "bsw_gen_pairs",
                   "bsw_count_pairs_file", "bsw_read_pairs_file", "bsw_write_pairs_file", "bsw_batch_from_pairs",
                   "bsw_batch_from_file", "bsw_batch_to_pairs", "bsw_batch_release", "bsw_batch_gen"}
 ABI = [
@@ -139,7 +139,6 @@ ABI = [
     ("bsw_fetch", C.c_int, [_P, _P, C.c_int64]),
     ("bsw_get_stats", C.c_int, [_P, C.POINTER(BswStats)]),
     ("bsw_bucket_order", C.c_int, [_P, C.c_int64, _P]),
-    ("bsw_partition", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     ("bsw_split_by_cost", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P]),
     ("bsw_gen_named_config", C.c_int, [C.c_int32, C.POINTER(BswGenConfig)]),
     ("bsw_gen_bounds", C.c_int, [C.POINTER(BswGenConfig), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -1,4 +1,4 @@
-// bsw_host.cpp -- length bucketing and the multi-GPU partitioner (host side).
+// bsw_host.cpp -- length bucketing and the cost-balanced cut of the multi-GPU partitioner (host side).
 //
 // Replaces, for the new engine:
 //   sortPairsLen / sortPairsId   benchmarks/bsw/bandedSWA.cpp:368-420  (counting sort by len1 in
@@ -131,27 +131,6 @@ static inline int64_t pair_cost(int32_t len1, int32_t len2, int32_t w)
     return (int64_t)len1 * std::min<int64_t>(len2, band) + 64;   // +64: per-pair fixed overhead
 }
 
-// Deals blocks of 1024 consecutive positions of the sorted batch onto n_shards, longest blocks
-// first onto the lightest shard; returns for every shard the list of block numbers (ascending),
-// so each shard stays bucketed and sees a similar length mix.
-void partition_blocks(const SortedBatch& sb, int32_t w, int32_t n_shards, std::vector<std::vector<int64_t>>& blocks_of)
-{
-    const int64_t BLK = 1024;
-    const int64_t nblk = (sb.n + BLK - 1) / BLK;
-    std::vector<int64_t> cost((size_t)n_shards, 0);
-    blocks_of.assign((size_t)n_shards, {});
-    for (int64_t b = nblk - 1; b >= 0; --b) {
-        int64_t c = 0;
-        const int64_t lo = b * BLK, hi = std::min(sb.n, lo + BLK);
-        for (int64_t s = lo; s < hi; ++s) c += pair_cost(sb.len1[s], sb.len2[s], w);
-        int best = 0;
-        for (int g = 1; g < n_shards; ++g) if (cost[g] < cost[best]) best = g;
-        cost[best] += c;
-        blocks_of[best].push_back(b);
-    }
-    for (auto& v : blocks_of) std::reverse(v.begin(), v.end());
-}
-
 } // namespace bsw
 
 using namespace bsw;
@@ -184,27 +163,6 @@ int bsw_split_by_cost(const SeqPair* pairs, int64_t n, int32_t w, int32_t n_shar
         const int64_t k = std::lower_bound(cum.begin(), cum.end(), target) - cum.begin();
         shard_begin[g] = std::max(shard_begin[g - 1], std::min(n, k));
     }
-    return BSW_OK;
-}
-
-int bsw_partition(const SeqPair* pairs, int64_t n, int32_t w, int32_t n_shards,
-                  int64_t* order, int64_t* shard_begin)
-{
-    if (n < 0 || n > 0x7fffffff || n_shards < 1 || !shard_begin || (n > 0 && (!pairs || !order))) return BSW_ERR_PARAM;
-    SortedBatch sb;
-    build_sorted_batch(global_pool(), pairs, n, 0, sb);
-    if (!sb.domain_ok) return BSW_ERR_DOMAIN;
-    std::vector<std::vector<int64_t>> blocks_of;
-    partition_blocks(sb, w, n_shards, blocks_of);
-    int64_t pos = 0;
-    for (int g = 0; g < n_shards; ++g) {
-        shard_begin[g] = pos;
-        for (int64_t b : blocks_of[g]) {
-            const int64_t lo = b * 1024, hi = std::min(n, lo + 1024);
-            for (int64_t s = lo; s < hi; ++s) order[pos++] = sb.idx[s];
-        }
-    }
-    shard_begin[n_shards] = pos;
     return BSW_OK;
 }
 

@@ -311,13 +311,11 @@ int bsw_get_stats(const bsw_engine* eng, bsw_stats* out);
  * contiguous range per device with equal estimated DP cost sum len1*min(len2, 2w+1) (bsw_split_by_cost is that cut,
  * exposed for callers that shard across processes), runs every range on its own host thread through its device's
  * chunk pipeline (length bucketing per chunk, on the device), and every result lands at its pair's input position.
- * bsw_bucket_order / bsw_partition are the host-side utilities for callers that want the global processing order:
- * order[] receives indices into pairs[] sorted by (len2, h0, len1); shard_begin[0..n_shards] receives cut points
- * into order[] that balance the same cost. */
+ * bsw_bucket_order is the host-side mirror of sortPairsLen for callers that want the processing order themselves:
+ * order[] receives indices into pairs[] sorted by (len2, h0, len1).  (Round 1's bsw_partition -- a global bucketing dealt
+ * onto shards in blocks -- lost the comparison against the contiguous cut and is gone.) */
 int bsw_split_by_cost(const SeqPair* pairs, int64_t n_pairs, int32_t w, int32_t n_shards, int64_t* shard_begin);
 int bsw_bucket_order(const SeqPair* pairs, int64_t n_pairs, int64_t* order);
-int bsw_partition(const SeqPair* pairs, int64_t n_pairs, int32_t w, int32_t n_shards,
-                  int64_t* order, int64_t* shard_begin);
 
 /* ---- synthetic-pair generator (the reference has no generator:
  * its inputs come from the dumper tools/bwa/bwamem.c:741-745,788-792) --------- */

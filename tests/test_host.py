@@ -52,18 +52,24 @@ def test_bucket_order_is_sorted_permutation(lib):
 
 
 @pytest.mark.parametrize("shards", [1, 2, 3, 8])
-def test_partition_balanced_and_complete(lib, shards):
-    p, _, _ = lib.gen_pairs(lib.gen_named_config("large"), 0, 60000)
+def test_split_by_cost_balanced_and_contiguous(lib, shards):
+    """The multi-GPU partitioner's cut (replaces the OpenMP batch loop, main_banded.cpp:279-291): contiguous ranges of
+    the input order with equal sum len1 * min(len2, 2w + 1) -- on a batch whose cost is not uniform in input order."""
+    a, _, _ = lib.gen_pairs(lib.gen_named_config("short8"), 0, 40000)
+    b, _, _ = lib.gen_pairs(lib.gen_named_config("long16"), 0, 20000)
+    p = np.zeros(len(a) + len(b), dtype=lib.SEQPAIR_DTYPE)
+    p[:len(a)] = a; p[len(a):] = b
     w = 100
-    order, begin = lib.partition(p, w, shards)
-    assert begin[0] == 0 and begin[-1] == len(p) and (np.diff(begin) >= 0).all()
-    assert np.array_equal(np.sort(order), np.arange(len(p)))
-    cost = p["len1"].astype(np.int64) * np.minimum(p["len2"], 2 * w + 1)
-    per = np.array([cost[order[begin[g]:begin[g + 1]]].sum() for g in range(shards)], dtype=np.float64)
-    assert per.max() / per.mean() < 1.05
-    for g in range(shards):                 # every shard stays bucketed (ascending query length)
-        l2 = p["len2"][order[begin[g]:begin[g + 1]]]
-        assert (np.diff(l2) >= 0).all()
+    begin = lib.split_by_cost(p, w, shards)
+    assert begin[0] == 0 and begin[-1] == len(p) and (np.diff(begin) > 0).all()
+    cost = p["len1"].astype(np.int64) * np.minimum(p["len2"], 2 * w + 1) + 64
+    per = np.add.reduceat(cost, begin[:-1]).astype(np.float64)
+    assert per.max() / per.mean() < 1.01
+    if shards > 1:
+        assert begin[1] > len(p) // shards          # more of the cheap pairs in the first range than an equal count
+    with pytest.raises(lib.BswError):
+        bad = p.copy(); bad["len1"][5] = 0
+        lib.split_by_cost(bad, w, shards)
 
 
 def test_text_format_roundtrip(lib, tmp_path):
