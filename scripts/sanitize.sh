@@ -33,6 +33,21 @@ with gb.Engine() as eng:
     eng.extend(pp, pr, pq, 100)
     assert all(np.array_equal(a[f], pp[f]) for f in gb.RESULT_FIELDS)
     print("short8 stats", eng.stats())
+    # packed route: 2-bit words read in place, RAW pairs, OutScore + 16-byte results; async queue; two device contexts
+    cfg.n_rate = 0.001
+    pairs, ref, qer = gb.gen_pairs(cfg, 0, 90000)
+    want = pairs.copy(); eng.extend(want, ref, qer, 100)
+    batch = gb.PackedBatch.from_pairs(pairs, ref, qer, pinned=True)
+    out = eng.extend_packed(batch, 100); out16 = eng.extend_packed(batch, 100, compact=True)
+    assert all(np.array_equal(out[f], want[f]) and np.array_equal(out16[f], want[f]) for f in gb.RESULT_FIELDS)
+    got = pairs.copy()
+    tk = [eng.extend_async(got[k * 512:(k + 1) * 512], ref, qer, 100) for k in range(20)]
+    [eng.wait(t) for t in tk]
+    assert all(np.array_equal(got[f][:10240], want[f][:10240]) for f in gb.RESULT_FIELDS)
+with gb.Engine(devices=[0, 0]) as eng:
+    out = eng.extend_packed(batch, 100)
+    assert eng.stats()["shards"] == 2 and all(np.array_equal(out[f], want[f]) for f in gb.RESULT_FIELDS)
+    print("packed / async / sharded ok")
 PY
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --log-file gpurun_out/sanitize_$tool.log python /tmp/san_case.py > gpurun_out/sanitize_$tool.out 2>&1
