@@ -38,9 +38,11 @@ struct ChainRun {
     int k = -1;                     // next position in srt, walking down
 };
 
-struct ChainBufs {                  // page-locked, grow-only staging of the left flanks; owned by the engine
+struct ChainBufs {                  // page-locked, grow-only staging of the left / right flanks; owned by the engine
     void* lp = nullptr; void* lq = nullptr; void* lr = nullptr;
     size_t lp_cap = 0, lq_cap = 0, lr_cap = 0;
+    void* rpp = nullptr; void* rq = nullptr; void* rr = nullptr;
+    size_t rpp_cap = 0, rq_cap = 0, rr_cap = 0;
     static bool grow(void*& p, size_t& cap, size_t need)
     {
         if (need <= cap) return true;
@@ -50,13 +52,14 @@ struct ChainBufs {                  // page-locked, grow-only staging of the lef
         if (!p) cap = 0;
         return p != nullptr;
     }
-    ~ChainBufs() { bsw_host_free(lp); bsw_host_free(lq); bsw_host_free(lr); }
+    ~ChainBufs() { bsw_host_free(lp); bsw_host_free(lq); bsw_host_free(lr); bsw_host_free(rpp); bsw_host_free(rq); bsw_host_free(rr); }
 };
 
 struct ChainCand {                  // one seed being extended in the current round
     int64_t chain; int seed;        // seed index inside the chain
     int lpair = -1, rpair = -1;     // positions in the round's left / right batch, -1 = none
     int64_t lq_off = 0, lr_off = 0; // byte offsets of the reversed left flanks in the staging buffers
+    int64_t rq_off = 0, rr_off = 0; // byte offsets of the right flanks' copies (caller's buffers pageable)
     int aw0, aw1;
 };
 
@@ -216,7 +219,6 @@ static int extend_chains_range(bsw_engine* eng, const bsw_chain* chains, int64_t
     bsw_stats total;
     memset(&total, 0, sizeof(total));
     std::vector<ChainCand> cand;
-    std::vector<SeqPair> rp;
     if (!eng->cbufs) eng->cbufs = new ChainBufs();
     ChainBufs& CB = *static_cast<ChainBufs*>(eng->cbufs);
     std::vector<int32_t> band, prev, pick;
@@ -377,8 +379,11 @@ static int extend_chains_range(bsw_engine* eng, const bsw_chain* chains, int64_t
         }
         });
 
-        // ---- right flanks: read in place, h0 = the left score (:765-800) -------------------------
-        size_t n_right = 0;
+        // ---- right flanks, h0 = the left score (:765-800): read in place when the caller's read / window buffers
+        // are page-locked, else copied into page-locked staging like the left flanks -- either way the extension call
+        // takes the engine's direct route (the staged route's host passes cost twice the left flanks' GPU phase)
+        const bool in_place = is_pinned(query) && is_pinned(ref);
+        size_t n_right = 0, rqb = 0, rrb = 0;
         for (ChainCand& cd : cand) {
             const bsw_chain& ch = chains[cd.chain];
             const bsw_seed& s = seeds[ch.seed_first + cd.seed];
@@ -388,8 +393,17 @@ static int extend_chains_range(bsw_engine* eng, const bsw_chain* chains, int64_t
             if (tlen <= 0) continue;
             if (tlen > 32767) { eng->err = "bsw_extend_chains: right reference flank longer than 32767"; return BSW_ERR_DOMAIN; }
             cd.rpair = (int)n_right++;
+            cd.rq_off = (int64_t)rqb; cd.rr_off = (int64_t)rrb;
+            rqb += (size_t)(ch.l_query - (s.qbeg + s.len)); rrb += (size_t)tlen;
         }
-        rp.resize(n_right); prev.resize(n_right);
+        prev.resize(n_right);
+        if (!CB.grow(CB.rpp, CB.rpp_cap, (n_right + 16) * sizeof(SeqPair)) ||
+            (!in_place && (!CB.grow(CB.rq, CB.rq_cap, rqb + 64) || !CB.grow(CB.rr, CB.rr_cap, rrb + 64)))) {
+            eng->err = "bsw_extend_chains: page-locked staging allocation failed";
+            return BSW_ERR_NOMEM;
+        }
+        SeqPair* const rp = static_cast<SeqPair*>(CB.rpp);
+        uint8_t* const rq = static_cast<uint8_t*>(CB.rq); uint8_t* const rr = static_cast<uint8_t*>(CB.rr);
         eng->pool->for_range((int64_t)cand.size(), 1024, [&](int64_t xb, int64_t xe, int) {
             for (int64_t x = xb; x < xe; ++x) {
                 const ChainCand& cd = cand[(size_t)x];
@@ -401,15 +415,22 @@ static int extend_chains_range(bsw_engine* eng, const bsw_chain* chains, int64_t
                 const int64_t re = s.rbeg + s.len - ch.rmax0;
                 SeqPair& sp = rp[(size_t)cd.rpair];
                 memset(&sp, 0, sizeof(sp));
-                sp.idq = ch.query_off + qe; sp.idr = ch.ref_off + re; sp.id = cd.rpair;
+                sp.id = cd.rpair;
                 sp.len2 = ch.l_query - qe; sp.len1 = (int32_t)(ch.rmax1 - ch.rmax0 - re); sp.h0 = a.score;
+                if (in_place) { sp.idq = ch.query_off + qe; sp.idr = ch.ref_off + re; }
+                else {
+                    sp.idq = cd.rq_off; sp.idr = cd.rr_off;
+                    memcpy(rq + cd.rq_off, query + ch.query_off + qe, (size_t)sp.len2);
+                    memcpy(rr + cd.rr_off, ref + ch.ref_off + re, (size_t)sp.len1);
+                }
                 prev[(size_t)cd.rpair] = a.score;
             }
         });
-        if (!rp.empty()) {
-            band.assign(rp.size(), w);
+        if (n_right > 0) {
+            band.assign(n_right, w);
             lap(3);
-            if (int rc = bsw_extend_retry(eng, rp.data(), ref, query, (int64_t)rp.size(), w, max_try, prev.data(), band.data()))
+            if (int rc = bsw_extend_retry(eng, rp, in_place ? ref : rr, in_place ? query : rq, (int64_t)n_right, w, max_try,
+                                          prev.data(), band.data()))
                 return rc;
             add_stats();
             lap(4);
