@@ -11,6 +11,7 @@
 #include <condition_variable>
 #include <functional>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include "../../include/bsw.h"
 
@@ -146,6 +147,56 @@ struct SplitMix64 {
     }
     inline double unit() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
 };
+
+// ---- 2-bit packing (host): 16 bases per 32-bit word, base k of a sequence at bits [2k, 2k+2) of word k / 16 -------
+// 8 base codes (one per byte, little endian in v) -> 16 bits
+inline uint32_t pack8(uint64_t v)
+{
+    v &= 0x0303030303030303ull;
+    v = (v | (v >> 6)) & 0x000F000F000F000Full;
+    v = (v | (v >> 12)) & 0x000000FF000000FFull;
+    return (uint32_t)((v | (v >> 24)) & 0xFFFFu);
+}
+
+// packs len bases into ceil(len / 16) words; returns true when a code above 3 (N) was seen (the words are then unusable).
+// Never reads outside [src, src + len): the last, partial word is taken from the sequence's LAST 8 bytes shifted into
+// place (a byte loop only for sequences shorter than 8).
+inline bool pack_seq(const uint8_t* src, int len, uint32_t* dst)
+{
+    int k = 0, wi = 0;
+    uint64_t high = 0;
+    for (; k + 16 <= len; k += 16, ++wi) {
+        uint64_t a, b;
+        memcpy(&a, src + k, 8); memcpy(&b, src + k + 8, 8);
+        high |= a | b;
+        dst[wi] = pack8(a) | (pack8(b) << 16);
+    }
+    int r = len - k;
+    if (r > 0) {
+        uint32_t wv = 0;
+        int sh = 0;
+        if (r >= 8) {
+            uint64_t a;
+            memcpy(&a, src + k, 8);
+            high |= a;
+            wv = pack8(a);
+            k += 8; r -= 8; sh = 16;
+        }
+        if (r > 0) {
+            if (len >= 8) {
+                uint64_t a;
+                memcpy(&a, src + len - 8, 8);
+                a >>= 8 * (8 - r);                      // the last r bytes, in the low bytes
+                high |= a;
+                wv |= pack8(a) << sh;
+            } else {
+                for (int j = 0; j < r; ++j) { high |= src[k + j]; wv |= (uint32_t)(src[k + j] & 3u) << (2 * j + sh); }
+            }
+        }
+        dst[wi] = wv;
+    }
+    return (high & 0xFCFCFCFCFCFCFCFCull) != 0;
+}
 
 // ---- bucketing (bsw_host.cpp) ----------------------------------------------------------
 // A batch in processing order: position s holds caller index idx[s]; len2/len1/h0 of that

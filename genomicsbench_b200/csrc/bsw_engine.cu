@@ -128,7 +128,9 @@ struct Slot {
     // chunk state
     int64_t a = 0; int n = 0;             // pairs [a, a + n) of the batch
     bool direct = false;
-    bool packed = false;                  // packed route (bsw_extend_packed): desc holds bsw_pair_desc records
+    bool packed = false;                  // packed route (bsw_extend_packed): desc holds bsw_pair_desc records, results leave as OutScore
+    bool src2bit = false;                 // the chunk's sequences arrived as 2-bit words (packed route, or packed by the staged route's host pass)
+    Buf<uint8_t> rawq, rawr;              // staged route: RAW side buffer (pairs with N, long queries), page-locked twin + device copy
     bool use16 = true;                    // this chunk's short pairs run the packed 16-bit kernel
     const uint8_t* q2src = nullptr;       // packed route: device copy of the chunk's 2-bit words (query / reference) ...
     const uint8_t* r2src = nullptr;
@@ -419,7 +421,7 @@ void slot_destroy(Slot& s)
     for (cudaEvent_t e : s.ev_tl) if (e) cudaEventDestroy(e);
     release(s.raw_pairs); release(s.desc); release(s.meta); release(s.res); release(s.perm); release(s.rank);
     release(s.bins); release(s.nlist); release(s.llist); release(s.qpk); release(s.tpk); release(s.scratch);
-    release(s.qraw); release(s.rraw); release(s.outbuf);
+    release(s.qraw); release(s.rraw); release(s.outbuf); release(s.rawq); release(s.rawr);
     if (s.d_info) cudaFree(s.d_info);
     if (s.h_info) cudaFreeHost(s.h_info);
     if (s.d_queue) cudaFree(s.d_queue);
@@ -639,7 +641,151 @@ int packed_info(bsw_engine* eng, DevCtx& c, Slot& s)
 // ------------------------------------------------------------------------------------------
 // stage A+B, staged route: one streaming host pass builds descriptors + gathers the bytes
 // ------------------------------------------------------------------------------------------
+int staged_prepare_bytes(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer);
+
+// Pageable host buffers: the one streaming pass over the caller's memory packs the sequences to 2 bits per base on
+// the way into page-locked staging (the host-side packer of the packed route, bsw_common.h), so the chunk crosses PCIe
+// at ~46 B per short pair instead of 138 and the device needs no pack kernel: it is handed to the 2-bit source path
+// of the packed route (descriptors with word offsets, DP kernels read the words in place).  Pairs that contain N, and
+// queries for the warp-per-pair kernel, keep one byte per base (RAW) in a side buffer.  The latency route (tiny: every
+// pair on the byte-reading warp-per-pair kernel) keeps the byte form of the pass.
 int staged_prepare(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer)
+{
+    static const bool bytes_only = getenv("BSW_STAGED_BYTES") && atoi(getenv("BSW_STAGED_BYTES")) != 0;   // A/B: round-1 form
+    if (s.tiny || bytes_only) return staged_prepare_bytes(eng, s, pairs, seq_ref, seq_qer);
+    const double t0 = now_ms();
+    const SeqPair* P = pairs + s.a;
+    const int n = s.n;
+    const int match = eng->p.match, short_max = eng->short_max;
+    const bool use16 = eng->use16;
+    const int BLK = std::max(256, std::min(4096, n / (2 * eng->pool->size())));
+    const int nblk = (n + BLK - 1) / BLK;
+    struct Sum { uint64_t qw = 0, rw = 0, rq = 0, rr = 0; };       // 2-bit words; RAW bytes of the long queries
+    std::vector<Sum> sums((size_t)nblk + 1);
+    std::vector<ChunkInfo> part((size_t)eng->pool->size());
+    for (ChunkInfo& I : part) init_info(I);
+    // pass 1 (records only): validate, summary, word / byte totals per block
+    eng->pool->run(nblk, [&](int64_t b, int t) {
+        ChunkInfo& I = part[(size_t)t];
+        Sum sm;
+        const int lo = (int)b * BLK, hi = std::min(n, lo + BLK);
+        for (int k = lo; k < hi; ++k) {
+            const SeqPair& sp = P[k];
+            if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.h0 < 0 ||
+                (int64_t)sp.h0 + (int64_t)sp.len2 * match > 32767 || sp.idr < 0 || sp.idq < 0) { I.bad++; continue; }
+            I.nominal += (unsigned long long)sp.len1 * (unsigned long long)sp.len2;
+            I.hist[std::min(sp.len2, LEN_HIST - 1)]++;
+            I.qmax_all = std::max(I.qmax_all, sp.len2);
+            if (sp.len2 <= short_max) {
+                sm.qw += (uint64_t)((sp.len2 + 15) >> 4); sm.rw += (uint64_t)((sp.len1 + 15) >> 4);
+                I.n_short++;
+                I.mn[0] = std::min(I.mn[0], sp.len2); I.mx[0] = std::max(I.mx[0], sp.len2);
+                I.mn[1] = std::min(I.mn[1], sp.h0);   I.mx[1] = std::max(I.mx[1], sp.h0);
+                I.mn[2] = std::min(I.mn[2], sp.len1); I.mx[2] = std::max(I.mx[2], sp.len1);
+                if (use16 && !k16::eligible(match, sp.len2, sp.h0)) I.n_wide++;
+            } else {
+                sm.rq += (uint64_t)sp.len2; sm.rr += (uint64_t)sp.len1;
+            }
+        }
+        sums[(size_t)b + 1] = sm;
+    });
+    ChunkInfo& I = s.info;
+    init_info(I);
+    for (const ChunkInfo& p : part) {
+        I.bad += p.bad; I.nominal += p.nominal; I.n_short += p.n_short; I.n_wide += p.n_wide;
+        I.qmax_all = std::max(I.qmax_all, p.qmax_all);
+        for (int f = 0; f < 3; ++f) { I.mn[f] = std::min(I.mn[f], p.mn[f]); I.mx[f] = std::max(I.mx[f], p.mx[f]); }
+        for (int k = 0; k < LEN_HIST; ++k) I.hist[k] += p.hist[k];
+    }
+    if (I.bad) return BSW_ERR_DOMAIN;
+    for (int b = 0; b < nblk; ++b) {
+        sums[(size_t)b + 1].qw += sums[(size_t)b].qw; sums[(size_t)b + 1].rw += sums[(size_t)b].rw;
+        sums[(size_t)b + 1].rq += sums[(size_t)b].rq; sums[(size_t)b + 1].rr += sums[(size_t)b].rr;
+    }
+    const Sum tot = sums[(size_t)nblk];
+    I.qbases = tot.qw * 16; I.tbases = tot.rw * 16;              // (they size the word arrays of device_prepare)
+    if (tot.qw > 0x3fffffffull || tot.rw > 0x3fffffffull || tot.rq > 0x3fffffffull || tot.rr > 0x3fffffffull) {
+        err_of(eng) = "chunk too large for 32-bit offsets";
+        return BSW_ERR_PARAM;
+    }
+    if (int rc = ensure(eng, s.desc, (size_t)n, true)) return rc;
+    if (int rc = ensure(eng, s.qraw, (size_t)tot.qw * 4 + 64, true)) return rc;
+    if (int rc = ensure(eng, s.rraw, (size_t)tot.rw * 4 + 64, true)) return rc;
+    uint32_t* const q2 = reinterpret_cast<uint32_t*>(s.qraw.h);
+    uint32_t* const r2 = reinterpret_cast<uint32_t*>(s.rraw.h);
+    // pass 2 (sequences, read once): pack, descriptors; pairs with N are remembered
+    std::vector<std::vector<int>> with_n((size_t)eng->pool->size());
+    eng->pool->run(nblk, [&](int64_t b, int t) {
+        Sum o = sums[(size_t)b];
+        const int lo = (int)b * BLK, hi = std::min(n, lo + BLK);
+        for (int k = lo; k < hi; ++k) {
+            const SeqPair& sp = P[k];
+            if (k + 4 < hi) {
+                __builtin_prefetch(seq_qer + P[k + 4].idq, 0, 0);
+                __builtin_prefetch(seq_ref + P[k + 4].idr, 0, 0);
+                __builtin_prefetch(seq_ref + P[k + 4].idr + 64, 0, 0);
+            }
+            if (sp.len2 <= short_max) {
+                const bool nq = pack_seq(seq_qer + sp.idq, sp.len2, q2 + o.qw);
+                const bool nr = pack_seq(seq_ref + sp.idr, sp.len1, r2 + o.rw);
+                s.desc.h[k] = make_int4((int)o.qw, (int)o.rw, sp.len2 | (sp.len1 << 16), sp.h0);
+                if (nq || nr) with_n[(size_t)t].push_back(k);
+                o.qw += (uint64_t)((sp.len2 + 15) >> 4); o.rw += (uint64_t)((sp.len1 + 15) >> 4);
+            } else {
+                s.desc.h[k] = make_int4((int)o.rq, (int)o.rr, sp.len2 | (sp.len1 << 16), sp.h0 | (BSW_PAIR_RAW << 16));
+                o.rq += (uint64_t)sp.len2; o.rr += (uint64_t)sp.len1;
+            }
+        }
+    });
+    // RAW side buffer: the long queries (offsets from pass 1), then the pairs with N
+    uint64_t rq = tot.rq, rr = tot.rr;
+    for (const std::vector<int>& v : with_n) for (int k : v) { rq += (uint64_t)P[k].len2; rr += (uint64_t)P[k].len1; }
+    if (rq > 0x3fffffffull || rr > 0x3fffffffull) { err_of(eng) = "chunk too large for 32-bit offsets"; return BSW_ERR_PARAM; }
+    if (int rc = ensure(eng, s.rawq, (size_t)rq + 64, true)) return rc;
+    if (int rc = ensure(eng, s.rawr, (size_t)rr + 64, true)) return rc;
+    if (tot.rq > 0)
+        eng->pool->run(nblk, [&](int64_t b, int) {
+            const int lo = (int)b * BLK, hi = std::min(n, lo + BLK);
+            for (int k = lo; k < hi; ++k) {
+                const SeqPair& sp = P[k];
+                if (sp.len2 <= short_max) continue;
+                memcpy(s.rawq.h + s.desc.h[k].x, seq_qer + sp.idq, (size_t)sp.len2);
+                memcpy(s.rawr.h + s.desc.h[k].y, seq_ref + sp.idr, (size_t)sp.len1);
+            }
+        });
+    {
+        uint64_t oq = tot.rq, orr = tot.rr;
+        for (const std::vector<int>& v : with_n)
+            for (int k : v) {
+                const SeqPair& sp = P[k];
+                memcpy(s.rawq.h + oq, seq_qer + sp.idq, (size_t)sp.len2);
+                memcpy(s.rawr.h + orr, seq_ref + sp.idr, (size_t)sp.len1);
+                s.desc.h[k] = make_int4((int)oq, (int)orr, sp.len2 | (sp.len1 << 16), sp.h0 | (BSW_PAIR_RAW << 16));
+                oq += (uint64_t)sp.len2; orr += (uint64_t)sp.len1;
+            }
+    }
+    memset(s.rawq.h + rq, 0, 64); memset(s.rawr.h + rr, 0, 64);
+    stats_of(eng).ms_pack += now_ms() - t0;
+    // H2D
+    bsw_info_init<<<1, PREP_BLOCK, 0, s.st>>>(s.d_info);
+    stats_of(eng).kernel_launches++;
+    CUDA_TRY(cudaMemcpyAsync(s.desc.d, s.desc.h, sizeof(int4) * (size_t)n, cudaMemcpyHostToDevice, s.st));
+    if (tot.qw) CUDA_TRY(cudaMemcpyAsync(s.qraw.d, s.qraw.h, (size_t)tot.qw * 4, cudaMemcpyHostToDevice, s.st));
+    if (tot.rw) CUDA_TRY(cudaMemcpyAsync(s.rraw.d, s.rraw.h, (size_t)tot.rw * 4, cudaMemcpyHostToDevice, s.st));
+    if (rq + rr > 0) {
+        CUDA_TRY(cudaMemcpyAsync(s.rawq.d, s.rawq.h, (size_t)rq + 64, cudaMemcpyHostToDevice, s.st));
+        CUDA_TRY(cudaMemcpyAsync(s.rawr.d, s.rawr.h, (size_t)rr + 64, cudaMemcpyHostToDevice, s.st));
+    }
+    s.src2bit = true;
+    s.q2src = s.qraw.d; s.r2src = s.rraw.d; s.q_lo = 0; s.r_lo = 0;
+    s.qbase = s.rawq.d; s.rbase = s.rawr.d;
+    s.seq_on_device = true;
+    stats_of(eng).h2d_bytes += (int64_t)(sizeof(int4) * (size_t)n + (tot.qw + tot.rw) * 4 + (rq + rr ? rq + rr + 128 : 0));
+    return BSW_OK;
+}
+
+// the byte form of the pass (latency route): descriptors + the sequences' bytes gathered into pinned staging
+int staged_prepare_bytes(bsw_engine* eng, Slot& s, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer)
 {
     const double t0 = now_ms();
     const SeqPair* P = pairs + s.a;
@@ -735,7 +881,7 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
     s.n_sorted = I.n_short;
     // (packed route: 2-bit pairs outside the 16-bit kernel's score domain cannot fall back to the byte kernel --
     // the chunk then runs the 32-bit kernel as a whole)
-    s.use16 = eng->use16 && !(s.packed && I.n_wide > 0);
+    s.use16 = eng->use16 && !(s.src2bit && I.n_wide > 0);
     const size_t qwords = (size_t)(I.qbases / 16) + (size_t)I.n_short + 8;
     const size_t twords = (size_t)(I.tbases / 16) + (size_t)I.n_short + 8;
     if (int rc = ensure(eng, s.meta, (size_t)n)) return rc;
@@ -791,7 +937,7 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
             bsw_bucket_scan<<<ntiles, PREP_BLOCK, 0, s.st>>>(s.bins.d, nbins, totals, ticket);
             TL_MARK(2);
             static const bool gather = getenv("BSW_PACKED_GATHER") && atoi(getenv("BSW_PACKED_GATHER")) != 0;   // A/B: re-lay the words in processing order
-            if (s.packed && !gather) {
+            if (s.src2bit && !gather) {
                 // packed route: the DP kernels read the 2-bit words where the host's DMA left them
                 bsw_bucket_scatter<true><<<grid_for(c, n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(
                     s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d, s.meta.d, s.nlist.d, s.d_info, s.q_lo, s.r_lo);
@@ -802,7 +948,7 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
                 bsw_bucket_scatter<false><<<grid_for(c, n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.desc.d, n, K, s.bins.d, totals, s.rank.d, s.perm.d);
                 TL_MARK(3);
                 // 2-bit packing in processing order
-                if (s.packed)
+                if (s.src2bit)
                     bsw_pack_pairs<true><<<grid_for(c, I.n_short, PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(
                         s.desc.d, s.perm.d, I.n_short, s.q2src, s.r2src, s.meta.d, s.qpk.d, s.tpk.d, s.nlist.d, s.d_info, 0, 1,
                         s.q_lo, s.r_lo);
@@ -1113,6 +1259,7 @@ int run_pipeline(bsw_engine* eng, const Job& job, int dev_lo, int ndev, int64_t 
         s.a = cut[(size_t)k]; s.n = (int)(cut[(size_t)k + 1] - cut[(size_t)k]);
         s.direct = direct;
         s.packed = packed;
+        s.src2bit = packed;                                   // (the staged route sets it in its host pass)
         s.tiny = tiny;
         s.st = partitioned ? s.st_svc : s.st_plain;
         if (g_timeline) { if (k == 0) CUDA_TRY(cudaEventRecord(tl_dev.ev_t0, s.st)); s.host_t[0] = now_ms() - tl_host0; }

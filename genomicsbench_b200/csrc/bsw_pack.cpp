@@ -14,31 +14,6 @@ using namespace bsw;
 
 namespace {
 
-// 8 base codes (one per byte, little endian in v) -> 16 bits, base k at bits [2k, 2k+2)
-inline uint32_t pack8(uint64_t v)
-{
-    v &= 0x0303030303030303ull;
-    v = (v | (v >> 6)) & 0x000F000F000F000Full;
-    v = (v | (v >> 12)) & 0x000000FF000000FFull;
-    return (uint32_t)((v | (v >> 24)) & 0xFFFFu);
-}
-
-// packs len bases into ceil(len / 16) words
-inline void pack_seq(const uint8_t* src, int len, uint32_t* dst)
-{
-    int k = 0, wi = 0;
-    for (; k + 16 <= len; k += 16, ++wi) {
-        uint64_t a, b;
-        memcpy(&a, src + k, 8); memcpy(&b, src + k + 8, 8);
-        dst[wi] = pack8(a) | (pack8(b) << 16);
-    }
-    if (k < len) {
-        uint32_t wv = 0;
-        for (int j = 0; k + j < len; ++j) wv |= (uint32_t)(src[k + j] & 3u) << (2 * j);
-        dst[wi] = wv;
-    }
-}
-
 inline void unpack_seq(const uint32_t* src, int len, uint8_t* dst)
 {
     for (int k = 0; k < len; ++k) dst[k] = (uint8_t)((src[k >> 4] >> ((k & 15) * 2)) & 3u);
