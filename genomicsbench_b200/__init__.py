@@ -151,7 +151,7 @@ class Engine:
         return int(r0.value), int(r1.value)
 
     def extend_chains(self, chains: np.ndarray, seeds: np.ndarray, query: np.ndarray, ref: np.ndarray, w: int,
-                      pen_clip5: int = 5, pen_clip3: int = 5, max_band_try: int = 2):
+                      pen_clip5: int = 5, pen_clip3: int = 5, max_band_try: int = 2, out=None):
         """mem_chain2aln for a batch of chains (tools/bwa/bwamem.c:632-822): seed -> left / right pair
         construction, band-doubling retry, local-vs-to-end decision.  chains = CHAIN_DTYPE, seeds = SEED_DTYPE;
         returns (regs ALNREG_DTYPE[len(seeds)], count int32[len(chains)]): the regions of chain c are
@@ -160,8 +160,13 @@ class Engine:
         seeds = np.ascontiguousarray(seeds, dtype=SEED_DTYPE)
         if query.dtype != np.uint8 or ref.dtype != np.uint8 or not query.flags.c_contiguous or not ref.flags.c_contiguous:
             raise ValueError("query / ref must be contiguous uint8 arrays (one base code per byte)")
-        regs = np.zeros(max(len(seeds), 1), dtype=ALNREG_DTYPE)
-        count = np.zeros(max(len(chains), 1), dtype=np.int32)
+        if out is not None:                                  # caller-owned result arrays (reused across calls, like a C caller's)
+            regs, count = out
+            if regs.dtype != ALNREG_DTYPE or count.dtype != np.int32 or len(regs) < len(seeds) or len(count) < len(chains):
+                raise ValueError("out = (regs ALNREG_DTYPE[>= len(seeds)], count int32[>= len(chains)])")
+        else:
+            regs = np.zeros(max(len(seeds), 1), dtype=ALNREG_DTYPE)
+            count = np.zeros(max(len(chains), 1), dtype=np.int32)
         opt = BswChainOpt(w, pen_clip5, pen_clip3, max_band_try)
         self._rc(self._lib.bsw_extend_chains(self._h, ptr(chains), len(chains), ptr(seeds), ptr(query), ptr(ref),
                                              C.byref(opt), ptr(regs), ptr(count)))

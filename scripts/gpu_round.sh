@@ -15,5 +15,5 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_
 timeout 800 python bench.py > $OUT/${TAG}_bench_short8.json 2> $OUT/${TAG}_bench_short8.err; echo "bench rc=$?"; tail -c 400 $OUT/${TAG}_bench_short8.json
 timeout 300 python scripts/chain_bench.py 400 3 2>/dev/null | tail -1 > $OUT/${TAG}_chain_bench.json; cut -c1-200 $OUT/${TAG}_chain_bench.json
 timeout 300 python scripts/global_bench.py 2>/dev/null | tail -1 > $OUT/${TAG}_global_bench.json; cut -c1-200 $OUT/${TAG}_global_bench.json
-bash scripts/gpu_ncu.sh $TAG "short8:11 long16:1 large:5 sweep_w100_z100:5 sweep_w500_z100:3" > $OUT/${TAG}_ncu.log 2>&1
+bash scripts/gpu_ncu.sh $TAG "${NCU_SPEC:-short8:11 long16:1 large:5 sweep_w100_z100:5 sweep_w500_z100:3}" > $OUT/${TAG}_ncu.log 2>&1
 du -sh $OUT
