@@ -130,6 +130,7 @@ struct Slot {
     bool direct = false;
     bool packed = false;                  // packed route (bsw_extend_packed): desc holds bsw_pair_desc records, results leave as OutScore
     bool src2bit = false;                 // the chunk's sequences arrived as 2-bit words (packed route, or packed by the staged route's host pass)
+    Buf<uint8_t> tinybuf;                 // latency route: one block {queue word | descriptors | query bytes | reference bytes}
     Buf<uint8_t> rawq, rawr;              // staged route: RAW side buffer (pairs with N, long queries), page-locked twin + device copy
     bool use16 = true;                    // this chunk's short pairs run the packed 16-bit kernel
     const uint8_t* q2src = nullptr;       // packed route: device copy of the chunk's 2-bit words (query / reference) ...
@@ -197,6 +198,7 @@ struct bsw_engine {
     void* gbufs = nullptr;                // device buffers of bsw_global (GlobalBufs, bsw_global.inl)
     bool global_attr_set = false;
     void* cbufs = nullptr;                // page-locked staging of bsw_extend_chains (ChainBufs, bsw_chain.inl)
+    bool cells_counted = false;           // the last run summed its effective cells itself (latency route): no device counters to collect
     void* clanes = nullptr;               // child engines of bsw_extend_chains' lanes (ChainLanes, bsw_chain.inl)
     void* aq = nullptr;                   // queue + worker of bsw_extend_async (AsyncQueue, bsw_async.inl)
     std::once_flag aq_once;
@@ -421,7 +423,7 @@ void slot_destroy(Slot& s)
     for (cudaEvent_t e : s.ev_tl) if (e) cudaEventDestroy(e);
     release(s.raw_pairs); release(s.desc); release(s.meta); release(s.res); release(s.perm); release(s.rank);
     release(s.bins); release(s.nlist); release(s.llist); release(s.qpk); release(s.tpk); release(s.scratch);
-    release(s.qraw); release(s.rraw); release(s.outbuf); release(s.rawq); release(s.rawr);
+    release(s.qraw); release(s.rraw); release(s.outbuf); release(s.rawq); release(s.rawr); release(s.tinybuf);
     if (s.d_info) cudaFree(s.d_info);
     if (s.h_info) cudaFreeHost(s.h_info);
     if (s.d_queue) cudaFree(s.d_queue);
@@ -1167,6 +1169,72 @@ const char* kDomainMsg =
 
 struct ChunkRef { int dev; int slot; };
 
+// The latency route: a call too small to fill the machine one pair per thread (bsw_params.tiny_batch; the reference
+// driver's habit is 512 pairs per call, scripts/run-cpu.sh:30).  One host pass validates the pairs and gathers
+// descriptors and sequence bytes into ONE page-locked block, whose first word is the kernel's work-queue counter
+// (the copy that brings the data also zeroes it); one copy in, the warp-per-pair kernel on every pair (rows in shared
+// memory), one copy out, one synchronisation: 4 CUDA calls per call instead of ~15, which is what bounds T driver
+// threads (the runtime serialises API calls per process).  Returns 1 when the call does not fit this route.
+int run_tiny(bsw_engine* eng, const Job& job, int dev_index, int64_t a0, int64_t n64)
+{
+    DevCtx& c = eng->devs[(size_t)dev_index];
+    bsw_stats& S = stats_of(eng);
+    const int n = (int)n64;
+    const SeqPair* P = job.pairs + a0;
+    const int match = eng->p.match;
+    uint64_t qtot = 0, rtot = 0, nominal = 0;
+    int qmax = 0;
+    for (int k = 0; k < n; ++k) {
+        const SeqPair& sp = P[k];
+        if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.h0 < 0 ||
+            (int64_t)sp.h0 + (int64_t)sp.len2 * match > 32767 || sp.idr < 0 || sp.idq < 0) {
+            err_of(eng) = kDomainMsg;
+            return BSW_ERR_DOMAIN;
+        }
+        qtot += (uint64_t)sp.len2; rtot += (uint64_t)sp.len1;
+        nominal += (uint64_t)sp.len1 * (uint64_t)sp.len2;
+        qmax = std::max(qmax, sp.len2);
+    }
+    const int long_stride = (qmax + 12) & ~3;
+    const size_t row_bytes = (size_t)LONG_WARPS * (size_t)long_stride * sizeof(uint32_t);
+    if (row_bytes > 48 * 1024 || qtot + rtot > (64u << 20)) return 1;      // very long queries: the general route
+    CUDA_TRY(cudaSetDevice(c.dev));
+    Slot* sp0 = nullptr;
+    if (int rc = get_slot(eng, c, 0, &sp0)) return rc;
+    Slot& s = *sp0;
+    const size_t off_desc = 64, off_q = off_desc + sizeof(int4) * (size_t)n;
+    const size_t off_r = (off_q + qtot + 64 + 15) & ~(size_t)15, total = off_r + rtot + 64;
+    if (int rc = ensure(eng, s.tinybuf, total, true)) return rc;
+    if (int rc = ensure(eng, s.res, (size_t)n, true)) return rc;
+    uint8_t* const hb = s.tinybuf.h;
+    memset(hb, 0, 64);                                                      // the queue counter (and padding)
+    int4* const hd = reinterpret_cast<int4*>(hb + off_desc);
+    uint64_t q = 0, r = 0;
+    for (int k = 0; k < n; ++k) {
+        const SeqPair& sp = P[k];
+        memcpy(hb + off_q + q, job.seq_qer + sp.idq, (size_t)sp.len2);
+        memcpy(hb + off_r + r, job.seq_ref + sp.idr, (size_t)sp.len1);
+        hd[k] = make_int4((int)q, (int)r, sp.len2 | (sp.len1 << 16), sp.h0);
+        q += (uint64_t)sp.len2; r += (uint64_t)sp.len1;
+    }
+    memset(hb + off_q + qtot, 0, 64); memset(hb + off_r + rtot, 0, 64);
+    cudaStream_t st = s.st_plain;
+    CUDA_TRY(cudaMemcpyAsync(s.tinybuf.d, hb, total, cudaMemcpyHostToDevice, st));
+    const int blocks = std::max(1, std::min((n + LONG_WARPS - 1) / LONG_WARPS, c.sms * 8));
+    bsw_long_kernel<true><<<blocks, LONG_WARPS * 32, row_bytes, st>>>(
+        reinterpret_cast<const int4*>(s.tinybuf.d + off_desc), nullptr, s.tinybuf.d + off_q, s.tinybuf.d + off_r, s.res.d, n, eng->kp,
+        nullptr, long_stride, reinterpret_cast<unsigned int*>(s.tinybuf.d), nullptr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(s.res.h, s.res.d, sizeof(int4) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    SeqPair* out = job.pairs + a0;
+    int64_t cells = 0;
+    for (int k = 0; k < n; ++k) { write_result(out[k], s.res.h[k]); cells += s.res.h[k].w; }
+    S.cells_nominal += (int64_t)nominal; S.cells_effective += cells; S.kernel_launches += 1; S.n_long += n;
+    S.h2d_bytes += (int64_t)total; S.d2h_bytes += (int64_t)sizeof(int4) * n;
+    return BSW_OK;
+}
+
 // Runs the chunks of the batch through the pipeline.  keep == true: stop before the DP launches
 // and keep every chunk resident in its own slot (bsw_stage).
 //
@@ -1203,6 +1271,7 @@ int run_pipeline(bsw_engine* eng, const Job& job, int dev_lo, int ndev, int64_t 
     }
     S.partitioned = partitioned ? 1 : 0;
     const bool tiny = !keep && !packed && eng->p.tiny_batch > 0 && n <= eng->p.tiny_batch;
+
     // chunk boundaries: a small first chunk (the first DP starts after a short H2D), full-size
     // chunks, then -- where transfers or the host bound the batch -- a geometric ramp-down so that the
     // work left after the last H2D (its DP and its D2H) is small.  PCIe-bound batches use smaller full-size chunks, sized so that the DP of one
@@ -1399,6 +1468,14 @@ inline double pair_cost(int len1, int len2, int w)
 int run_sharded(bsw_engine* eng, const Job& job, int64_t n, int64_t chunk_pairs)
 {
     const int ndev = (int)eng->devs.size();
+    eng->cells_counted = false;
+    if (!job.pb && eng->p.tiny_batch > 0 && n <= eng->p.tiny_batch) {
+        static const bool fused = !(getenv("BSW_TINY_FUSED") && atoi(getenv("BSW_TINY_FUSED")) == 0);     // A/B: 0 = the chunk pipeline's latency route
+        if (fused) {
+            const int rc = run_tiny(eng, job, 0, 0, n);
+            if (rc != 1) { eng->stats.shards = 1; eng->cells_counted = true; return rc; }      // (the results carried their cell counts)
+        }
+    }
     if (int rc = zero_cells(eng)) return rc;
     static const bool deal = getenv("BSW_MULTI") && std::string(getenv("BSW_MULTI")) == "deal";
     eng->stats.shards = 1;
@@ -1642,7 +1719,7 @@ int bsw_extend(bsw_engine* eng, SeqPair* pairs, const uint8_t* seq_ref, const ui
         rc = run_sharded(eng, job, n, CHUNK_EXTEND);
     }
     if (rc != BSW_OK) { quiesce(eng); return rc; }
-    if (int rc2 = collect_cells(eng)) return rc2;
+    if (!eng->cells_counted) if (int rc2 = collect_cells(eng)) return rc2;
     eng->stats.ms_total = now_ms() - t_begin;
     return BSW_OK;
 }

@@ -383,14 +383,14 @@ bsw_long_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ perm
     uint32_t* const eh = SMEM ? long_rows + (size_t)(threadIdx.x >> 5) * scratch_stride
                               : scratch + (size_t)gwarp * scratch_stride;
     const int e_ins4 = 4 * P.e_ins;
-    long long my_cells = 0;
+    long long my_cells = 0, pair_cells0 = 0;
 
     for (;;) {
         unsigned k = 0;
         if (lane == 0) k = atomicAdd(queue, 1u);
         k = __shfl_sync(FULL, k, 0);
         if (k >= (unsigned)count) break;
-        const int s = (int)perm[k];
+        const int s = perm ? (int)perm[k] : (int)k;       // (no list: every pair of the call, in input order -- the latency route)
         const int4 md = meta[s];
         const int qlen = md.z & 0xffff, tlen = (md.z >> 16) & 0xffff, h0 = md.w & 0xffff;
         const uint8_t* qb = qbytes + (ptrdiff_t)md.x;     // signed: sequences are read in place
@@ -527,10 +527,15 @@ bsw_long_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ perm
                 end = min(j + 2, qlen);
             }
         }
-        if (lane == 0) res[s] = bsw_pack_result(st);
+        if (lane == 0) {
+            int4 r = bsw_pack_result(st);
+            if (!cell_counter) { r.w = (int)(my_cells - pair_cells0); }   // latency route: the pair's effective cells travel with its result
+            res[s] = r;
+        }
+        pair_cells0 = my_cells;
         __syncwarp();
     }
-    if (lane == 0 && my_cells) atomicAdd(cell_counter, (unsigned long long)my_cells);
+    if (lane == 0 && my_cells && cell_counter) atomicAdd(cell_counter, (unsigned long long)my_cells);
 }
 
 // ---------------------------------------------------------------------------------------
