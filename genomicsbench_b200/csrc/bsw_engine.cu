@@ -128,6 +128,7 @@ struct Slot {
     // chunk state
     int64_t a = 0; int n = 0;             // pairs [a, a + n) of the batch
     bool direct = false;
+    bool out_records = false;             // direct route: results leave inside the records' device copy (one DMA, no host pass); else 16 B per pair + a host pass
     bool packed = false;                  // packed route (bsw_extend_packed): desc holds bsw_pair_desc records, results leave as OutScore
     bool src2bit = false;                 // the chunk's sequences arrived as 2-bit words (packed route, or packed by the staged route's host pass)
     Buf<uint8_t> tinybuf;                 // latency route: one block {queue word | descriptors | query bytes | reference bytes}
@@ -887,7 +888,7 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
     const size_t qwords = (size_t)(I.qbases / 16) + (size_t)I.n_short + 8;
     const size_t twords = (size_t)(I.tbases / 16) + (size_t)I.n_short + 8;
     if (int rc = ensure(eng, s.meta, (size_t)n)) return rc;
-    if (int rc = ensure(eng, s.res, (size_t)n, !s.direct)) return rc;
+    if (int rc = ensure(eng, s.res, (size_t)n, !s.out_records)) return rc;
     if (int rc = ensure(eng, s.qpk, qwords)) return rc;
     if (int rc = ensure(eng, s.tpk, twords)) return rc;
     if (int rc = ensure(eng, s.perm, (size_t)n)) return rc;
@@ -1107,7 +1108,7 @@ int output_chunk(bsw_engine* eng, DevCtx& c, Slot& s, const Job& job)
             stats_of(eng).kernel_launches++;
             stats_of(eng).d2h_bytes += (int64_t)sizeof(OutScore) * s.n;
         }
-    } else if (s.direct) {
+    } else if (s.out_records) {
         // results go into the device copy of the records, which then returns by one DMA (the
         // input fields come back as they left; per-field writes over PCIe would be 4-byte TLPs)
         bsw_writeback<<<grid_for(c, s.n, 2 * PREP_BLOCK), PREP_BLOCK, 0, s.st>>>(s.res.d, s.n, reinterpret_cast<SeqPair*>(s.raw_pairs.d));
@@ -1133,7 +1134,7 @@ inline void write_result(SeqPair& sp, const int4 v)
 // staged route: second streaming pass, results into the caller's records
 void unpack_chunk(bsw_engine* eng, Slot& s, SeqPair* pairs)
 {
-    if (s.direct) return;
+    if (s.out_records || s.packed) return;
     const double t0 = now_ms();
     SeqPair* P = pairs + s.a;
     const int4* r = s.res.h;
@@ -1249,6 +1250,9 @@ int run_pipeline(bsw_engine* eng, const Job& job, int dev_lo, int ndev, int64_t 
     const uint8_t* const seq_qer = job.seq_qer;
     const bool packed = job.pb != nullptr;
     const bool direct = packed || (!job.force_staged && is_pinned(pairs) && is_pinned(seq_ref) && is_pinned(seq_qer));
+    // direct route, way out: the records' device copy with the six fields filled in (72 B per pair, no host pass), or
+    // BSW_DIRECT_OUT=results: the 16-byte results + the staged route's host pass into the caller's records
+    static const bool out_records = !(getenv("BSW_DIRECT_OUT") && std::string(getenv("BSW_DIRECT_OUT")) == "results");
     // PCIe-bound or compute-bound?  A sample of the records gives DP time (nominal cells at the
     // resident kernel rate) against transfer time (record + sequence bytes at PCIe rate) per pair.
     // PCIe-bound batches run partitioned: chunk streams on the service SMs, DP on the rest.
@@ -1327,6 +1331,7 @@ int run_pipeline(bsw_engine* eng, const Job& job, int dev_lo, int ndev, int64_t 
         Slot& s = *sp;
         s.a = cut[(size_t)k]; s.n = (int)(cut[(size_t)k + 1] - cut[(size_t)k]);
         s.direct = direct;
+        s.out_records = direct && !packed && out_records;
         s.packed = packed;
         s.src2bit = packed;                                   // (the staged route sets it in its host pass)
         s.tiny = tiny;
@@ -1907,8 +1912,8 @@ int bsw_fetch(bsw_engine* eng, SeqPair* pairs, int64_t n)
     for (auto& ds : eng->staged_chunks) {
         DevCtx& c = eng->devs[(size_t)ds.first]; Slot& s = c.slots[(size_t)ds.second];
         CUDA_TRY(cudaSetDevice(c.dev));
-        s.direct = pinned_out && s.direct;           // the record DMA needs the chunk's device copy
-        if (!s.direct) if (int rc = ensure(eng, s.res, (size_t)s.n, true)) return rc;
+        s.out_records = pinned_out && s.direct && s.out_records;      // the record DMA needs the chunk's device copy
+        if (!s.out_records) if (int rc = ensure(eng, s.res, (size_t)s.n, true)) return rc;
         Job job;
         job.pairs = pairs;
         if (int rc = output_chunk(eng, c, s, job)) return rc;
