@@ -185,7 +185,7 @@ static int extend_chains_range(bsw_engine* eng, const bsw_chain* chains, int64_t
     const bsw_params& P = eng->p;
     std::vector<ChainRun> run((size_t)n_chains);
     std::vector<int64_t> groups;                                // first chain of every read (chains of a read are adjacent)
-    int64_t n_seeds_total = 0;
+    int64_t n_seeds_total = 0, seed_lo = INT64_MAX;
     for (int64_t c = 0; c < n_chains; ++c) {
         const bsw_chain& ch = chains[c];
         out_count[c] = 0;
@@ -196,14 +196,18 @@ static int extend_chains_range(bsw_engine* eng, const bsw_chain* chains, int64_t
             return BSW_ERR_PARAM;
         }
         n_seeds_total = std::max(n_seeds_total, ch.seed_first + ch.n_seeds);
+        seed_lo = std::min(seed_lo, ch.seed_first);
     }
-    std::vector<uint64_t> srt_all((size_t)n_seeds_total);       // every chain sorts its own slice [seed_first, + n_seeds)
+    // every chain sorts its own slice [seed_first, + n_seeds); only the span this range of chains uses is allocated
+    // (a lane of a large batch sees a fraction of the seeds)
+    if (n_chains == 0) seed_lo = 0;
+    std::unique_ptr<uint64_t[]> srt_all(new uint64_t[(size_t)std::max<int64_t>(n_seeds_total - seed_lo, 1)]);
     std::atomic<int> bad_seed{0};
     eng->pool->for_range(n_chains, 1024, [&](int64_t cb, int64_t ce, int) {
         for (int64_t c = cb; c < ce; ++c) {
             const bsw_chain& ch = chains[c];
             ChainRun& R = run[(size_t)c];
-            R.srt = srt_all.data() + ch.seed_first;
+            R.srt = srt_all.get() + (ch.seed_first - seed_lo);
             for (int i = 0; i < ch.n_seeds; ++i) {
                 const bsw_seed& s = seeds[ch.seed_first + i];
                 if (s.len < 1 || s.qbeg < 0 || s.qbeg + s.len > ch.l_query || s.score < 1 || s.rbeg < ch.rmax0 ||

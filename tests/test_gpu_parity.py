@@ -159,6 +159,11 @@ def test_latency_route_matches_reference_golden(lib, case):
         st = eng.stats()
         assert np.array_equal(results_matrix(a), expect)
         assert st["n_long"] == len(pairs) and st["n_short"] == 0          # every pair took the warp-per-pair kernel
+        assert st["kernel_launches"] == 1                                 # the fused latency route: one kernel, 4 CUDA calls
+        with lib.Engine(**params) as plain:                               # same effective cells as the throughput route counts
+            b = pairs.copy()
+            plain.extend(b, ref, qer, w)
+            assert plain.stats()["cells_effective"] == st["cells_effective"] > 0
         pp, pr, pq = lib.pinned_copy(pairs), lib.pinned_copy(ref), lib.pinned_copy(qer)
         eng.extend(pp, pr, pq, w)
         assert np.array_equal(results_matrix(pp), expect)
