@@ -19,3 +19,15 @@ timeout 600 $TR --master-port 29611 bench.py --impl reference --gpus $N --steps 
 tail -c 400 $OUT/${TAG}_bench_ref_n$N.json
 timeout 600 $TR --master-port 29612 bench.py --gpus $N --steps 20 --warmup 3 > $OUT/${TAG}_bench_short8_n$N.json 2> $OUT/${TAG}_bench_short8_n$N.err
 tail -c 1500 $OUT/${TAG}_bench_short8_n$N.json; tail -5 $OUT/${TAG}_bench_short8_n$N.err
+# A/B at N ranks: the direct route's way out (records DMA vs 16-byte results + host pass) where the host fabric bounds e2e
+BSW_DIRECT_OUT=results timeout 300 $TR --master-port 29613 bench.py --gpus $N --steps 10 --warmup 3 --no-split-legs --no-cpu-baseline \
+    > $OUT/${TAG}_bench_short8_n${N}_out_results.json 2> /dev/null
+python - <<PY
+import json
+for tag in ("", "_out_results"):
+    try:
+        d = json.loads(open("$OUT/${TAG}_bench_short8_n$N%s.json" % tag).read().strip().splitlines()[-1])
+        print("e2e drop-in%s: %.1f GCUPS %.2f ms/step; packed %.1f GCUPS" % (tag, d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["packed"]["value"]))
+    except Exception as e:
+        print("no line", tag, e)
+PY
