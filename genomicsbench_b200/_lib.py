@@ -39,7 +39,8 @@ class BswParams(C.Structure):
         ("zdrop", C.c_int32), ("end_bonus", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32),
         ("ambig", C.c_int32), ("zdrop_mode", C.c_int32), ("n_devices", C.c_int32),
         ("devices", C.c_int32 * 16), ("host_threads", C.c_int32), ("long_min_qlen", C.c_int32),
-        ("short_variant", C.c_int32), ("tiny_batch", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("short_variant", C.c_int32), ("tiny_batch", C.c_int32), ("warp_max_pairs", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 

@@ -22,6 +22,7 @@
 #include "bsw_common.h"
 #include "bsw_kernels.cuh"
 #include "bsw_kernel16.cuh"
+#include "bsw_warp16.cuh"
 #include "bsw_prep.cuh"
 #include "bsw_global.cuh"
 #include <cstdio>
@@ -41,6 +42,9 @@ namespace {
 
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
 constexpr int SHORT_MAX_QLEN = 824;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
+constexpr int WARP_BLOCK = 128;           // threads per block of the warp-per-pair register kernel (bsw_warp16.cuh): 4 pairs
+// default bsw_params.warp_max_pairs: calls of at most this many pairs run their short pairs one per WARP (see warp_ok)
+constexpr int WARP_MAX_PAIRS = 4096;
 constexpr int NSTREAMS = 16;              // DP compute streams per device (one shared-memory class each, run concurrently)
 constexpr int NSLOTS = 8;                 // chunks in flight per device (records ahead / prepare / compute / drain, + slack before a slot is reused)
 constexpr int64_t CHUNK_EXTEND = 1 << 18; // largest chunk of bsw_extend (overlap vs bucketing quality)
@@ -98,6 +102,7 @@ struct Launch {
     int block;            // threads (= pairs) per block: 64, or 32 where that keeps more warps resident
     int wcols = 0;        // packed kernel: columns of the circular row (then qstride = wcols + 4), 0 = the row holds the whole query
     int plane = 0;        // packed kernel: query stride that sizes the 2-bit query plane (= qstride unless circular)
+    bool warp = false;    // the warp-per-pair register kernel (queries <= w16::MAX_QLEN)
 };
 
 template <class T>
@@ -141,6 +146,7 @@ struct Slot {
     unsigned int q_lo = 0, r_lo = 0;      // ... and the batch word offset of its first word
     Buf<uint8_t> outbuf;                  // packed route: OutScore records on their way out
     bool tiny = false;                    // latency route: every pair goes to the warp-per-pair kernel (run_pipeline)
+    bool warp_ok = false;                 // the whole call is small enough for the warp-per-pair kernel (tail chunks of a large call are not)
     bool seq_on_device = false;           // both sequence buffers are device copies with >= 64 bytes of slack behind them
     const uint8_t* qbase = nullptr;       // device-visible address of descriptor offset 0 (query / reference)
     const uint8_t* rbase = nullptr;
@@ -296,6 +302,17 @@ inline int bits_for(uint32_t range)      // bits needed to hold values 0..range
     return b;
 }
 
+// A call of n pairs runs its short pairs (queries <= w16::MAX_QLEN) one per warp?  One thread sweeps a 151-bp pair in
+// ~0.4 ms whatever the batch, so a call that leaves most schedulers without a warp is bound by that latency; the
+// warp-per-pair register kernel (bsw_warp16.cuh) pays several times the instructions per cell for a row swept by 32
+// lanes.  bsw_params.warp_max_pairs moves the crossover (-1: never).
+bool warp_ok(const bsw_engine* eng, int64_t n)
+{
+    if (!eng->use16 || eng->p.warp_max_pairs < 0 || n <= 0) return false;
+    if (7 * eng->kp.e_ins > 32767) return false;                // the per-column decay of an entering F must fit 16 bits
+    return n <= (eng->p.warp_max_pairs > 0 ? eng->p.warp_max_pairs : WARP_MAX_PAIRS);
+}
+
 int set_kernel_attrs(bsw_engine* eng, DevCtx& c)
 {
     if (c.attr_set) return BSW_OK;
@@ -368,6 +385,7 @@ int validate_params(const bsw_params* p, std::string& why)
     if (p->long_min_qlen < 0) return bad("long_min_qlen must be >= 0");
     if (p->short_variant != BSW_SHORT_PACKED16 && p->short_variant != BSW_SHORT_WIDE32) return bad("short_variant");
     if (p->tiny_batch < 0) return bad("tiny_batch must be >= 0");
+    if (p->warp_max_pairs < -1) return bad("warp_max_pairs must be >= -1");
     return BSW_OK;
 }
 
@@ -993,6 +1011,22 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
                 pos += cnt;
             }
             if (s.use16) for (Launch& L : s.plan) L.block = short16_block(L.qstride, L.plane, L.wcols != 0);
+            // a call too small to fill the machine one pair per thread: the classes with queries <= w16::MAX_QLEN (a prefix
+            // of the processing order) become one launch of the warp-per-pair register kernel
+            if (s.use16 && s.warp_ok && pos > 0 && I.mn[0] <= w16::MAX_QLEN) {
+                int cnt = 0;
+                for (int l = I.mn[0]; l <= std::min(I.mx[0], w16::MAX_QLEN); ++l) cnt += (int)I.hist[l];
+                size_t k = 0;
+                while (k < s.plan.size() && s.plan[k].first + s.plan[k].count <= cnt) ++k;
+                if (k < s.plan.size() && s.plan[k].first < cnt) {            // a merged class straddles the limit: cut it
+                    s.plan[k].count -= cnt - s.plan[k].first;
+                    s.plan[k].first = cnt;
+                }
+                s.plan.erase(s.plan.begin(), s.plan.begin() + (std::ptrdiff_t)k);
+                Launch L{0, cnt, 0, WARP_BLOCK};
+                L.warp = true;
+                s.plan.insert(s.plan.begin(), L);
+            }
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -1006,6 +1040,18 @@ int device_prepare(bsw_engine* eng, DevCtx& c, Slot& s)
     stats_of(eng).kernel_launches++;
     CUDA_TRY(cudaEventRecord(s.ev_lists, s.st));
     return BSW_OK;
+}
+
+void launch_warp(bsw_engine* eng, cudaStream_t st, const int4* meta, const uint32_t* perm, const uint32_t* qseq,
+                 const uint32_t* tseq, int4* res, int first, int count, unsigned long long* cells)
+{
+    constexpr int PAIRS = WARP_BLOCK / 32;
+    const int grid = (count + PAIRS - 1) / PAIRS;
+    const size_t smem = w16::MASK_BYTES + (size_t)PAIRS * w16::SCORE_BYTES;
+    if (eng->kp.oe_del == eng->kp.oe_ins)
+        bsw_warp16_kernel<WARP_BLOCK, true><<<grid, WARP_BLOCK, smem, st>>>(meta, perm, qseq, tseq, res, first, count, eng->kp, cells);
+    else
+        bsw_warp16_kernel<WARP_BLOCK, false><<<grid, WARP_BLOCK, smem, st>>>(meta, perm, qseq, tseq, res, first, count, eng->kp, cells);
 }
 
 // DP launches of a chunk: fan out over the device's compute streams (those of the DP partition
@@ -1024,7 +1070,9 @@ int launch_dp(bsw_engine* eng, DevCtx& c, Slot& s, bool partitioned = false)
         const Launch& L = s.plan[(size_t)k];
         cudaStream_t st = cs[li % NSTREAMS];
         const int grid = (L.count + L.block - 1) / L.block;
-        if (s.use16) {
+        if (L.warp) {
+            launch_warp(eng, st, s.meta.d, s.perm.d, s.dp_q, s.dp_t, s.res.d, L.first, L.count, c.d_cells);
+        } else if (s.use16) {
             const bool sg = eng->kp.oe_del == eng->kp.oe_ins;
             const size_t smem = k16::smem_bytes(L.block, L.qstride, L.plane);
 #define BSW_LAUNCH16(B, SG, CIRC)                                                                                     \
@@ -1203,6 +1251,46 @@ int run_tiny(bsw_engine* eng, const Job& job, int dev_index, int64_t a0, int64_t
     Slot* sp0 = nullptr;
     if (int rc = get_slot(eng, c, 0, &sp0)) return rc;
     Slot& s = *sp0;
+    // Queries of at most 255 bases: the warp-per-pair register kernel (bsw_warp16.cuh) on 2-bit words packed by the host
+    // pass.  A call with an N or a pair outside the 16-bit score domain keeps the byte route below.
+    if (qmax <= w16::MAX_QLEN && warp_ok(eng, n)) {
+        if (int rc = set_kernel_attrs(eng, c)) return rc;
+        const size_t off_desc = 64, off_q = off_desc + sizeof(int4) * (size_t)n;
+        const size_t qwords = (size_t)(qtot / 16) + (size_t)n + 4, twords = (size_t)(rtot / 16) + (size_t)n + 4;
+        const size_t off_t = off_q + 4 * qwords;
+        if (int rc = ensure(eng, s.tinybuf, off_t + 4 * twords, true)) return rc;
+        if (int rc = ensure(eng, s.res, (size_t)n, true)) return rc;
+        uint8_t* const hb = s.tinybuf.h;
+        int4* const hd = reinterpret_cast<int4*>(hb + off_desc);
+        uint32_t* const hq = reinterpret_cast<uint32_t*>(hb + off_q);
+        uint32_t* const ht = reinterpret_cast<uint32_t*>(hb + off_t);
+        uint32_t q = 0, r = 0;
+        bool plain = true;
+        for (int k = 0; k < n && plain; ++k) {
+            const SeqPair& sp = P[k];
+            if (!k16::eligible(match, sp.len2, sp.h0)) { plain = false; break; }
+            if (pack_seq(job.seq_qer + sp.idq, sp.len2, hq + q) | pack_seq(job.seq_ref + sp.idr, sp.len1, ht + r)) { plain = false; break; }
+            hd[k] = make_int4((int)q, (int)r, sp.len2 | (sp.len1 << 16), sp.h0);
+            q += (uint32_t)(sp.len2 + 15) >> 4; r += (uint32_t)(sp.len1 + 15) >> 4;
+        }
+        if (plain) {
+            cudaStream_t st = s.st_plain;
+            const size_t h2d = off_t + 4 * (size_t)r;
+            CUDA_TRY(cudaMemcpyAsync(s.tinybuf.d, hb, h2d, cudaMemcpyHostToDevice, st));
+            launch_warp(eng, st, reinterpret_cast<const int4*>(s.tinybuf.d + off_desc), nullptr,
+                        reinterpret_cast<const uint32_t*>(s.tinybuf.d + off_q), reinterpret_cast<const uint32_t*>(s.tinybuf.d + off_t),
+                        s.res.d, 0, n, nullptr);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(s.res.h, s.res.d, sizeof(int4) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            SeqPair* out = job.pairs + a0;
+            int64_t cells = 0;
+            for (int k = 0; k < n; ++k) { write_result(out[k], s.res.h[k]); cells += s.res.h[k].w; }
+            S.cells_nominal += (int64_t)nominal; S.cells_effective += cells; S.kernel_launches += 1; S.n_short += n;
+            S.h2d_bytes += (int64_t)h2d; S.d2h_bytes += (int64_t)sizeof(int4) * n;
+            return BSW_OK;
+        }
+    }
     const size_t off_desc = 64, off_q = off_desc + sizeof(int4) * (size_t)n;
     const size_t off_r = (off_q + qtot + 64 + 15) & ~(size_t)15, total = off_r + rtot + 64;
     if (int rc = ensure(eng, s.tinybuf, total, true)) return rc;
@@ -1335,6 +1423,7 @@ int run_pipeline(bsw_engine* eng, const Job& job, int dev_lo, int ndev, int64_t 
         s.packed = packed;
         s.src2bit = packed;                                   // (the staged route sets it in its host pass)
         s.tiny = tiny;
+        s.warp_ok = warp_ok(eng, n);
         s.st = partitioned ? s.st_svc : s.st_plain;
         if (g_timeline) { if (k == 0) CUDA_TRY(cudaEventRecord(tl_dev.ev_t0, s.st)); s.host_t[0] = now_ms() - tl_host0; }
         CUDA_TRY(cudaEventRecord(s.ev_k0, s.st));

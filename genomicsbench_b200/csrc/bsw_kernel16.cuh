@@ -221,7 +221,7 @@ BSW_HD int hibit(uint32_t x)
 #endif
 }
 
-// a << s with s in 0..63: 0 from 32 on (PTX shl clamps the amount; C++ << does not)
+// a << s: 0 for s >= 32 and for negative s (PTX shl takes the amount as unsigned and clamps it; C++ << does not)
 BSW_HD uint32_t shl_sat(uint32_t a, int s)
 {
 #if defined(__CUDA_ARCH__)
@@ -229,7 +229,7 @@ BSW_HD uint32_t shl_sat(uint32_t a, int s)
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(s));
     return r;
 #else
-    return s >= 32 ? 0u : a << s;
+    return (unsigned)s >= 32u ? 0u : a << s;
 #endif
 }
 BSW_HD int imax0(int a) { return a > 0 ? a : 0; }

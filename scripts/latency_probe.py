@@ -14,9 +14,11 @@ want = allp.copy()
 with gb.Engine() as e0:
     e0.extend(want, ref, qer, 100)
 
+CPP_ONLY = os.environ.get("LAT_CPP_ONLY", "") not in ("", "0")       # LAT_CPP_ONLY=1: only the C++ probe at the end
+
 print("sync, one thread (pageable buffers):")
 sw = gb.BandedPairWiseSW(6, 1, 6, 1, 100, 5, None, 1, 4, 1, devices=[0])
-for n in (512, 4096, 16384, 65536):
+for n in (512, 2048, 4096, 16384, 65536):
     pairs = allp[:n].copy()
     for _ in range(5): sw.getScores16(pairs, ref, qer, n, 1, 100)
     t0 = time.perf_counter(); reps = 30
@@ -52,11 +54,11 @@ def run(T, depth, rounds):
     return pairs / dt / 1e6, calls / max(batches, 1), ok
 
 print("blocking submit + wait per 512-pair call (C++ drop-in route), T threads:")
-for T in (1, 2, 4, 8, 16, 32):
+for T in (() if CPP_ONLY else (1, 2, 4, 8, 16, 32)):
     r, cf, ok = run(T, 1, 60)
     print(f"  T={T:3d}            {r:7.2f} M pairs/s   calls per batch {cf:5.1f}   results ok {ok}")
 print("async, T threads x D calls in flight:")
-for T, D in ((1, 8), (8, 2), (8, 4), (8, 8), (16, 4)):
+for T, D in (() if CPP_ONLY else ((1, 8), (8, 2), (8, 4), (8, 8), (16, 4))):
     r, cf, ok = run(T, D, 30)
     print(f"  T={T:3d} D={D:2d}       {r:7.2f} M pairs/s   calls per batch {cf:5.1f}   results ok {ok}")
 

@@ -7,22 +7,24 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
-SO = HERE / "libk16_emu.so"
-SRC = HERE / "k16_emu.cu"
-DEPS = [SRC, ROOT / "genomicsbench_b200/csrc/bsw_kernel16.cuh", ROOT / "genomicsbench_b200/csrc/bsw_kernels.cuh"]
+CSRC = ROOT / "genomicsbench_b200/csrc"
+DEPS = [CSRC / "bsw_kernel16.cuh", CSRC / "bsw_kernels.cuh", CSRC / "bsw_warp16.cuh"]
 
 
-def build(force: bool = False) -> Path:
-    if not force and SO.exists() and all(SO.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
-        return SO
+def build(force: bool = False, name: str = "k16") -> Path:
+    """name = "k16" (thread-per-pair sweep) or "w16" (warp-per-pair register sweep, the lanes as coroutines)."""
+    so, src = HERE / f"lib{name}_emu.so", HERE / f"{name}_emu.cu"
+    if not force and so.exists() and all(so.stat().st_mtime >= d.stat().st_mtime for d in DEPS + [src]):
+        return so
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-shared",
-           "-Xcompiler", "-fPIC,-fopenmp", "-I", str(ROOT / "include"), "-o", str(SO), str(SRC), "-lgomp"]
+           "-Xcompiler", "-fPIC,-fopenmp,-pthread", "-I", str(ROOT / "include"), "-o", str(so), str(src), "-lgomp", "-lpthread"]
     env = dict(os.environ)
     env["PATH"] = "/usr/bin:" + env.get("PATH", "")
     subprocess.run(cmd, check=True, env=env)
-    return SO
+    return so
 
 
 if __name__ == "__main__":
     print(build(force=True))
+    print(build(force=True, name="w16"))

@@ -19,10 +19,12 @@ def out_matrix(out):
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_packed_matches_reference_golden(lib, case):
+@pytest.mark.parametrize("warp_max_pairs", [-1, 0])
+def test_packed_matches_reference_golden(lib, case, warp_max_pairs):
+    """warp_max_pairs = -1: the thread-per-pair kernel; 0 (default): batches this small run the warp-per-pair register kernel."""
     pairs, ref, qer, w, params, expect, _ = load_golden(case)
     b = lib.PackedBatch.from_pairs(pairs, ref, qer)
-    with lib.Engine(**params) as eng:
+    with lib.Engine(warp_max_pairs=warp_max_pairs, **params) as eng:
         out = eng.extend_packed(b, w)
         st = eng.stats()
         out16 = eng.extend_packed(b, w, compact=True)

@@ -14,10 +14,13 @@ def engine_kwargs(params, **extra):
     return dict(params, **extra)
 
 
+# bsw_params.warp_max_pairs: -1 = the thread-per-pair kernel whatever the batch size, 0 = the default (calls this small
+# run their queries of up to 255 bases on the warp-per-pair register kernel, bsw_warp16.cuh)
+@pytest.mark.parametrize("warp_max_pairs", [-1, 0])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_cuda_matches_reference_golden(lib, case):
+def test_cuda_matches_reference_golden(lib, case, warp_max_pairs):
     pairs, ref, qer, w, params, expect, _ = load_golden(case)
-    with lib.Engine(**engine_kwargs(params)) as eng:
+    with lib.Engine(**engine_kwargs(params, warp_max_pairs=warp_max_pairs)) as eng:
         eng.extend(pairs, ref, qer, w)
         st = eng.stats()
     got = results_matrix(pairs)
@@ -118,9 +121,11 @@ SWEEP = [
 ]
 
 
+@pytest.mark.parametrize("warp_max_pairs", [-1, 1 << 20])
 @pytest.mark.parametrize("idx", range(len(SWEEP)))
-def test_cuda_matches_oracle_on_seeded_inputs(lib, oracle, idx):
+def test_cuda_matches_oracle_on_seeded_inputs(lib, oracle, idx, warp_max_pairs):
     name, over, sc, w, n = SWEEP[idx]
+    sc = dict(sc)
     cfg = lib.gen_named_config(name)
     cfg.seed = 0x5EED0000 + idx
     for k, v in over.items():
@@ -128,7 +133,9 @@ def test_cuda_matches_oracle_on_seeded_inputs(lib, oracle, idx):
     pairs, ref, qer = lib.gen_pairs(cfg, 0, n)
     want = pairs.copy()
     cells = oracle.batch(make_params(**sc), want, ref, qer, w)
-    with lib.Engine(**sc) as eng:
+    # warp_max_pairs = 2^20: every plain pair with a query of up to 255 bases on the warp-per-pair register kernel,
+    # whatever the batch size; -1: none
+    with lib.Engine(**sc, warp_max_pairs=warp_max_pairs) as eng:
         eng.extend(pairs, ref, qer, w)
         st = eng.stats()
     a, b = results_matrix(pairs), results_matrix(want)
@@ -153,13 +160,22 @@ def test_latency_route_matches_reference_golden(lib, case):
     reference driver's -b 512 batches).  Same results, on pageable and on page-locked buffers."""
     pairs, ref, qer, w, params, expect, _ = load_golden(case)
     pairs = pairs[:1200].copy(); expect = expect[:1200]
-    with lib.Engine(tiny_batch=1536, **params) as eng:
+    with lib.Engine(tiny_batch=1536, warp_max_pairs=-1, **params) as eng:
         a = pairs.copy()
         eng.extend(a, ref, qer, w)
         st = eng.stats()
         assert np.array_equal(results_matrix(a), expect)
-        assert st["n_long"] == len(pairs) and st["n_short"] == 0          # every pair took the warp-per-pair kernel
+        assert st["n_long"] == len(pairs) and st["n_short"] == 0          # every pair took the 32-bit warp-per-pair kernel
         assert st["kernel_launches"] == 1                                 # the fused latency route: one kernel, 4 CUDA calls
+    with lib.Engine(tiny_batch=1536, **params) as eng:
+        # default: a call of plain pairs (no N, scores within 16 bits, queries <= 255) runs the warp-per-pair REGISTER
+        # kernel on 2-bit words packed by the host pass; any other call the kernel above.  One kernel either way.
+        a = pairs.copy()
+        eng.extend(a, ref, qer, w)
+        st = eng.stats()
+        assert np.array_equal(results_matrix(a), expect)
+        assert (st["n_long"], st["n_short"]) == ((0, len(pairs)) if case in ("small_151bp", "tiny_w3") else (len(pairs), 0))
+        assert st["kernel_launches"] == 1
         with lib.Engine(**params) as plain:                               # same effective cells as the throughput route counts
             b = pairs.copy()
             plain.extend(b, ref, qer, w)
