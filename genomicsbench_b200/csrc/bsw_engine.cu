@@ -25,6 +25,7 @@
 #include "bsw_warp16.cuh"
 #include "bsw_prep.cuh"
 #include "bsw_global.cuh"
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -43,7 +44,8 @@ namespace {
 constexpr int SHORT_BLOCK = 64;           // threads (= pairs) per block of the short kernel
 constexpr int SHORT_MAX_QLEN = 824;       // eh words + query byte plane of SHORT_BLOCK threads must fit 227 KB
 constexpr int WARP_BLOCK = 128;           // threads per block of the warp-per-pair register kernel (bsw_warp16.cuh): 4 pairs
-// default bsw_params.warp_max_pairs: calls of at most this many pairs run their short pairs one per WARP (see warp_ok)
+// default bsw_params.warp_max_pairs: pairs a device runs one per WARP at any moment, all calls and engines of the process
+// together (see WarpLease)
 constexpr int WARP_MAX_PAIRS = 4096;
 constexpr int NSTREAMS = 16;              // DP compute streams per device (one shared-memory class each, run concurrently)
 constexpr int NSLOTS = 8;                 // chunks in flight per device (records ahead / prepare / compute / drain, + slack before a slot is reused)
@@ -302,14 +304,48 @@ inline int bits_for(uint32_t range)      // bits needed to hold values 0..range
     return b;
 }
 
-// A call of n pairs runs its short pairs (queries <= w16::MAX_QLEN) one per warp?  One thread sweeps a 151-bp pair in
+// May a call of n pairs run its short pairs (queries <= w16::MAX_QLEN) one per warp?  One thread sweeps a 151-bp pair in
 // ~0.4 ms whatever the batch, so a call that leaves most schedulers without a warp is bound by that latency; the
-// warp-per-pair register kernel (bsw_warp16.cuh) pays several times the instructions per cell for a row swept by 32
-// lanes.  bsw_params.warp_max_pairs moves the crossover (-1: never).
-bool warp_ok(const bsw_engine* eng, int64_t n)
+// warp-per-pair register kernel (bsw_warp16.cuh) sweeps it in ~0.14 ms, at ~10 x the issue slots per cell.  That pays
+// while the GPU has issue slots to spare: measured (profiles/r03c_warp_probe.json, r03d_latency_ab.txt) up to ~4 000
+// 151-bp pairs in flight on the device -- one call of that size, or eight of the driver's 512-pair calls; beyond that
+// the issue rate bounds them all and the thread-per-pair kernel serves more pairs per second.  So the pairs on the
+// warp kernel are a per-device budget (bsw_params.warp_max_pairs; -1: never), shared by every call and engine of
+// the process: a call takes its share for as long as it runs, or runs thread-per-pair.
+std::atomic<int64_t> g_warp_pairs[64];           // per CUDA device: pairs of running calls that took the warp kernel
+
+struct WarpLease {
+    int dev = -1;
+    int64_t n = 0;
+    WarpLease() = default;
+    WarpLease(const WarpLease&) = delete;
+    WarpLease& operator=(const WarpLease&) = delete;
+    ~WarpLease() { release(); }
+    bool acquire(const bsw_engine* eng, int cuda_dev, int64_t pairs, int e_ins, bool use16, int32_t limit_param)
+    {
+        (void)eng;
+        if (!use16 || limit_param < 0 || pairs <= 0 || cuda_dev < 0 || cuda_dev >= 64) return false;
+        if (7 * e_ins > 32767) return false;                    // the per-column decay of an entering F must fit 16 bits
+        const int64_t limit = limit_param > 0 ? limit_param : WARP_MAX_PAIRS;
+        std::atomic<int64_t>& g = g_warp_pairs[cuda_dev];
+        int64_t cur = g.load(std::memory_order_relaxed);
+        do {
+            if (cur + pairs > limit) return false;
+        } while (!g.compare_exchange_weak(cur, cur + pairs, std::memory_order_relaxed));
+        dev = cuda_dev; n = pairs;
+        return true;
+    }
+    void release()
+    {
+        if (dev >= 0) g_warp_pairs[dev].fetch_sub(n, std::memory_order_relaxed);
+        dev = -1; n = 0;
+    }
+};
+
+// the static part of the rule, for a batch that stays resident (bsw_stage): no lease is held between its runs
+bool warp_fits(const bsw_engine* eng, int64_t n)
 {
-    if (!eng->use16 || eng->p.warp_max_pairs < 0 || n <= 0) return false;
-    if (7 * eng->kp.e_ins > 32767) return false;                // the per-column decay of an entering F must fit 16 bits
+    if (!eng->use16 || eng->p.warp_max_pairs < 0 || n <= 0 || 7 * eng->kp.e_ins > 32767) return false;
     return n <= (eng->p.warp_max_pairs > 0 ? eng->p.warp_max_pairs : WARP_MAX_PAIRS);
 }
 
@@ -1253,7 +1289,7 @@ int run_tiny(bsw_engine* eng, const Job& job, int dev_index, int64_t a0, int64_t
     Slot& s = *sp0;
     // Queries of at most 255 bases: the warp-per-pair register kernel (bsw_warp16.cuh) on 2-bit words packed by the host
     // pass.  A call with an N or a pair outside the 16-bit score domain keeps the byte route below.
-    if (qmax <= w16::MAX_QLEN && warp_ok(eng, n)) {
+    if (qmax <= w16::MAX_QLEN && eng->use16 && eng->p.warp_max_pairs >= 0 && 7 * eng->kp.e_ins <= 32767) {
         if (int rc = set_kernel_attrs(eng, c)) return rc;
         const size_t off_desc = 64, off_q = off_desc + sizeof(int4) * (size_t)n;
         const size_t qwords = (size_t)(qtot / 16) + (size_t)n + 4, twords = (size_t)(rtot / 16) + (size_t)n + 4;
@@ -1277,9 +1313,25 @@ int run_tiny(bsw_engine* eng, const Job& job, int dev_index, int64_t a0, int64_t
             cudaStream_t st = s.st_plain;
             const size_t h2d = off_t + 4 * (size_t)r;
             CUDA_TRY(cudaMemcpyAsync(s.tinybuf.d, hb, h2d, cudaMemcpyHostToDevice, st));
-            launch_warp(eng, st, reinterpret_cast<const int4*>(s.tinybuf.d + off_desc), nullptr,
-                        reinterpret_cast<const uint32_t*>(s.tinybuf.d + off_q), reinterpret_cast<const uint32_t*>(s.tinybuf.d + off_t),
-                        s.res.d, 0, n, nullptr);
+            const int4* const d_desc = reinterpret_cast<const int4*>(s.tinybuf.d + off_desc);
+            const uint32_t* const d_q = reinterpret_cast<const uint32_t*>(s.tinybuf.d + off_q);
+            const uint32_t* const d_t = reinterpret_cast<const uint32_t*>(s.tinybuf.d + off_t);
+            // a warp per pair while the device's budget of such pairs lasts (WarpLease), else the thread-per-pair kernel on
+            // the same words: 0.4 ms per call instead of 0.14, but next to no load on a GPU whose issue rate is the bound
+            WarpLease lease;
+            if (!lease.acquire(eng, c.dev, n, eng->kp.e_ins, eng->use16, eng->p.warp_max_pairs)) {
+                const int qs = stride_for(qmax, true);
+                const int block = short16_block(qs, qs, false);
+                const int grid = (n + block - 1) / block;
+                const size_t smem = k16::smem_bytes(block, qs, qs);
+                const bool sg = eng->kp.oe_del == eng->kp.oe_ins;
+#define BSW_LAUNCH16T(B, SG) bsw_short16_kernel<B, SG, false><<<grid, B, smem, st>>>(d_desc, nullptr, d_q, d_t, s.res.d, 0, n, qs, eng->kp, nullptr, 0)
+                if (block == 32) { if (sg) BSW_LAUNCH16T(32, true); else BSW_LAUNCH16T(32, false); }
+                else { if (sg) BSW_LAUNCH16T(64, true); else BSW_LAUNCH16T(64, false); }
+#undef BSW_LAUNCH16T
+            } else {
+                launch_warp(eng, st, d_desc, nullptr, d_q, d_t, s.res.d, 0, n, nullptr);
+            }
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemcpyAsync(s.res.h, s.res.d, sizeof(int4) * (size_t)n, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -1363,6 +1415,11 @@ int run_pipeline(bsw_engine* eng, const Job& job, int dev_lo, int ndev, int64_t 
     }
     S.partitioned = partitioned ? 1 : 0;
     const bool tiny = !keep && !packed && eng->p.tiny_batch > 0 && n <= eng->p.tiny_batch;
+    // short pairs one per warp (bsw_warp16.cuh)?  A call on one device takes its pairs out of the device's budget for as
+    // long as it runs; a resident batch (its runs come later) and a batch dealt over several devices go by size alone
+    WarpLease warp_lease;
+    const bool warp_pairs = (keep || ndev != 1) ? warp_fits(eng, n)
+        : warp_lease.acquire(eng, eng->devs[(size_t)dev_lo].dev, n, eng->kp.e_ins, eng->use16, eng->p.warp_max_pairs);
 
     // chunk boundaries: a small first chunk (the first DP starts after a short H2D), full-size
     // chunks, then -- where transfers or the host bound the batch -- a geometric ramp-down so that the
@@ -1423,7 +1480,7 @@ int run_pipeline(bsw_engine* eng, const Job& job, int dev_lo, int ndev, int64_t 
         s.packed = packed;
         s.src2bit = packed;                                   // (the staged route sets it in its host pass)
         s.tiny = tiny;
-        s.warp_ok = warp_ok(eng, n);
+        s.warp_ok = warp_pairs;
         s.st = partitioned ? s.st_svc : s.st_plain;
         if (g_timeline) { if (k == 0) CUDA_TRY(cudaEventRecord(tl_dev.ev_t0, s.st)); s.host_t[0] = now_ms() - tl_host0; }
         CUDA_TRY(cudaEventRecord(s.ev_k0, s.st));

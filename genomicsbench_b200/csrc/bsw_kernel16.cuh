@@ -665,6 +665,8 @@ BSW_HD int circ_cols(int w) { return (2 * w + 16 + 7) & ~7; }
 #if defined(__CUDACC__)
 // qstride = words per thread row; wcols = 0, or the columns of the circular row (then qstride = wcols + 4: the
 // padding keeps qstride / 4 odd, i.e. the 128-bit accesses of a quarter warp in distinct bank groups)
+// perm == nullptr: results in input order; cell_counter == nullptr: a result's .w carries the pair's effective cells
+// (both: the latency route under load, run_tiny)
 template <int BLOCK, bool SAMEGAP, bool CIRC = false>
 __global__ void __launch_bounds__(BLOCK)
 bsw_short16_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ perm,
@@ -688,9 +690,12 @@ bsw_short16_kernel(const int4* __restrict__ meta, const uint32_t* __restrict__ p
             PairState st;
             k16::pair_sweep<SAMEGAP, CIRC>(P, md, qseq + (uint32_t)md.x, tseq + (uint32_t)md.y, eh_sa, qp_sa, BLOCK * 2u,
                                            tab_sa, st, my_cells, (uint32_t)wcols);
-            res[perm[first + local]] = bsw_pack_result(st);
+            int4 r = bsw_pack_result(st);
+            if (!cell_counter) r.w = (int)my_cells;
+            res[perm ? perm[first + local] : (uint32_t)(first + local)] = r;
         }
     }
+    if (!cell_counter) return;
     for (int off = 16; off > 0; off >>= 1) my_cells += __shfl_down_sync(0xffffffffu, my_cells, off);
     if ((tid & 31) == 0 && my_cells) atomicAdd(cell_counter, (unsigned long long)my_cells);
 }

@@ -85,6 +85,8 @@ BandedPairWiseSW::BandedPairWiseSW(const int o_del, const int e_del, const int o
     params_.mismatch = w_mismatch;         // positive penalty; the reference negates it at :66
     params_.ambig = DEFAULT_AMBIG;         // vector code hard-wires -1 (:69) and ignores `mat`
     params_.tiny_batch = 1536;             // the driver feeds -b 512 pairs per call (scripts/run-cpu.sh:30): latency route
+    // experiments (scripts/latency_probe.py): BSW_SHIM_WARP_MAX = bsw_params.warp_max_pairs
+    if (const char* e = getenv("BSW_SHIM_WARP_MAX")) params_.warp_max_pairs = atoi(e);
     memset(&stats_, 0, sizeof(stats_));
     // The reference constructs its objects before its timed region (main_banded.cpp:253-258, timing starts at :272):
     // bring the shared engine and its coalescing queue up here, not inside the first getScores16 call.  Best effort:

@@ -78,10 +78,13 @@ typedef struct bsw_params {
                                              memory), ~2x lower latency for batches that cannot fill the GPU one pair
                                              per thread; 0 = off (default).  The BandedPairWiseSW class sets 1536: the
                                              reference driver's habit is -b 512 (scripts/run-cpu.sh:30)              */
-    int32_t warp_max_pairs;               /* calls of at most this many pairs run their short pairs (queries <= 255, no N,
-                                             16-bit scores) one per WARP, the row in registers (bsw_warp16.cuh): a call too
-                                             small to fill the GPU one pair per thread is bound by one thread's time for
-                                             one pair (~0.4 ms at 151 bp).  0 = default (4096), -1 = never            */
+    int32_t warp_max_pairs;               /* pairs a device runs one per WARP at any moment (queries <= 255, no N, 16-bit
+                                             scores; the row in registers, bsw_warp16.cuh): a call too small to fill the
+                                             GPU one pair per thread is bound by one thread's time for one pair (~0.4 ms
+                                             at 151 bp; a warp: ~0.14 ms, at ~10 x the issue slots).  The budget is shared
+                                             by all calls and engines of the process: a call that fits takes its share
+                                             while it runs, any other runs thread-per-pair.  0 = default (4096),
+                                             -1 = never                                                               */
     int32_t reserved[4];
 } bsw_params;
 

@@ -6,6 +6,7 @@
 #include "bandedSWA.h"
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <omp.h>
@@ -40,7 +41,7 @@ int main(int argc, char** argv)
         return true;
     };
     printf("blocking getScores16, %d pairs per call, T threads (one BandedPairWiseSW per thread), %lld pairs per pass:\n", B, (long long)n);
-    for (int T : {1, 2, 4, 8, 16, 32}) {
+    for (int T : {1, 2, 4, 8, 16, 32, 64}) {
         std::vector<BandedPairWiseSW*> sw((size_t)T);
         for (int t = 0; t < T; ++t) sw[(size_t)t] = new BandedPairWiseSW(6, 1, 6, 1, 100, 5, mat, 1, 4, 1);
         std::vector<SeqPair> got = pairs;
@@ -61,6 +62,7 @@ int main(int argc, char** argv)
         fflush(stdout);
         for (auto* p : sw) delete p;
     }
+    if (getenv("LAT_BLOCKING_ONLY")) return 0;
     printf("bsw_extend_async, %d pairs per call, T threads x D calls in flight:\n", B);
     bsw_params P;
     bsw_default_params(&P);

@@ -71,5 +71,8 @@ if os.path.exists(BIN):
         with open(path, "wb") as f:
             f.write(struct.pack("<3q", len(allp), len(ref), len(qer)))
             f.write(allp.tobytes()); f.write(ref.tobytes()); f.write(qer.tobytes())
-        print("\nC++ (scripts/latency_probe.cpp):", flush=True)
-        subprocess.run([BIN, path])
+        # LAT_ENVS="A=1 B=2;C=3": one run of the C++ probe per ';'-separated environment (A/B of the shim's switches)
+        for envs in os.environ.get("LAT_ENVS", "").split(";"):
+            extra = dict(kv.split("=", 1) for kv in envs.split() if "=" in kv)
+            print(f"\nC++ (scripts/latency_probe.cpp) {extra if extra else ''}:", flush=True)
+            subprocess.run([BIN, path], env=dict(os.environ, **extra))

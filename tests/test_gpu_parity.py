@@ -176,6 +176,13 @@ def test_latency_route_matches_reference_golden(lib, case):
         assert np.array_equal(results_matrix(a), expect)
         assert (st["n_long"], st["n_short"]) == ((0, len(pairs)) if case in ("small_151bp", "tiny_w3") else (len(pairs), 0))
         assert st["kernel_launches"] == 1
+    with lib.Engine(tiny_batch=1536, warp_max_pairs=1, **params) as eng:
+        # ... and, when the device's budget of warp-per-pair pairs is taken (here: a budget of one pair), the thread-per-pair
+        # kernel on the same words
+        a = pairs.copy()
+        eng.extend(a, ref, qer, w)
+        assert np.array_equal(results_matrix(a), expect)
+        assert eng.stats()["cells_effective"] == st["cells_effective"] and eng.stats()["kernel_launches"] == 1
         with lib.Engine(**params) as plain:                               # same effective cells as the throughput route counts
             b = pairs.copy()
             plain.extend(b, ref, qer, w)
