@@ -21,6 +21,7 @@ for wl, n in (("short8", 1_000_000), ("long16", 1_000_000)):
             vals = [float(x) for x in m.group(3).split("|")]
             tot += sum(vals) * UNIT[m.group(2)]
             launches = len(vals)
-    out[wl] = {"dram_bytes_per_step": tot, "launches": launches, "pairs_per_gpu": n, "source": f"profiles/{f.name}"}
+    out[wl] = {**out.get(wl, {}), "dram_bytes_per_step": tot, "launches": launches, "pairs_per_gpu": n,
+               "source": f"profiles/{f.name}"}        # (keeps the hand-added warm-L2 / gathered figures and the note)
 out_path.write_text(json.dumps(out, indent=1) + "\n")
 print(json.dumps(out, indent=1))
