@@ -1,0 +1,168 @@
+"""bsw_global's second kernel (csrc/bsw_global2.cuh: rows in band coordinates, 16-bit slots, 4-bit directions) and its
+chunk planner (csrc/bsw_global_plan.h) executed on the CPU (tests/emu/g2_emu.cu) and compared with the goldens the
+reference's own ksw_global2 produced (tools/bwa/ksw.c:502-606) and with the oracle on seeded sweeps -- scores and
+CIGARs bit for bit, in both slot widths, across chunk cuts and launch classes."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import make_params
+from test_global import GLOBAL_CASES, load_global_case
+
+SEQPAIR = np.dtype([("idr", "<i8"), ("idq", "<i8"), ("id", "<i8"), ("len1", "<i4"), ("len2", "<i4"), ("h0", "<i4"),
+                    ("seqid", "<i4"), ("regid", "<i4"), ("score", "<i4"), ("tle", "<i4"), ("gtle", "<i4"), ("qle", "<i4"),
+                    ("gscore", "<i4"), ("max_off", "<i4"), ("pad", "<i4")])
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from emu.build import build
+    lib = C.CDLL(str(build(name="g2")))
+    lib.g2_emu_global.restype = C.c_int
+    lib.g2_emu_global.argtypes = [C.c_void_p] * 4 + [C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong] + \
+        [C.c_void_p] * 3 + [C.c_longlong, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def test_seqpair_layout_matches_header():
+    import genomicsbench_b200._lib as L
+    assert SEQPAIR.itemsize == 72 == L.SEQPAIR_DTYPE.itemsize
+    for f in ("idr", "idq", "len1", "len2"):
+        assert SEQPAIR.fields[f][1] == L.SEQPAIR_DTYPE.fields[f][1]
+
+
+def run_emu(lib, P: dict, len1, len2, target, query, w, rows=0, caps_m=0, caps_z=0):
+    n = len(len1)
+    pairs = np.zeros(n, dtype=SEQPAIR)
+    pairs["len1"], pairs["len2"] = len1, len2
+    pairs["idr"] = np.concatenate([[0], np.cumsum(len1)[:-1]]) if n else []
+    pairs["idq"] = np.concatenate([[0], np.cumsum(len2)[:-1]]) if n else []
+    prm = np.array([P["o_del"], P["e_del"], P["o_ins"], P["e_ins"], P["match"], P["mismatch"], P["ambig"]], dtype=np.int32)
+    w = np.ascontiguousarray(np.broadcast_to(np.asarray(w, dtype=np.int32), (n,)))
+    score = np.zeros(n, np.int32); ncig = np.zeros(n, np.int32); off = np.zeros(n + 1, np.int64)
+    cap = int((pairs["len1"].astype(np.int64) + pairs["len2"]).sum()) + 1
+    cigar = np.zeros(cap, np.uint32); info = np.zeros(5, np.int64)
+    target = np.ascontiguousarray(target, dtype=np.uint8); query = np.ascontiguousarray(query, dtype=np.uint8)
+    rc = lib.g2_emu_global(prm.ctypes.data, pairs.ctypes.data, target.ctypes.data, query.ctypes.data, n, w.ctypes.data, rows,
+                           caps_m, caps_z, score.ctypes.data, ncig.ctypes.data, cigar.ctypes.data, cap, off.ctypes.data,
+                           info.ctypes.data)
+    return rc, score, ncig, cigar[: off[n]], off, info
+
+
+@pytest.mark.parametrize("rows", [16, 32])
+@pytest.mark.parametrize("case", GLOBAL_CASES)
+def test_emulated_kernel_matches_reference_golden(emu, case, rows):
+    c = load_global_case(case); z = c["z"]
+    rc, score, ncig, cigar, off, info = run_emu(emu, c["P"], z["len1"], z["len2"], z["target"], z["query"], z["w"], rows=rows)
+    assert rc == 0
+    assert np.array_equal(score, z["score"])
+    assert np.array_equal(ncig, z["n_cigar"]) and np.array_equal(np.diff(off), z["n_cigar"])
+    assert np.array_equal(cigar, z["cigar"])
+    assert info[0] == 1 and info[1] >= 1 and info[2] == (rows == 16) and info[4] == 0
+
+
+def test_emulated_default_choice_and_chunk_cuts(emu):
+    """The engine's own choice of slot width; chunks cut by the alignment cap and by the direction-matrix cap (whole
+    ranges, and alignment by alignment when a range alone is too much) all give the same answer."""
+    c = load_global_case("global_default"); z = c["z"]
+    tile = 7                                   # 4 900 alignments: three ranges of the planner
+    args = (c["P"], np.tile(z["len1"], tile), np.tile(z["len2"], tile), np.tile(z["target"], tile), np.tile(z["query"], tile),
+            np.tile(z["w"], tile))
+    want = (np.tile(z["score"], tile), np.tile(z["cigar"], tile))
+    for kw, chunks in ((dict(), 1), (dict(caps_m=2048), 3), (dict(caps_z=1 << 21), None), (dict(caps_z=40000), None)):
+        rc, score, ncig, cigar, off, info = run_emu(emu, *args, **kw)
+        assert rc == 0 and info[2] == 1
+        assert np.array_equal(score, want[0]) and np.array_equal(cigar, want[1]), kw
+        if chunks:
+            assert info[0] == chunks
+        else:
+            assert info[0] > 3
+    # effective cells = the sum over rows of the window width
+    rc, *_, info = run_emu(emu, *args)
+    w = z["w"].astype(np.int64); q = z["len2"].astype(np.int64); t = z["len1"].astype(np.int64)
+    cells = sum(int(sum(min(i + wv + 1, ql) - max(i - wv, 0) for i in range(tl))) for ql, tl, wv in zip(q, t, w))
+    assert info[3] == cells * tile
+
+
+@pytest.mark.parametrize("rows", [16, 32])
+def test_emulated_kernel_matches_oracle_on_seeded_sweeps(emu, oracle, rows):
+    """Random pairs over three parameter sets: wide bands against short queries (row_slots' second branch), w = 0,
+    N on either side, length-1 sequences, bands wider than any sequence, free gap opens."""
+    rng = np.random.default_rng(0xB5B20406 + rows)
+    for params in (dict(), dict(o_del=3, e_del=2, o_ins=7, e_ins=3, match=3, mismatch=5, ambig=-2),
+                   dict(o_del=0, e_del=1, o_ins=0, e_ins=1, match=2, mismatch=1, ambig=0)):
+        P = make_params(**params)
+        Pd = dict(o_del=P.o_del, e_del=P.e_del, o_ins=P.o_ins, e_ins=P.e_ins, match=P.match, mismatch=P.mismatch, ambig=P.ambig)
+        qs, ts, ws = [], [], []
+        for k in range(500):
+            ql = int(rng.integers(1, 140)) if k % 5 else int(rng.integers(1, 9))
+            q = rng.integers(0, 5 if k % 3 == 0 else 4, ql).astype(np.uint8)
+            if k % 2:
+                t = q.copy()
+                for _ in range(int(rng.integers(0, 6))):
+                    pos = int(rng.integers(0, len(t) + 1)); u = rng.random()
+                    if u < 0.4 and len(t) > 1: t = np.delete(t, min(pos, len(t) - 1))
+                    elif u < 0.8: t = np.insert(t, pos, rng.integers(0, 4))
+                    else: t[min(pos, len(t) - 1)] = rng.integers(0, 5)
+            else:
+                t = rng.integers(0, 4, int(rng.integers(max(1, ql - 12), ql + 13))).astype(np.uint8)
+            d = abs(len(q) - len(t))
+            w = d + (0 if k % 7 == 0 else int(rng.integers(0, 12)) if k % 11 else int(rng.integers(100, 300)))
+            qs.append(q); ts.append(t.astype(np.uint8)); ws.append(w)
+        rc, score, ncig, cigar, off, info = run_emu(emu, Pd, [len(t) for t in ts], [len(q) for q in qs], np.concatenate(ts),
+                                                    np.concatenate(qs), ws, rows=rows)
+        assert rc == 0 and info[1] > 1 and info[4] == 0  # several launch classes; nothing left 16 bits
+        for k in range(len(qs)):
+            sc, cg = oracle.global_align(P, qs[k], ts[k], ws[k])
+            assert sc == score[k], (params, k)
+            assert np.array_equal(cg, cigar[off[k]: off[k + 1]]), (params, k)
+
+
+def test_emulated_long_alignments_need_wide_slots(emu, oracle):
+    """Values beyond 16 bits: the 16-bit slots are refused, the default choice runs 64-bit slots and is exact."""
+    rng = np.random.default_rng(0xB5B20407)
+    P = make_params(match=9, mismatch=9)
+    Pd = dict(o_del=P.o_del, e_del=P.e_del, o_ins=P.o_ins, e_ins=P.e_ins, match=9, mismatch=9, ambig=P.ambig)
+    q = rng.integers(0, 4, 4000).astype(np.uint8)
+    t = q.copy(); t[::97] = (t[::97] + 1) % 4; t = np.delete(t, [500, 501, 2000])
+    assert run_emu(emu, Pd, [len(t)], [len(q)], t, q, 10, rows=16)[0] == -1
+    rc, score, ncig, cigar, off, info = run_emu(emu, Pd, [len(t)], [len(q)], t, q, 10)
+    assert rc == 0 and info[2] == 0
+    sc, cg = oracle.global_align(P, q, t, 10)
+    assert sc == score[0] and sc > 32767 and np.array_equal(cg, cigar)
+
+
+def test_emulated_16_bit_slots_at_the_edge_of_their_domain(emu, oracle):
+    """rows16_ok's bound is what decides: the worst alignments it still admits (nothing matches, heavy penalties, the
+    longest lengths) stay inside 16 bits and exact; one base longer and the default choice leaves the 16-bit slots."""
+    rng = np.random.default_rng(0xB5B20408)
+    P = make_params(o_del=40, e_del=9, o_ins=35, e_ins=11, match=2, mismatch=30, ambig=-25)
+    Pd = dict(o_del=40, e_del=9, o_ins=35, e_ins=11, match=2, mismatch=30, ambig=-25)
+    # lo = 30 * (len + 1) + 3 * 49 + 11 * (w + 2) <= 32000
+    w = 20
+    n = (32000 - 3 * 49 - 11 * (w + 2)) // 30 - 1
+    for kind in range(3):
+        q = np.zeros(n, np.uint8) if kind < 2 else rng.integers(0, 4, n).astype(np.uint8)
+        t = np.ones(n - (w if kind == 1 else 0), np.uint8) if kind < 2 else (q[: n - 7] + 1) % 4
+        rc, score, ncig, cigar, off, info = run_emu(emu, Pd, [len(t)], [len(q)], t, q, w)
+        assert rc == 0 and info[2] == 1 and info[4] == 0
+        sc, cg = oracle.global_align(P, q, t, w)
+        assert sc == score[0] and np.array_equal(cg, cigar)
+    q = np.zeros(n + 2, np.uint8); t = np.ones(n + 2, np.uint8)
+    rc, score, ncig, cigar, off, info = run_emu(emu, Pd, [len(t)], [len(q)], t, q, w)
+    assert rc == 0 and info[2] == 0
+    sc, cg = oracle.global_align(P, q, t, w)
+    assert sc == score[0] and np.array_equal(cg, cigar)
+
+
+def test_emulated_domain_checks(emu):
+    """Scores beyond a signed byte and rows beyond shared memory are refused (the engine runs the first kernel then)."""
+    P = dict(o_del=6, e_del=1, o_ins=6, e_ins=1, match=1, mismatch=4, ambig=-1)
+    q = np.zeros(40, np.uint8)
+    assert run_emu(emu, dict(P, match=200), [40], [40], q, q, 3)[0] == -1
+    assert run_emu(emu, P, [40], [40], q, q, 3000)[0] == 0          # a band wider than the sequences costs no more slots than the sequences
+    q = np.zeros(3000, np.uint8)
+    assert run_emu(emu, P, [3000], [3000], q, q, 2900)[0] == -1
