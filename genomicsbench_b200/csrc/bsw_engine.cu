@@ -25,6 +25,8 @@
 #include "bsw_warp16.cuh"
 #include "bsw_prep.cuh"
 #include "bsw_global.cuh"
+#include "bsw_global2.cuh"
+#include "bsw_global_plan.h"
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -205,7 +207,7 @@ struct bsw_engine {
     int32_t w = 0;
     std::vector<std::pair<int, int>> staged_chunks;   // (device, slot) per chunk, batch order
     void* gbufs = nullptr;                // device buffers of bsw_global (GlobalBufs, bsw_global.inl)
-    bool global_attr_set = false;
+    bool global_attr_set = false, global2_attr_set = false;
     void* cbufs = nullptr;                // page-locked staging of bsw_extend_chains (ChainBufs, bsw_chain.inl)
     bool cells_counted = false;           // the last run summed its effective cells itself (latency route): no device counters to collect
     void* clanes = nullptr;               // child engines of bsw_extend_chains' lanes (ChainLanes, bsw_chain.inl)

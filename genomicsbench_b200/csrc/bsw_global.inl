@@ -1,8 +1,14 @@
 // bsw_global.inl -- host side of bsw_global (banded global alignment + CIGAR);
 // included by bsw_engine.cu inside extern "C".  Chunks of alignments go to the engine's first device:
 // gather the two byte strings of every alignment, one thread per alignment computes score and
-// operation list (bsw_global.cuh), a second kernel packs the lists, and they land in the caller's
-// buffer one after the other (cigar_off[]).
+// operation list, a second kernel packs the lists, and they land in the caller's buffer one after the
+// other (cigar_off[]).
+// Two forms.  run_global2 is the default: the chunk planner of bsw_global_plan.h on the thread pool (sizes,
+// descriptors + gather, parallel radix sort into work order, one launch per shared-memory class), the kernel of
+// bsw_global2.cuh, class launches side by side on the device's DP streams.  run_global1 is the first form
+// (bsw_global.cuh: 32-bit rows as a circular buffer or in HBM, byte directions); it takes what the second kernel's
+// domain excludes -- scores beyond a signed byte, rows beyond shared memory -- and BSW_GLOBAL_KERNEL=1 selects it
+// for A/B runs.
 namespace {
 
 // One chunk in flight: grow-only device buffers with page-locked twins for everything that crosses PCIe.  Two of
@@ -22,8 +28,11 @@ struct GlobalSlot {
     long long cells = 0;
 };
 
+constexpr size_t G2_SMEM_MAX = 200 * 1024;       // dynamic shared memory of a block of the second kernel
+
 struct GlobalBufs {
     GlobalSlot slot[2];
+    g2::ChunkPlan plan[2];
     std::vector<GlobalDesc> hd;
     std::vector<uint64_t> key, tmp;
 };
@@ -62,36 +71,13 @@ static void bsw_global_release(bsw_engine* eng)
     eng->gbufs = nullptr;
 }
 
-int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer, int64_t n,
-               const int32_t* w, int32_t* score, int32_t* n_cigar, uint32_t* cigar, int64_t cigar_cap,
-               int64_t* cigar_off)
+// first form: arguments validated by bsw_global, statistics zeroed, n > 0
+static int run_global1(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer, int64_t n,
+                       const int32_t* w, int32_t* score, int32_t* n_cigar, uint32_t* cigar, int64_t cigar_cap,
+                       int64_t* cigar_off)
 {
-    if (!eng) return BSW_ERR_PARAM;
-    eng->err.clear();
-    if (n < 0 || (n > 0 && (!pairs || !seq_ref || !seq_qer || !w || !score || !n_cigar || !cigar || !cigar_off)) || cigar_cap < 0) {
-        eng->err = "bsw_global: bad arguments";
-        return BSW_ERR_PARAM;
-    }
     bsw_stats& S = eng->stats;
-    memset(&S, 0, sizeof(S));
-    S.pairs = n;
-    if (cigar_off) cigar_off[0] = 0;
-    if (n == 0) return BSW_OK;
     const double t_begin = now_ms();
-    std::atomic<int> bad{0};
-    eng->pool->for_range(n, 16384, [&](int64_t b, int64_t e, int) {
-        for (int64_t i = b; i < e; ++i) {
-            const SeqPair& sp = pairs[i];
-            const long long dl = (long long)sp.len1 - (long long)sp.len2;
-            if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.idr < 0 || sp.idq < 0 || w[i] < 0 ||
-                w[i] > 32767 || (dl < 0 ? -dl : dl) > w[i]) bad.store(1, std::memory_order_relaxed);
-        }
-    });
-    if (bad.load()) {
-        eng->err = "bsw_global: need 1 <= len1, len2 <= 32767, offsets >= 0 and |len1 - len2| <= w <= 32767 "
-                   "(outside the band the reference's backtrack leaves its matrix, ksw.c:593-595)";
-        return BSW_ERR_DOMAIN;
-    }
     DevCtx& c = eng->devs[0];
     CUDA_TRY(cudaSetDevice(c.dev));
     if (!eng->gbufs) eng->gbufs = new GlobalBufs();
@@ -254,4 +240,208 @@ int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, co
     }
     S.ms_total = now_ms() - t_begin;
     return BSW_OK;
+}
+
+// second form (bsw_global2.cuh + bsw_global_plan.h): arguments validated by bsw_global, statistics zeroed, n > 0,
+// every alignment inside the second kernel's domain with the slot width r16 says
+static int run_global2(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer, int64_t n,
+                       const int32_t* w, int32_t* score, int32_t* n_cigar, uint32_t* cigar, int64_t cigar_cap,
+                       int64_t* cigar_off, bool r16)
+{
+    bsw_stats& S = eng->stats;
+    const double t_begin = now_ms();
+    DevCtx& c = eng->devs[0];
+    CUDA_TRY(cudaSetDevice(c.dev));
+    if (!eng->gbufs) eng->gbufs = new GlobalBufs();
+    GlobalBufs& B = *static_cast<GlobalBufs*>(eng->gbufs);
+    for (GlobalSlot& G : B.slot)
+        if (!G.st) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&G.st, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreate(&G.e0));
+            CUDA_TRY(cudaEventCreate(&G.e1));
+        }
+    g2::Params GP{};
+    GP.o_del = eng->p.o_del; GP.e_del = eng->p.e_del; GP.o_ins = eng->p.o_ins; GP.e_ins = eng->p.e_ins;
+    g2::fill_table(GP, eng->p.match, -eng->p.mismatch, eng->p.ambig);
+    if (!eng->global2_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(g2::bsw_global2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM_MAX));
+        CUDA_TRY(cudaFuncSetAttribute(g2::bsw_global2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM_MAX));
+        // resident blocks are bounded by shared memory alone (47 registers, 20 - 40 KB a block): all of it to shared memory
+        CUDA_TRY(cudaFuncSetAttribute(g2::bsw_global2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(g2::bsw_global2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        eng->global2_attr_set = true;
+    }
+    // alignments per chunk: enough of them that the device's threads stay occupied while the longest alignments of the chunk
+    // finish (they start first), few enough that the host plans chunk k + 1 while chunk k runs; BSW_GLOBAL_CHUNK overrides
+    g2::Caps caps;
+    caps.m = 1 << 17;
+    if (const char* ch = getenv("BSW_GLOBAL_CHUNK")) caps.m = std::min<int64_t>(1 << 18, std::max<int64_t>(1, atoll(ch)));
+    auto par = [&](int64_t cnt, int64_t grain, auto&& fn) { eng->pool->for_range(cnt, grain, fn); };
+    const int slices = eng->pool->size();
+
+    // host part of a chunk: plan (sizes, descriptors, gather into page-locked staging, work order, launches); then
+    // everything the device does with it, enqueued on the slot's stream (nothing here waits for the device)
+    auto launch = [&](GlobalSlot& G, g2::ChunkPlan& pl, int64_t first) -> int {
+        const double t_host0 = now_ms();
+        g2::plan_sizes(pairs, w, first, n, caps, par, pl);
+        const int64_t m = pl.m;
+        G.first = first; G.m = m; G.cap_words = pl.cig_words; G.cells = pl.cells;
+        if (int rc = ensure(eng, G.q, (size_t)pl.q_bytes + 16, true)) return rc;      // pinned staging twins: the copies run at link speed
+        if (int rc = ensure(eng, G.r, (size_t)pl.r_bytes + 16, true)) return rc;
+        if (int rc = ensure(eng, G.desc, (size_t)m, true)) return rc;
+        if (int rc = ensure(eng, G.z, (size_t)pl.z_bytes + 16)) return rc;
+        if (int rc = ensure(eng, G.cig, (size_t)pl.cig_words + 16)) return rc;
+        if (int rc = ensure(eng, G.packed, (size_t)pl.cig_words + 16, true)) return rc;
+        if (int rc = ensure(eng, G.score, (size_t)m, true)) return rc;
+        if (int rc = ensure(eng, G.ncig, (size_t)m, true)) return rc;
+        if (int rc = ensure(eng, G.off, (size_t)m + 1, true)) return rc;
+        g2::plan_fill(pairs, w, seq_ref, seq_qer, slices, par, pl, G.desc.h, G.q.h, G.r.h);
+        cudaStream_t st = G.st;
+        const int threads = (int)m;
+        CUDA_TRY(cudaMemcpyAsync(G.desc.d, G.desc.h, sizeof(GlobalDesc) * (size_t)m, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(G.q.d, G.q.h, (size_t)pl.q_bytes + 8, cudaMemcpyHostToDevice, st));     // (+ 8: the last query's padding)
+        CUDA_TRY(cudaMemcpyAsync(G.r.d, G.r.h, (size_t)pl.r_bytes + 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(G.e0, st));
+        // one launch per class, largest rows first; several classes run side by side on the device's DP streams
+        const int nl = (int)pl.launches.size();
+        const int used = nl > 1 ? std::min(nl, NSTREAMS) : 0;
+        for (int k = 0; k < used; ++k) CUDA_TRY(cudaStreamWaitEvent(c.cs[k], G.e0, 0));
+        for (int k = 0; k < nl; ++k) {
+            const g2::Launch& L = pl.launches[(size_t)k];
+            cudaStream_t ks = used ? c.cs[k % NSTREAMS] : st;
+            const int gblocks = (L.count + g2::BLOCK - 1) / g2::BLOCK;
+            const size_t smem = g2::smem_bytes(r16, L.slots, L.qwords);
+            if (r16)
+                g2::bsw_global2_kernel<true><<<gblocks, g2::BLOCK, smem, ks>>>(G.desc.d + L.first, L.count, G.q.d, G.r.d, L.slots, G.z.d,
+                                                                               G.cig.d, G.score.d, G.ncig.d, GP);
+            else
+                g2::bsw_global2_kernel<false><<<gblocks, g2::BLOCK, smem, ks>>>(G.desc.d + L.first, L.count, G.q.d, G.r.d, L.slots, G.z.d,
+                                                                                G.cig.d, G.score.d, G.ncig.d, GP);
+        }
+        CUDA_TRY(cudaGetLastError());
+        for (int k = 0; k < used; ++k) {
+            CUDA_TRY(cudaEventRecord(c.ev_join[k], c.cs[k]));
+            CUDA_TRY(cudaStreamWaitEvent(st, c.ev_join[k], 0));
+        }
+        CUDA_TRY(cudaEventRecord(G.e1, st));
+        bsw_cigar_offsets<<<1, 1024, 0, st>>>(G.ncig.d, threads, G.off.d);
+        bsw_cigar_compact<<<(threads + 127) / 128, 128, 0, st>>>(G.desc.d, threads, G.cig.d, G.ncig.d, G.off.d, G.packed.d);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(G.score.h, G.score.d, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(G.ncig.h, G.ncig.d, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(G.off.h, G.off.d, sizeof(long long) * ((size_t)m + 1), cudaMemcpyDeviceToHost, st));
+        S.kernel_launches += nl + 2;
+        S.h2d_bytes += (int64_t)(sizeof(GlobalDesc) * (size_t)m + (size_t)pl.q_bytes + (size_t)pl.r_bytes);
+        S.cells_nominal += pl.cells_nominal;
+        S.ms_pack += now_ms() - t_host0;                 // host: plan, gather, work order, enqueue
+        return BSW_OK;
+    };
+    long long out_pos = 0;
+    // results of a chunk into the caller's arrays (behind those of the earlier chunks), the copies on the pool
+    auto finish = [&](GlobalSlot& G) -> int {
+        const double t_w0 = now_ms();
+        CUDA_TRY(cudaStreamSynchronize(G.st));
+        const double t_w1 = now_ms();
+        S.ms_d2h += t_w1 - t_w0;                         // host waiting for the device
+        const int64_t m = G.m, first = G.first;
+        const long long run = G.off.h[m];
+        if (out_pos + run > cigar_cap) {
+            eng->err = "bsw_global: cigar buffer too small (len1 + len2 entries per alignment always suffice)";
+            return BSW_ERR_PARAM;
+        }
+        if (run > 0) CUDA_TRY(cudaMemcpyAsync(G.packed.h, G.packed.d, sizeof(uint32_t) * (size_t)run, cudaMemcpyDeviceToHost, G.st));
+        const long long base = out_pos;
+        eng->pool->for_range(m, 16384, [&](int64_t b, int64_t e, int) {
+            memcpy(score + first + b, G.score.h + b, sizeof(int32_t) * (size_t)(e - b));
+            memcpy(n_cigar + first + b, G.ncig.h + b, sizeof(int32_t) * (size_t)(e - b));
+            for (int64_t k = b; k < e; ++k) cigar_off[first + k + 1] = base + G.off.h[k + 1];
+        });
+        CUDA_TRY(cudaStreamSynchronize(G.st));
+        if (run > 0)
+            eng->pool->for_range(run, 1 << 18, [&](int64_t b, int64_t e, int) {
+                memcpy(cigar + base + b, G.packed.h + b, sizeof(uint32_t) * (size_t)(e - b));
+            });
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, G.e0, G.e1) == cudaSuccess) S.ms_kernel += (double)ms;
+        S.cells_effective += G.cells;
+        S.d2h_bytes += (int64_t)(16 * m + 4 * run);
+        out_pos += run;
+        S.ms_scatter += now_ms() - t_w1;                 // host: results into the caller's arrays (incl. the wait for the packed lists)
+        return BSW_OK;
+    };
+    int64_t next = 0;
+    int cur = 0;
+    bool pending[2] = {false, false};
+    while (next < n) {
+        GlobalSlot& G = B.slot[cur];
+        if (pending[cur]) { if (int rc = finish(G)) { cudaDeviceSynchronize(); return rc; } pending[cur] = false; }
+        if (int rc = launch(G, B.plan[cur], next)) { cudaDeviceSynchronize(); return rc; }
+        pending[cur] = true;
+        next += G.m;
+        cur ^= 1;
+    }
+    // drain in submission order: the slot that was launched first is the one `cur` points at now
+    for (int k = 0; k < 2; ++k) {
+        GlobalSlot& G = B.slot[cur];
+        if (pending[cur]) { if (int rc = finish(G)) { cudaDeviceSynchronize(); return rc; } pending[cur] = false; }
+        cur ^= 1;
+    }
+    S.ms_total = now_ms() - t_begin;
+    return BSW_OK;
+}
+
+int bsw_global(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq_ref, const uint8_t* seq_qer, int64_t n,
+               const int32_t* w, int32_t* score, int32_t* n_cigar, uint32_t* cigar, int64_t cigar_cap,
+               int64_t* cigar_off)
+{
+    if (!eng) return BSW_ERR_PARAM;
+    eng->err.clear();
+    if (n < 0 || (n > 0 && (!pairs || !seq_ref || !seq_qer || !w || !score || !n_cigar || !cigar || !cigar_off)) || cigar_cap < 0) {
+        eng->err = "bsw_global: bad arguments";
+        return BSW_ERR_PARAM;
+    }
+    bsw_stats& S = eng->stats;
+    memset(&S, 0, sizeof(S));
+    S.pairs = n;
+    if (cigar_off) cigar_off[0] = 0;
+    if (n == 0) return BSW_OK;
+    // one pass: the domain of the entry point, and which kernel takes the call -- the second wants every score in a
+    // signed byte and every alignment's rows + query in shared memory; its 16-bit slots want every value in 16 bits
+    g2::Params GP{};
+    GP.o_del = eng->p.o_del; GP.e_del = eng->p.e_del; GP.o_ins = eng->p.o_ins; GP.e_ins = eng->p.e_ins;
+    const int match = eng->p.match, mm = -eng->p.mismatch, ambig = eng->p.ambig;
+    std::atomic<int> bad{0}, wide{0}, big16{0}, big32{0};
+    eng->pool->for_range(n, 16384, [&](int64_t b, int64_t e, int) {
+        int bad_l = 0, wide_l = 0, big16_l = 0, big32_l = 0;
+        for (int64_t i = b; i < e; ++i) {
+            const SeqPair& sp = pairs[i];
+            const long long dl = (long long)sp.len1 - (long long)sp.len2;
+            if (sp.len1 < 1 || sp.len1 > 32767 || sp.len2 < 1 || sp.len2 > 32767 || sp.idr < 0 || sp.idq < 0 || w[i] < 0 ||
+                w[i] > 32767 || (dl < 0 ? -dl : dl) > w[i]) { bad_l = 1; continue; }
+            const int wv = g2::eff_w(sp.len2, sp.len1, w[i]);
+            const int sc = g2::slots_class(g2::row_slots(sp.len2, wv)), qc = g2::qwords_class(g2::query_words(sp.len2));
+            if (!g2::rows16_ok(GP, match, mm, ambig, sp.len2, sp.len1, wv)) wide_l = 1;
+            if (g2::smem_bytes(true, sc, qc) > G2_SMEM_MAX) big16_l = 1;
+            if (g2::smem_bytes(false, sc, qc) > G2_SMEM_MAX) big32_l = 1;
+        }
+        if (bad_l) bad.store(1, std::memory_order_relaxed);
+        if (wide_l) wide.store(1, std::memory_order_relaxed);
+        if (big16_l) big16.store(1, std::memory_order_relaxed);
+        if (big32_l) big32.store(1, std::memory_order_relaxed);
+    });
+    if (bad.load()) {
+        eng->err = "bsw_global: need 1 <= len1, len2 <= 32767, offsets >= 0 and |len1 - len2| <= w <= 32767 "
+                   "(outside the band the reference's backtrack leaves its matrix, ksw.c:593-595)";
+        return BSW_ERR_DOMAIN;
+    }
+    // one slot width per call: 16 bits when every value fits them and every alignment fits shared memory at that
+    // width, else 64-bit slots if every alignment fits at that width, else the first kernel.
+    // BSW_GLOBAL_KERNEL (A/B runs): 1 = the first kernel, 2w = the second with 64-bit slots
+    const char* pick = getenv("BSW_GLOBAL_KERNEL");
+    const bool want1 = pick && pick[0] == '1', want_wide = pick && pick[0] == '2' && pick[1] == 'w';
+    const bool can16 = !wide.load() && !big16.load(), can32 = !big32.load();
+    const bool r16 = can16 && !want_wide;
+    const bool second = g2::scores_ok(match, mm, ambig) && !want1 && (r16 || can32);
+    if (second) return run_global2(eng, pairs, seq_ref, seq_qer, n, w, score, n_cigar, cigar, cigar_cap, cigar_off, r16);
+    return run_global1(eng, pairs, seq_ref, seq_qer, n, w, score, n_cigar, cigar, cigar_cap, cigar_off);
 }

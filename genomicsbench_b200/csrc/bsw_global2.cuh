@@ -255,22 +255,31 @@ BSW_HD void align_one(const Params& P, int qlen, int tlen, int w, const uint32_t
             int hh[8], ee[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) S::load(rp + (size_t)(c + 1 + k) * SW, hh[k], ee[k]);
-            uint32_t acc = 0;
+            // (two direction half-words per block: 16 dependent shifts each instead of 32 in a row)
+            uint32_t acc = 0, acc2 = 0;
             int oh, oe;
-#define BSW_G2_STEP(K, SWORD)                                                           \
-            BSW_G2_CELL(add_byte<(K) & 3>(SWORD, hh[K]), ee[K], oh, oe, acc)            \
+#define BSW_G2_STEP(K, SWORD, ACC)                                                      \
+            BSW_G2_CELL(add_byte<(K) & 3>(SWORD, hh[K]), ee[K], oh, oe, ACC)            \
             S::store(rp + (size_t)(c + (K)) * SW, oh, oe);
-            BSW_G2_STEP(0, s03) BSW_G2_STEP(1, s03) BSW_G2_STEP(2, s03) BSW_G2_STEP(3, s03)
-            BSW_G2_STEP(4, s47) BSW_G2_STEP(5, s47) BSW_G2_STEP(6, s47) BSW_G2_STEP(7, s47)
-#undef BSW_G2_STEP
-            zi[c >> 3] = acc;
+            BSW_G2_STEP(0, s03, acc) BSW_G2_STEP(1, s03, acc) BSW_G2_STEP(2, s03, acc) BSW_G2_STEP(3, s03, acc)
+            BSW_G2_STEP(4, s47, acc2) BSW_G2_STEP(5, s47, acc2) BSW_G2_STEP(6, s47, acc2) BSW_G2_STEP(7, s47, acc2)
+            zi[c >> 3] = prmt(acc2, acc, 0x5410u);                               // acc << 16 | acc2
         }
         if (c < ncell) {
             const uint32_t q8 = funnel_r(qlo, qw[QSTRIDE], qsh);                // (the word behind the query's last is padding)
             const uint32_t s03 = prmt(tlo, thi, q8), s47 = prmt(tlo, thi, q8 >> 16);
             uint32_t acc = 0;
             const int c0 = c;
-            for (int k = 0; c < ncell; ++c, ++k) {
+            int k = 0;
+            if (c + 4 <= ncell) {                                               // four cells at once, then at most three one by one
+                int hh[4], ee[4], oh, oe;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) S::load(rp + (size_t)(c + 1 + u) * SW, hh[u], ee[u]);
+                BSW_G2_STEP(0, s03, acc) BSW_G2_STEP(1, s03, acc) BSW_G2_STEP(2, s03, acc) BSW_G2_STEP(3, s03, acc)
+                c += 4; k = 4;
+            }
+#undef BSW_G2_STEP
+            for (; c < ncell; ++c, ++k) {
                 int hd, e, oh, oe;
                 S::load(rp + (size_t)(c + 1) * SW, hd, e);
                 const int s = (int)(int8_t)((k < 4 ? s03 : s47) >> (8 * (k & 3)) & 0xff);

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Throughput of bsw_global (banded global alignment + CIGAR) next to the reference's own
-ksw_global2 on one host thread.  Workload: the pairs of tests/golden/global/global_default.npz tiled T
+ksw_global2 on one host thread (GLOBAL_BENCH_NO_CPU=1 skips that leg; BSW_GLOBAL_KERNEL=1 / 2w selects the first kernel /
+the second kernel's 64-bit slots for A/B runs).  Workload: the pairs of tests/golden/global/global_default.npz tiled T
 times; results are checked against the tiled golden.  Usage: python scripts/global_bench.py [tiles=300] [reps=5]"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,8 +29,10 @@ line = {"metric": "global_alignments_per_sec", "alignments": int(len(big)), "sec
         "band_cells": int(st["cells_effective"]), "gcups_band": st["cells_effective"] / best / 1e9,
         "kernel_ms": st["ms_kernel"], "gcups_band_kernel_only": st["cells_effective"] / (st["ms_kernel"] * 1e-3) / 1e9,
         "host_ms": {"prepare_and_enqueue": st["ms_pack"], "wait_for_device": st["ms_d2h"], "results_out": st["ms_scatter"], "call_total": st["ms_total"]},
-        "cigar_ops": int(len(cigar)), "gpu_launches": int(st["kernel_launches"]), "buffers": "pageable numpy arrays"}
-if KswReference.available():
+        "cigar_ops": int(len(cigar)), "gpu_launches": int(st["kernel_launches"]), "buffers": "pageable numpy arrays",
+        "kernel": {"": "second (bsw_global2.cuh), 16-bit slots", "1": "first (bsw_global.cuh)", "2w": "second, 64-bit slots"}.get(
+            os.environ.get("BSW_GLOBAL_KERNEL", ""), "?")}
+if KswReference.available() and not os.environ.get("GLOBAL_BENCH_NO_CPU"):
     K = KswReference(); P = make_params(**c["P"])
     t0 = time.perf_counter(); done = 0
     while time.perf_counter() - t0 < 3.0:

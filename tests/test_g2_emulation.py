@@ -72,7 +72,7 @@ def test_emulated_default_choice_and_chunk_cuts(emu):
     args = (c["P"], np.tile(z["len1"], tile), np.tile(z["len2"], tile), np.tile(z["target"], tile), np.tile(z["query"], tile),
             np.tile(z["w"], tile))
     want = (np.tile(z["score"], tile), np.tile(z["cigar"], tile))
-    for kw, chunks in ((dict(), 1), (dict(caps_m=2048), 3), (dict(caps_z=1 << 21), None), (dict(caps_z=40000), None)):
+    for kw, chunks in ((dict(), 1), (dict(caps_m=2048), 3), (dict(caps_m=3000), 2), (dict(caps_m=1), 4900), (dict(caps_z=1 << 21), None), (dict(caps_z=40000), None)):
         rc, score, ncig, cigar, off, info = run_emu(emu, *args, **kw)
         assert rc == 0 and info[2] == 1
         assert np.array_equal(score, want[0]) and np.array_equal(cigar, want[1]), kw

@@ -64,8 +64,15 @@ def _pairs_of(lib, c):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["", "2w", "1"])
 @pytest.mark.parametrize("case", GLOBAL_CASES)
-def test_bsw_global_matches_reference_golden(lib, case):
+def test_bsw_global_matches_reference_golden(lib, case, kernel, monkeypatch):
+    """kernel: "" = the default (second kernel, csrc/bsw_global2.cuh, 16-bit slots), "2w" = its 64-bit slots, "1" = the
+    first kernel (csrc/bsw_global.cuh), which stays the route for what the second one's domain excludes."""
+    if kernel:
+        monkeypatch.setenv("BSW_GLOBAL_KERNEL", kernel)
+    else:
+        monkeypatch.delenv("BSW_GLOBAL_KERNEL", raising=False)
     c = load_global_case(case); z = c["z"]
     pairs, ref, qer = _pairs_of(lib, c)
     with lib.Engine(**c["P"]) as eng:
@@ -75,6 +82,39 @@ def test_bsw_global_matches_reference_golden(lib, case):
     assert np.array_equal(np.diff(off), z["n_cigar"])
     assert np.array_equal(cigar, z["cigar"])
     assert st["kernel_launches"] >= 2 and st["cells_effective"] > 0
+    # which form ran: the second gathers every query 8-aligned and every target 4-aligned, the first packs them tight
+    l1, l2 = z["len1"].astype(np.int64), z["len2"].astype(np.int64)
+    tight = 40 * len(l1) + int(l1.sum() + l2.sum())            # 40 = sizeof(GlobalDesc)
+    padded = 40 * len(l1) + int(((l1 + 3) // 4 * 4).sum() + ((l2 + 7) // 8 * 8).sum())
+    assert st["h2d_bytes"] == (tight if kernel == "1" else padded)
+
+
+@pytest.mark.gpu
+def test_bsw_global_outside_the_second_kernels_domain(lib, oracle, monkeypatch):
+    """Rows beyond shared memory (a band as wide as long sequences) run the first kernel with its rows in HBM; values
+    beyond 16 bits run the second kernel with 64-bit slots."""
+    monkeypatch.delenv("BSW_GLOBAL_KERNEL", raising=False)
+    rng = np.random.default_rng(0xB5B20409)
+    for params, n, qlen, w in ((dict(), 3, 2000, 1500), (dict(match=9, mismatch=9), 3, 4000, 12)):
+        P = make_params(**params)
+        qs, ts = [], []
+        for _ in range(n):
+            q = rng.integers(0, 4, qlen).astype(np.uint8)
+            t = q.copy(); t[::17] = (t[::17] + 1) % 4; t = np.delete(t, [5, 40])
+            qs.append(q); ts.append(t)
+        pairs = np.zeros(n, dtype=lib.SEQPAIR_DTYPE)
+        pairs["len1"], pairs["len2"] = [len(t) for t in ts], [len(q) for q in qs]
+        pairs["idr"] = np.concatenate([[0], np.cumsum(pairs["len1"])[:-1]]); pairs["idq"] = np.concatenate([[0], np.cumsum(pairs["len2"])[:-1]])
+        pairs["h0"] = 1
+        with lib.Engine(**params) as eng:
+            score, cigar, off = eng.global_align(pairs, np.concatenate(ts), np.concatenate(qs), w)
+            st = eng.stats()
+        l1, l2 = pairs["len1"].astype(np.int64), pairs["len2"].astype(np.int64)
+        first_kernel = st["h2d_bytes"] == 40 * n + int(l1.sum() + l2.sum())
+        assert first_kernel == (w == 1500)
+        for k in range(n):
+            sc, cg = oracle.global_align(P, qs[k], ts[k], w)
+            assert sc == score[k] and np.array_equal(cg, cigar[off[k]: off[k + 1]])
 
 
 @pytest.mark.gpu
