@@ -25,10 +25,25 @@ for r in range(reps + 1):
     if r: best = min(best, dt)
     st = eng.stats()
 assert np.array_equal(score, np.tile(z["score"], tiles)) and np.array_equal(cigar, np.tile(z["cigar"], tiles))
+# the same call with caller-owned result arrays reused across calls, as a C caller would hold them (fresh numpy arrays
+# cost the first touch of every page inside the call and a copy of the operation list behind it)
+out = (np.zeros(len(big), np.int32), np.zeros(len(big), np.int32), np.zeros(len(cigar) + 16, np.uint32), np.zeros(len(big) + 1, np.int64))
+best_reused, st_reused = 1e9, st
+for r in range(reps + 1 if reps else 0):
+    t0 = time.perf_counter()
+    score2, cigar2, off2 = eng.global_align(big, ref, qer, wbig, out=out)
+    dt = time.perf_counter() - t0
+    if r and dt < best_reused: best_reused, st_reused = dt, eng.stats()
+if reps:
+    assert np.array_equal(score2, score) and np.array_equal(cigar2, cigar) and np.array_equal(off2, off)
 line = {"metric": "global_alignments_per_sec", "alignments": int(len(big)), "seconds": best, "value": len(big) / best,
         "band_cells": int(st["cells_effective"]), "gcups_band": st["cells_effective"] / best / 1e9,
         "kernel_ms": st["ms_kernel"], "gcups_band_kernel_only": st["cells_effective"] / (st["ms_kernel"] * 1e-3) / 1e9,
         "host_ms": {"prepare_and_enqueue": st["ms_pack"], "wait_for_device": st["ms_d2h"], "results_out": st["ms_scatter"], "call_total": st["ms_total"]},
+        "seconds_reused_result_arrays": best_reused if reps else None,
+        "value_reused_result_arrays": len(big) / best_reused if reps else None,
+        "host_ms_reused_result_arrays": {"prepare_and_enqueue": st_reused["ms_pack"], "wait_for_device": st_reused["ms_d2h"],
+                                         "results_out": st_reused["ms_scatter"], "call_total": st_reused["ms_total"], "kernel_ms": st_reused["ms_kernel"]},
         "cigar_ops": int(len(cigar)), "gpu_launches": int(st["kernel_launches"]), "buffers": "pageable numpy arrays",
         "kernel": {"": "second (bsw_global2.cuh), 16-bit slots", "1": "first (bsw_global.cuh)", "2w": "second, 64-bit slots"}.get(
             os.environ.get("BSW_GLOBAL_KERNEL", ""), "?")}

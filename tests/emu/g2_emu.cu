@@ -114,4 +114,19 @@ int g2_emu_global(const int* prm, const SeqPair* pairs, const uint8_t* seq_ref, 
     return 0;
 }
 
+// the planner's radix sort on n seeded keys with `slices` slices against std::stable_sort on the same bits; 0 = equal
+int g2_emu_sort_check(long long n, int slices, unsigned long long seed)
+{
+    std::vector<uint64_t> keys((size_t)n), tmp, ref;
+    std::vector<uint32_t> hist;
+    uint64_t x = seed | 1;
+    for (auto& k : keys) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; k = (x & ~0x3ffffull) | (uint64_t)((&k - keys.data()) & 0x3ffff); }
+    for (size_t k = 0; k < keys.size(); k += 3) keys[k] = (keys[k / 2] & ~0x3ffffull) | (keys[k] & 0x3ffff);      // many equal keys: stability shows
+    ref = keys;
+    std::stable_sort(ref.begin(), ref.end(), [](uint64_t a, uint64_t b) { return (a >> 18) < (b >> 18); });
+    SerialPar par;
+    g2::radix_sort(keys, tmp, hist, 18, 64, slices, par);
+    return keys == ref ? 0 : 1;
+}
+
 } // extern "C"

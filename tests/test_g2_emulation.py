@@ -166,3 +166,21 @@ def test_emulated_domain_checks(emu):
     assert run_emu(emu, P, [40], [40], q, q, 3000)[0] == 0          # a band wider than the sequences costs no more slots than the sequences
     q = np.zeros(3000, np.uint8)
     assert run_emu(emu, P, [3000], [3000], q, q, 2900)[0] == -1
+
+
+@pytest.mark.parametrize("n,slices", [(1, 4), (5000, 1), (70000, 3), (300000, 16), (262144, 7)])
+def test_planner_radix_sort_is_a_stable_sort(emu, n, slices):
+    """The work order's parallel LSD radix sort (slices counted and scattered side by side) = std::stable_sort on the key bits."""
+    emu.g2_emu_sort_check.restype = C.c_int
+    emu.g2_emu_sort_check.argtypes = [C.c_longlong, C.c_int, C.c_ulonglong]
+    assert emu.g2_emu_sort_check(n, slices, 0x9E3779B97F4A7C15 + n) == 0
+
+
+def test_emulated_large_chunk_goes_through_the_sliced_sort(emu):
+    """70 000 alignments in one chunk: the planner's sort runs with several slices, ranges of every pass are many."""
+    c = load_global_case("global_default"); z = c["z"]
+    tile = 100
+    rc, score, ncig, cigar, off, info = run_emu(emu, c["P"], np.tile(z["len1"], tile), np.tile(z["len2"], tile), np.tile(z["target"], tile),
+                                                np.tile(z["query"], tile), np.tile(z["w"], tile))
+    assert rc == 0 and info[0] == 1 and info[4] == 0
+    assert np.array_equal(score, np.tile(z["score"], tile)) and np.array_equal(cigar, np.tile(z["cigar"], tile))

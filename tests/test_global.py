@@ -155,6 +155,14 @@ def test_bsw_global_edges_and_errors(lib, oracle):
         big = np.tile(pairs, 300)                                                # 210 000 alignments: several chunks
         s3, c3, o3 = eng.global_align(big, ref, qer, np.tile(z["w"], 300))
         assert np.array_equal(s3, np.tile(z["score"], 300)) and np.array_equal(c3, np.tile(z["cigar"], 300))
+        # caller-owned result arrays, reused across calls; a cigar buffer one entry short is refused
+        out = (np.zeros(len(big), np.int32), np.zeros(len(big), np.int32), np.zeros(len(c3), np.uint32), np.zeros(len(big) + 1, np.int64))
+        for _ in range(2):
+            s4, c4, o4 = eng.global_align(big, ref, qer, np.tile(z["w"], 300), out=out)
+            assert np.array_equal(s4, s3) and np.array_equal(c4, c3) and np.array_equal(o4, o3)
+        with pytest.raises(lib.BswError) as ei:
+            eng.global_align(big, ref, qer, np.tile(z["w"], 300), out=(out[0], out[1], out[2][:-1], out[3]))
+        assert ei.value.code == -1
         bad = pairs[:4].copy(); bad["len1"][2] = bad["len2"][2] + 50
         with pytest.raises(lib.BswError) as ei:
             eng.global_align(bad, ref, qer, 10)
