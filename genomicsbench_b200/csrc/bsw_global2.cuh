@@ -21,9 +21,9 @@
 //    base selects an 8-byte table (scores against A C G T N as signed bytes, kernel parameter), the four query
 //    nibbles are the PRMT's selector.  H(i-1, j-1) + s is then one IDP.4A against a one-hot byte vector (FMA pipe:
 //    it widens the byte and adds).  Needs |score| <= 127 (host check).
-//  * Directions: four raw comparison bits per cell (M < E, max(M, E) < F, E extended, F extended), each the SIGN
+//  * Directions: four raw comparison bits per cell (M < H, E < H, E extended, F extended), each the SIGN
 //    of a difference, shifted into the block's direction word by one funnel shift (SHF.L.W) -- no predicate, no
-//    select; the differences run on the FMA pipe, maxima are VIMNMX / VIADDMNMX.  Eight cells per 32-bit store:
+//    select; the differences run on the FMA pipe, H = max(M, E, F) is one VIMNMX3, E and F one VIADDMNMX each.  Eight cells per 32-bit store:
 //    the direction matrix is half the first kernel's size.  The backtrack decodes the bits into ksw.c's
 //    which-state machine.
 //  * Backtrack: the operation being built stays in registers (the first kernel read-modify-wrote the list in
@@ -122,6 +122,15 @@ template <int K> BSW_HD int add_byte(uint32_t sw, int c)
     return c + (int)(int8_t)(sw >> (8 * K) & 0xff);
 #endif
 }
+// max(a, b, c): VIMNMX3
+BSW_HD int max3(int a, int b, int c)
+{
+#if defined(__CUDA_ARCH__)
+    return __vimax3_s32(a, b, c);
+#else
+    return std::max(a, std::max(b, c));
+#endif
+}
 // max(a + b, c): VIADDMNMX
 BSW_HD int addmax(int a, int b, int c)
 {
@@ -185,19 +194,21 @@ template <> struct Slots<false> {
 
 // One cell (ksw.c:544-566).  In: m = H(i-1, j-1) + s, E(i, j) in e_in, the running f and h1 = H(i, j-1).
 // Out: H(i, j) in h1 (the old h1 and E(i+1, j) go to the slot: out_h, out_e), f = F(i, j+1), and four bits
-// shifted into acc, each the sign of a difference (no difference can wrap: |values| <= 2^30 + lengths * scores):
-//   M < E              <=>  m - e < 0                 (ksw.c:551: d = m >= e ? 0 : 1)
-//   max(M, E) < F      <=>  max(m, e) - f < 0         (:553: d = h >= f ? d : 2)
+// shifted into acc, each the sign of a difference (no difference can wrap: |values| <= 2^30 + lengths * scores).
+// H = max(M, E, F) is one VIMNMX3; which of the three it came from (ksw.c:551-553: M on M >= E and M >= F, else E
+// on E >= F, else F) follows from two signs:
+//   M < H              <=>  m - H < 0      (not set: M)
+//   E < H              <=>  e - H < 0      (M < H and not set: E; both set: F)
 //   E extended         <=>  (m - oe_del) - E' < 0     (:558: e > t, E' = max(e - e_del, t))
 //   F extended         <=>  (m - oe_ins) - F' < 0     (:563)
 #define BSW_G2_CELL(m_in, e_in, out_h, out_e, acc)                                      \
     {                                                                                   \
         const int m_ = (m_in), e_ = (e_in);                                             \
-        const int h0_ = m_ > e_ ? m_ : e_;                                              \
-        acc = push_sign(acc, m_ - e_);                                                  \
-        acc = push_sign(acc, h0_ - f);                                                  \
+        const int hn_ = max3(m_, e_, f);                                                \
+        acc = push_sign(acc, m_ - hn_);                                                 \
+        acc = push_sign(acc, e_ - hn_);                                                 \
         out_h = h1;                                                                     \
-        h1 = h0_ > f ? h0_ : f;                                                         \
+        h1 = hn_;                                                                       \
         const int t1_ = m_ - oe_del, t2_ = m_ - oe_ins;                                 \
         out_e = addmax(e_, -P.e_del, t1_);                                              \
         f = addmax(f, -P.e_ins, t2_);                                                   \
@@ -294,7 +305,7 @@ BSW_HD void align_one(const Params& P, int qlen, int tlen, int w, const uint32_t
     score_out = last_h1;        // eh[qlen].h (ksw.c:590): the last row ends at qlen inside the supported domain (qlen <= tlen + w)
 
     // backtrack (ksw.c:591-603).  State `which`: 0 = H, 1 = E (deletion), 2 = F (insertion); a cell's four bits
-    // decode to the reference's next state: from H 2 if max(M, E) < F, else M < E; from E 1 if extended; from F 2 if extended.
+    // decode to the reference's next state: from H 0 unless M < H, then 1 unless E < H, else 2; from E 1 if extended; from F 2 if extended.
     int n_op = 0, which = 0, cur_op = -1, cur_len = 0;
     auto push = [&](int op, int len) {                                          // push_cigar, ksw.c:489-500
         if (op == cur_op) cur_len += len;
@@ -314,7 +325,7 @@ BSW_HD void align_one(const Params& P, int qlen, int tlen, int w, const uint32_t
                 const int c = k - (i > w ? i - w : 0);
                 if ((c >> 3) != wi) { reload = true; break; }
                 const uint32_t nib = cell_bits(b[t], c & 7);
-                which = which == 0 ? ((nib & 4u) ? 2 : (int)(nib >> 3)) : which == 1 ? (int)(nib >> 1 & 1u) : (int)(nib << 1 & 2u);
+                which = which == 0 ? ((nib & 8u) ? ((nib & 4u) ? 2 : 1) : 0) : which == 1 ? (int)(nib >> 1 & 1u) : (int)(nib << 1 & 2u);
                 if (which == 2) { push(1, 1); --k; if (k < 0) { reload = true; break; } }
                 else { if (which == 0) { push(0, 1); --k; } else push(2, 1); --i; break; }
             }
