@@ -304,7 +304,7 @@ static int run_global2(bsw_engine* eng, const SeqPair* pairs, const uint8_t* seq
         CUDA_TRY(cudaEventRecord(G.e0, st));
         // one launch per class, largest rows first; several classes run side by side on the device's DP streams
         const int nl = (int)pl.launches.size();
-        const int used = nl > 1 ? std::min(nl, NSTREAMS) : 0;
+        const int used = nl > 1 && !getenv("BSW_GLOBAL_SERIAL") ? std::min(nl, NSTREAMS) : 0;      // (BSW_GLOBAL_SERIAL: A/B, one stream)
         for (int k = 0; k < used; ++k) CUDA_TRY(cudaStreamWaitEvent(c.cs[k], G.e0, 0));
         for (int k = 0; k < nl; ++k) {
             const g2::Launch& L = pl.launches[(size_t)k];

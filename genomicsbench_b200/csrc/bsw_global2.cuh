@@ -27,7 +27,7 @@
 //    the direction matrix is half the first kernel's size.  The backtrack decodes the bits into ksw.c's
 //    which-state machine.
 //  * Backtrack: the operation being built stays in registers (the first kernel read-modify-wrote the list in
-//    HBM at every step), and the words of the next three rows are requested together with the current one --
+//    HBM at every step), and the words of the next seven rows are requested together with the current one --
 //    the walk moves up one row per step and its column drifts by at most one, so their address is known.
 //
 // align_one is __host__ __device__: tests/emu/g2_emu.cu runs the very same source on the CPU against the
@@ -62,11 +62,7 @@ inline void fill_table(Params& P, int match, int mismatch_neg, int ambig)
     const uint32_t m = (uint8_t)(int8_t)match, x = (uint8_t)(int8_t)mismatch_neg, a = (uint8_t)(int8_t)ambig;
     P.mm4 = x * 0x01010101u; P.amb4 = a * 0x01010101u; P.mx = m ^ x; P.amb1 = a;
 }
-BSW_HD void row_table(const Params& P, int tb, uint32_t& lo, uint32_t& hi)
-{
-    lo = tb < 4 ? P.mm4 ^ (P.mx << (8 * tb)) : P.amb4;
-    hi = P.amb1;
-}
+BSW_HD uint32_t row_table_lo(const Params& P, int tb) { return tb < 4 ? P.mm4 ^ (P.mx << (8 * tb)) : P.amb4; }      // (the high word is amb1)
 inline bool scores_ok(int match, int mismatch_neg, int ambig)
 {
     auto ok = [](int v) { return v >= -127 && v <= 127; };
@@ -162,13 +158,17 @@ BSW_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh)
 // ---- row slots --------------------------------------------------------------------------------------------
 // R16: word e << 16 | h;  else two words {h, e}.  `rows` points at the thread's slot 0; consecutive slots are
 // STRIDE words apart (the block's threads interleaved: bank = lane)
+// Accesses are volatile: they stay in source order, so a block's loads are issued a whole block ahead of their use
+// (the compiler otherwise sinks each one next to its consumer and the sweep waits for shared memory: 25 % of the
+// stall samples of the first build, profiles/r04d_ncu_global2_w20.txt).
 template <bool R16> struct Slots;
 template <> struct Slots<true> {
     static constexpr int WORDS = 1;
+    typedef uint32_t Raw;
+    static BSW_HD Raw load_raw(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
     // widening the two halves = two IDP.2A against unit byte vectors: FMA pipe, the ALU pipe is the kernel's bound
-    static BSW_HD void load(const uint32_t* p, int& h, int& e)
+    static BSW_HD void unpack(Raw c, int& h, int& e)
     {
-        const uint32_t c = *p;
 #if defined(__CUDA_ARCH__)
         h = __dp2a_lo((int)c, 0x0001, 0); e = __dp2a_lo((int)c, 0x0100, 0);
 #else
@@ -181,16 +181,35 @@ template <> struct Slots<true> {
         // (emulation) a value that does not fit: only H(i, beg - 1) = -2^30 of a row that starts inside the query may, its slot is never read
         if (e < -32768 || e > 32767 || ((h < -32768 || h > 32767) && h != G_MINUS_INF)) ++emu_wraps;
 #endif
-        *p = prmt((uint32_t)h, (uint32_t)e, 0x5410u);
+        *reinterpret_cast<volatile uint32_t*>(p) = prmt((uint32_t)h, (uint32_t)e, 0x5410u);
     }
     static BSW_HD int neg() { return NEG16; }
 };
 template <> struct Slots<false> {
     static constexpr int WORDS = 2;
-    static BSW_HD void load(const uint32_t* p, int& h, int& e) { const uint2 c = *reinterpret_cast<const uint2*>(p); h = (int)c.x; e = (int)c.y; }
-    static BSW_HD void store(uint32_t* p, int h, int e) { *reinterpret_cast<uint2*>(p) = make_uint2((uint32_t)h, (uint32_t)e); }
+    typedef uint2 Raw;
+    static BSW_HD Raw load_raw(const uint32_t* p)
+    {
+#if defined(__CUDA_ARCH__)
+        uint2 v;                                 // one LDS.64 that keeps its place (a volatile uint2 access would split in two)
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+        return v;
+#else
+        return *reinterpret_cast<const uint2*>(p);
+#endif
+    }
+    static BSW_HD void unpack(Raw c, int& h, int& e) { h = (int)c.x; e = (int)c.y; }
+    static BSW_HD void store(uint32_t* p, int h, int e)
+    {
+#if defined(__CUDA_ARCH__)
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(h), "r"(e) : "memory");
+#else
+        *reinterpret_cast<uint2*>(p) = make_uint2((uint32_t)h, (uint32_t)e);
+#endif
+    }
     static BSW_HD int neg() { return G_MINUS_INF; }
 };
+template <bool R16> BSW_HD void slot_load(const uint32_t* p, int& h, int& e) { Slots<R16>::unpack(Slots<R16>::load_raw(p), h, e); }
 
 // One cell (ksw.c:544-566).  In: m = H(i-1, j-1) + s, E(i, j) in e_in, the running f and h1 = H(i, j-1).
 // Out: H(i, j) in h1 (the old h1 and E(i+1, j) go to the slot: out_h, out_e), f = F(i, j+1), and four bits
@@ -220,7 +239,7 @@ template <> struct Slots<false> {
 // the first comparison in the nibble's top bit
 BSW_HD uint32_t cell_bits(uint32_t word, int c) { return word >> (28 - 4 * c) & 0xfu; }
 
-// q: the thread's query, 4 bits per base (codes 0 .. 4), eight bases per word, one word of padding behind;
+// q: the thread's query, 4 bits per base (codes 0 .. 4), eight bases per word, two words of padding behind;
 // consecutive words QSTRIDE words apart.  r: target bases, one per byte (global, 4-aligned, padded).
 // rows: slot 0 of the thread's row; z: the alignment's direction words; cg: its operation list (qlen + tlen words)
 template <bool R16, int STRIDE, int QSTRIDE>
@@ -237,35 +256,59 @@ BSW_HD void align_one(const Params& P, int qlen, int tlen, int w, const uint32_t
         S::store(p, 0, S::neg());
         for (int j = 1; j < qlen && j <= w; ++j) S::store(p + (size_t)j * SW, -(P.o_ins + P.e_ins * j), S::neg());   // (column min(w + 1, qlen) is written by row 0 itself)
     }
+    // byte 4 of every row's score table (N in the query): the same for all rows; kept in a register the optimiser cannot
+    // re-derive from the parameter bank (it re-loaded it with an LDC in every block, and the PRMT behind it waited)
+    uint32_t thi = P.amb1;
+#if defined(__CUDA_ARCH__)
+    asm volatile("mov.u32 %0, %0;" : "+r"(thi));
+#endif
     int last_h1 = 0;
-    uint32_t tw = 0;
+    // four target bases per load, requested four rows before their first use (r is 4-aligned, readable to its span)
+    uint32_t tw = 0, tw_next = *reinterpret_cast<const uint32_t*>(r);
     for (int i = 0; i < tlen; ++i) {                                            // ksw.c:527-589
         const int beg = i > w ? i - w : 0;
         const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
         const int ncell = end - beg;
         int f = G_MINUS_INF;
         int h1 = beg == 0 ? -(P.o_del + P.e_del * (i + 1)) : G_MINUS_INF;
-        if ((i & 3) == 0) tw = *reinterpret_cast<const uint32_t*>(r + i);       // four target bases per load
+        if ((i & 3) == 0) {
+            tw = tw_next;
+            if (i + 4 < tlen) tw_next = *reinterpret_cast<const uint32_t*>(r + i + 4);
+        }
         int tb = (int)(tw >> (8 * (i & 3)) & 0xff);
         tb = tb > 4 ? 4 : tb;
-        uint32_t tlo, thi;
-        row_table(P, tb, tlo, thi);
+        const uint32_t tlo = row_table_lo(P, tb);
         uint32_t* rp = rows + (size_t)(w > i ? w - i : 0) * SW;                // slot of the row's first cell
         uint32_t* zi = z + (size_t)i * pitch;
         // the row's query bases: eight per block, cut out of two consecutive words at the row's bit offset
+        // (two words are in registers and the third is requested while a block computes: the word behind the query's
+        // last two are padding)
         const uint32_t* qw = q + (size_t)(beg >> 3) * QSTRIDE;
         const uint32_t qsh = (uint32_t)(beg & 7) * 4u;
-        uint32_t qlo = *qw;
+        uint32_t qlo = qw[0], qhi = qw[QSTRIDE];
         int c = 0;
+        // a block's eight slots are loaded while the block before it computes (slots c + 9 .. c + 16 are not written before
+        // block c + 8 runs: block c stores slots c .. c + 7)
+        typename S::Raw cur[8];
+        if (ncell >= 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cur[k] = S::load_raw(rp + (size_t)(1 + k) * SW);
+        }
         for (; c + 8 <= ncell; c += 8) {
+            typename S::Raw nxt[8];
+            const bool more = c + 16 <= ncell;
+            if (more) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) nxt[k] = S::load_raw(rp + (size_t)(c + 9 + k) * SW);
+            }
+            const uint32_t qnext = *reinterpret_cast<const volatile uint32_t*>(qw + 2 * QSTRIDE);
             qw += QSTRIDE;
-            const uint32_t qhi = *qw;
             const uint32_t q8 = funnel_r(qlo, qhi, qsh);
-            qlo = qhi;
+            qlo = qhi; qhi = qnext;
             const uint32_t s03 = prmt(tlo, thi, q8), s47 = prmt(tlo, thi, q8 >> 16);   // the eight scores, one signed byte each
             int hh[8], ee[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) S::load(rp + (size_t)(c + 1 + k) * SW, hh[k], ee[k]);
+            for (int k = 0; k < 8; ++k) S::unpack(cur[k], hh[k], ee[k]);
             // (two direction half-words per block: 16 dependent shifts each instead of 32 in a row)
             uint32_t acc = 0, acc2 = 0;
             int oh, oe;
@@ -275,9 +318,13 @@ BSW_HD void align_one(const Params& P, int qlen, int tlen, int w, const uint32_t
             BSW_G2_STEP(0, s03, acc) BSW_G2_STEP(1, s03, acc) BSW_G2_STEP(2, s03, acc) BSW_G2_STEP(3, s03, acc)
             BSW_G2_STEP(4, s47, acc2) BSW_G2_STEP(5, s47, acc2) BSW_G2_STEP(6, s47, acc2) BSW_G2_STEP(7, s47, acc2)
             zi[c >> 3] = prmt(acc2, acc, 0x5410u);                               // acc << 16 | acc2
+            if (more) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+            }
         }
         if (c < ncell) {
-            const uint32_t q8 = funnel_r(qlo, qw[QSTRIDE], qsh);                // (the word behind the query's last is padding)
+            const uint32_t q8 = funnel_r(qlo, qhi, qsh);
             const uint32_t s03 = prmt(tlo, thi, q8), s47 = prmt(tlo, thi, q8 >> 16);
             uint32_t acc = 0;
             const int c0 = c;
@@ -285,14 +332,14 @@ BSW_HD void align_one(const Params& P, int qlen, int tlen, int w, const uint32_t
             if (c + 4 <= ncell) {                                               // four cells at once, then at most three one by one
                 int hh[4], ee[4], oh, oe;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) S::load(rp + (size_t)(c + 1 + u) * SW, hh[u], ee[u]);
+                for (int u = 0; u < 4; ++u) slot_load<R16>(rp + (size_t)(c + 1 + u) * SW, hh[u], ee[u]);
                 BSW_G2_STEP(0, s03, acc) BSW_G2_STEP(1, s03, acc) BSW_G2_STEP(2, s03, acc) BSW_G2_STEP(3, s03, acc)
                 c += 4; k = 4;
             }
 #undef BSW_G2_STEP
             for (; c < ncell; ++c, ++k) {
                 int hd, e, oh, oe;
-                S::load(rp + (size_t)(c + 1) * SW, hd, e);
+                slot_load<R16>(rp + (size_t)(c + 1) * SW, hd, e);
                 const int s = (int)(int8_t)((k < 4 ? s03 : s47) >> (8 * (k & 3)) & 0xff);
                 BSW_G2_CELL(hd + s, e, oh, oe, acc)
                 S::store(rp + (size_t)c * SW, oh, oe);
@@ -313,13 +360,13 @@ BSW_HD void align_one(const Params& P, int qlen, int tlen, int w, const uint32_t
     };
     int i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
     while (i >= 0 && k >= 0) {
-        const int wi = (k - (i > w ? i - w : 0)) >> 3;                          // the word the walk is in; rows i .. i-3 of it
-        uint32_t b[4];
+        const int wi = (k - (i > w ? i - w : 0)) >> 3;                          // the word the walk is in; rows i .. i-7 of it
+        uint32_t b[8];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) b[t] = z[(size_t)(i - t > 0 ? i - t : 0) * pitch + wi];
+        for (int t = 0; t < 8; ++t) b[t] = z[(size_t)(i - t > 0 ? i - t : 0) * pitch + wi];
         bool reload = false;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < 8; ++t) {
             if (reload) break;
             for (;;) {                                                          // steps inside row i (insertions stay in it)
                 const int c = k - (i > w ? i - w : 0);
@@ -359,7 +406,7 @@ BSW_HD uint32_t pack8(uint32_t b03, uint32_t b47)
 #endif
     return squeeze(b03) | squeeze(b47) << 16;
 }
-// the thread's packed query: words 0 .. ceil(qlen / 8) (the last one is the padding the partial block's funnel shift
+// the thread's packed query: words 0 .. ceil(qlen / 8) + 1 (the last two are the padding the funnel shifts' look-ahead
 // reads); src = the query's bytes (4-aligned, readable up to the next multiple of 8 -- the gather pads)
 template <int QSTRIDE>
 BSW_HD void pack_query(const uint8_t* src, int qlen, uint32_t* q)
@@ -368,11 +415,12 @@ BSW_HD void pack_query(const uint8_t* src, int qlen, uint32_t* q)
     const int nw = (qlen + 7) >> 3;
     for (int k = 0; k < nw; ++k) q[(size_t)k * QSTRIDE] = pack8(s[2 * k], s[2 * k + 1]);
     q[(size_t)nw * QSTRIDE] = 0;
+    q[(size_t)(nw + 1) * QSTRIDE] = 0;
 }
 
-// 32-bit words of a thread's packed query (with the padding word); bytes of dynamic shared memory of a launch
+// 32-bit words of a thread's packed query (with the two padding words); bytes of dynamic shared memory of a launch
 // whose threads need `slots` row slots and `qwords` query words each
-BSW_HD int query_words(int qlen) { return ((qlen + 7) >> 3) + 1; }
+BSW_HD int query_words(int qlen) { return ((qlen + 7) >> 3) + 2; }
 inline size_t smem_bytes(bool r16, int slots, int qwords)
 {
     return ((size_t)slots * (r16 ? 4 : 8) + (size_t)qwords * 4) * BLOCK;
