@@ -23,9 +23,11 @@
 //    it widens the byte and adds).  Needs |score| <= 127 (host check).
 //  * Directions: four raw comparison bits per cell (M < H, E < H, E extended, F extended), each the SIGN
 //    of a difference, shifted into the block's direction word by one funnel shift (SHF.L.W) -- no predicate, no
-//    select; the differences run on the FMA pipe, H = max(M, E, F) is one VIMNMX3, E and F one VIADDMNMX each.  Eight cells per 32-bit store:
-//    the direction matrix is half the first kernel's size.  The backtrack decodes the bits into ksw.c's
-//    which-state machine.
+//    select; the differences run on the FMA pipe, H = max(M, E, F) is one VIMNMX3, E and F one VIADDMNMX each.
+//    Eight cells per 32-bit store: the direction matrix is half the first kernel's size.  The backtrack decodes
+//    the bits into ksw.c's which-state machine.
+//  * Loads run ahead: a block's eight slots and the next query word are requested while the block before it
+//    computes, the target's bases four rows before their first use.
 //  * Backtrack: the operation being built stays in registers (the first kernel read-modify-wrote the list in
 //    HBM at every step), and the words of the next seven rows are requested together with the current one --
 //    the walk moves up one row per step and its column drifts by at most one, so their address is known.
