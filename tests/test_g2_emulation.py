@@ -184,3 +184,31 @@ def test_emulated_large_chunk_goes_through_the_sliced_sort(emu):
                                                 np.tile(z["query"], tile), np.tile(z["w"], tile))
     assert rc == 0 and info[0] == 1 and info[4] == 0
     assert np.array_equal(score, np.tile(z["score"], tile)) and np.array_equal(cigar, np.tile(z["cigar"], tile))
+
+
+def test_emulated_16_bit_domain_randomised(emu, oracle):
+    """Random scoring schemes with the longest sequences rows16_ok still admits for them (up to 2 500 bases), built to
+    push values down (nothing matches, N everywhere, one long gap) or up (everything matches): the 16-bit slots run,
+    nothing leaves 16 bits, results are the oracle's."""
+    rng = np.random.default_rng(0xB5B2040A)
+    for trial in range(60):
+        match = int(rng.integers(1, 25)); mismatch = int(rng.integers(1, 60)); ambig = -int(rng.integers(0, 50))
+        o_del, o_ins = int(rng.integers(0, 60)), int(rng.integers(0, 60))
+        e_del, e_ins = int(rng.integers(1, 16)), int(rng.integers(1, 16))
+        w = int(rng.integers(0, 40))
+        worst = max(mismatch, -ambig); gap = max(o_del + e_del, o_ins + e_ins); ext = max(e_del, e_ins)
+        n = min((32000 - 3 * gap - ext * (w + 2)) // worst, (32000 - gap) // match) - 1
+        n = int(min(n, 2500))
+        assert n > w + 2
+        P = make_params(o_del=o_del, e_del=e_del, o_ins=o_ins, e_ins=e_ins, match=match, mismatch=mismatch, ambig=ambig)
+        Pd = dict(o_del=o_del, e_del=e_del, o_ins=o_ins, e_ins=e_ins, match=match, mismatch=mismatch, ambig=ambig)
+        kind = trial % 5
+        if kind == 0:   q, t = np.zeros(n, np.uint8), np.ones(n, np.uint8)                    # nothing matches
+        elif kind == 1: q, t = np.full(n, 4, np.uint8), np.full(n - w, 4, np.uint8)           # N everywhere, the longest gap the band allows
+        elif kind == 2: q = rng.integers(0, 4, n).astype(np.uint8); t = q.copy()              # everything matches
+        elif kind == 3: q = np.zeros(n - w, np.uint8); t = np.ones(n, np.uint8)               # nothing matches + gap on the other side
+        else:           q = rng.integers(0, 5, n).astype(np.uint8); t = rng.integers(0, 5, n - int(rng.integers(0, w + 1))).astype(np.uint8)
+        rc, score, ncig, cigar, off, info = run_emu(emu, Pd, [len(t)], [len(q)], t, q, w)
+        assert rc == 0 and info[2] == 1 and info[4] == 0, (trial, Pd, n, w)
+        sc, cg = oracle.global_align(P, q, t, w)
+        assert sc == score[0] and np.array_equal(cg, cigar), (trial, Pd, n, w)
