@@ -38,6 +38,7 @@ struct ChunkPlan {
     // per range of PLAN_RANGE alignments: where its first alignment's bytes / words start
     std::vector<long long> rq, rr, rz, rc;
     std::vector<uint64_t> key, tmp;              // work order
+    std::vector<GlobalDesc> din;                 // descriptors in input order (permuted into work order by plan_fill)
     std::vector<uint32_t> hist;
 };
 
@@ -173,9 +174,8 @@ void plan_fill(const SeqPair* pairs, const int32_t* w, const uint8_t* seq_ref, c
     const int64_t m = pl.m, first = pl.first;
     const int64_t nr = (m + PLAN_RANGE - 1) / PLAN_RANGE;
     pl.key.resize((size_t)m);
-    static thread_local std::vector<GlobalDesc> t_desc;
-    t_desc.resize((size_t)m);                            // input-order descriptors; permuted below
-    GlobalDesc* const din = t_desc.data();
+    pl.din.resize((size_t)m);
+    GlobalDesc* const din = pl.din.data();
     par(nr, 1, [&](int64_t rb, int64_t re, int) {
         for (int64_t rg = rb; rg < re; ++rg) {
             long long q = pl.rq[(size_t)rg], r = pl.rr[(size_t)rg], z = pl.rz[(size_t)rg], c = pl.rc[(size_t)rg];
