@@ -15,6 +15,10 @@ sys.path.insert(0, str(ROOT))
 from oracle.pyoracle import KswReference, make_params   # noqa: E402
 
 OUT = Path(__file__).resolve().parent / "global"
+# cases only the CPU emulation of the second kernel runs (tests/test_g2_emulation.py): regimes beyond the four above --
+# bands far wider than the indels need (many launch classes, rows of up to 250 slots), heavy scores with a positive
+# score against N, free gap opens
+OUT_EMU = Path(__file__).resolve().parent / "global_emu"
 
 CASES = {
     "global_default": dict(seed=0xB5B20401, n=700, qlen=(20, 260), err=(0.0, 0.10), wextra=(0, 30), params={}),
@@ -22,6 +26,15 @@ CASES = {
                            params=dict(o_del=4, e_del=2, o_ins=5, e_ins=1, match=2, mismatch=3)),
     "global_tiny":    dict(seed=0xB5B20403, n=300, qlen=(1, 12), err=(0.0, 0.4), wextra=(0, 3), params={}),
     "global_long":    dict(seed=0xB5B20404, n=60, qlen=(600, 1500), err=(0.01, 0.06), wextra=(5, 60), params={}),
+}
+
+
+CASES_EMU = {
+    "wide_bands":   dict(seed=0xB5B20411, n=300, qlen=(30, 300), err=(0.0, 0.12), wextra=(0, 120), params={}),
+    "heavy_scores": dict(seed=0xB5B20412, n=300, qlen=(10, 400), err=(0.02, 0.2), wextra=(0, 20),
+                         params=dict(o_del=11, e_del=3, o_ins=9, e_ins=4, match=7, mismatch=13, ambig=2)),
+    "free_opens":   dict(seed=0xB5B20413, n=300, qlen=(5, 150), err=(0.05, 0.3), wextra=(0, 10),
+                         params=dict(o_del=0, e_del=2, o_ins=0, e_ins=1, match=1, mismatch=2, ambig=-1)),
 }
 
 
@@ -45,9 +58,10 @@ def make_pair(rng, qlen, err):
 
 
 def main():
-    OUT.mkdir(exist_ok=True)
+    OUT.mkdir(exist_ok=True); OUT_EMU.mkdir(exist_ok=True)
     K = KswReference()
-    for name, spec in CASES.items():
+    only_emu = "--emu-only" in sys.argv                  # leave the committed GPU cases as they are
+    for name, spec, out_dir in [(n, s, OUT) for n, s in CASES.items() if not only_emu] + [(n, s, OUT_EMU) for n, s in CASES_EMU.items()]:
         rng = np.random.default_rng(spec["seed"])
         P = make_params(**spec["params"])
         qs, ts, ws, scores, cig, cig_n = [], [], [], [], [], []
@@ -57,7 +71,7 @@ def main():
             w = max(w, 1)
             sc, cg = K.global_align(P, q, t, w)
             qs.append(q); ts.append(t); ws.append(w); scores.append(sc); cig.append(cg); cig_n.append(len(cg))
-        np.savez_compressed(OUT / f"{name}.npz", query=np.concatenate(qs), target=np.concatenate(ts),
+        np.savez_compressed(out_dir / f"{name}.npz", query=np.concatenate(qs), target=np.concatenate(ts),
                             len2=np.array([len(x) for x in qs], np.int32), len1=np.array([len(x) for x in ts], np.int32),
                             w=np.array(ws, np.int32), score=np.array(scores, np.int32), cigar=np.concatenate(cig),
                             n_cigar=np.array(cig_n, np.int32),

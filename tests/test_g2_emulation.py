@@ -10,7 +10,17 @@ import numpy as np
 import pytest
 
 from oracle.pyoracle import make_params
+from conftest import GOLDEN_DIR
 from test_global import GLOBAL_CASES, load_global_case
+
+# goldens of the reference's ksw_global2 that only this file runs (tests/golden/make_golden_global.py, CASES_EMU)
+EMU_CASES = sorted(p.stem for p in (GOLDEN_DIR / "global_emu").glob("*.npz"))
+
+
+def load_emu_case(name):
+    z = np.load(GOLDEN_DIR / "global_emu" / f"{name}.npz")
+    o_del, e_del, o_ins, e_ins, match, mismatch, ambig = (int(v) for v in z["params"])
+    return z, dict(o_del=o_del, e_del=e_del, o_ins=o_ins, e_ins=e_ins, match=match, mismatch=mismatch, ambig=ambig)
 
 SEQPAIR = np.dtype([("idr", "<i8"), ("idq", "<i8"), ("id", "<i8"), ("len1", "<i4"), ("len2", "<i4"), ("h0", "<i4"),
                     ("seqid", "<i4"), ("regid", "<i4"), ("score", "<i4"), ("tle", "<i4"), ("gtle", "<i4"), ("qle", "<i4"),
@@ -212,3 +222,21 @@ def test_emulated_16_bit_domain_randomised(emu, oracle):
         assert rc == 0 and info[2] == 1 and info[4] == 0, (trial, Pd, n, w)
         sc, cg = oracle.global_align(P, q, t, w)
         assert sc == score[0] and np.array_equal(cg, cigar), (trial, Pd, n, w)
+
+
+@pytest.mark.parametrize("rows", [16, 32])
+@pytest.mark.parametrize("case", EMU_CASES)
+def test_emulated_kernel_matches_more_reference_goldens(emu, oracle, case, rows):
+    """Bands far wider than needed (up to 250 slots, many launch classes), heavy scores with a positive score against N,
+    free gap opens: scores and CIGARs of the reference's own ksw_global2; the oracle is held to the same vectors."""
+    z, P = load_emu_case(case)
+    rc, score, ncig, cigar, off, info = run_emu(emu, P, z["len1"], z["len2"], z["target"], z["query"], z["w"], rows=rows)
+    assert rc == 0 and info[4] == 0
+    assert np.array_equal(score, z["score"]) and np.array_equal(ncig, z["n_cigar"]) and np.array_equal(cigar, z["cigar"])
+    if rows == 16:
+        Po = make_params(**P)
+        qoff = np.concatenate([[0], np.cumsum(z["len2"])]); toff = np.concatenate([[0], np.cumsum(z["len1"])])
+        coff = np.concatenate([[0], np.cumsum(z["n_cigar"])])
+        for k in range(0, len(z["w"]), 3):
+            sc, cg = oracle.global_align(Po, z["query"][qoff[k]: qoff[k + 1]], z["target"][toff[k]: toff[k + 1]], int(z["w"][k]))
+            assert sc == int(z["score"][k]) and np.array_equal(cg, z["cigar"][coff[k]: coff[k + 1]])
